@@ -1,0 +1,494 @@
+"""ctypes front end of the CPU oracle (oracle/libwx_oracle.so).  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
+this module; the product package never does (tests/test_host_logic.py checks that).
+
+Array convention ("Julia memory order"): a Julia array of size (d1, d2, ..., dk) -- first index
+fastest, batch last -- is held as a C-contiguous numpy array of shape (dk, ..., d2, d1).  So a batch of
+signals x (n, N) is numpy (N, n); a packet table (n, L+1, N) is numpy (N, L+1, n); a 2-D image batch
+(m, n, N) is numpy (N, n, m).  The bytes are identical to what the Julia reference holds.
+`jl(A)` converts a numpy array indexed like the Julia literal (A[i1, i2, ...]) into that layout.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def build(force: bool = False) -> str:
+    """Compile the C restatement (gcc) if needed; returns the library path."""
+    so = os.path.join(_HERE, "libwx_oracle.so")
+    srcs = [os.path.join(_HERE, f) for f in ("wx_oracle.c", "wx_oracle_impl.h", "Makefile")]
+    if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.run(["make", "-C", _HERE, "-s", "CC=gcc"] + (["-B"] if force else []), check=True)
+    return so
+
+
+def lib() -> C.CDLL:
+    global _LIB
+    if _LIB is None:
+        _LIB = C.CDLL(build())
+    return _LIB
+
+
+def jl(a) -> np.ndarray:
+    """numpy array indexed like a Julia literal -> Julia memory order (all axes reversed)."""
+    a = np.asarray(a)
+    return np.ascontiguousarray(a.transpose(tuple(range(a.ndim))[::-1]))
+
+
+unjl = jl   # the conversion is an involution
+
+_CT = {"l": C.c_long, "i": C.c_int, "d": C.c_double}
+
+
+def _sfx(dt) -> str:
+    dt = np.dtype(dt)
+    if dt == np.float64:
+        return "f64"
+    if dt == np.float32:
+        return "f32"
+    raise TypeError(f"unsupported element type {dt}")
+
+
+def _call(name: str, sig: str, *args, restype=None):
+    """sig: one char per argument. P = array pointer (any dtype, passed as void*), l = long, i = int,
+    d = double."""
+    f = getattr(lib(), name)
+    cargs = []
+    keep = []
+    for s, a in zip(sig, args):
+        if s == "P":
+            if a is None:
+                cargs.append(C.c_void_p(0))
+            else:
+                assert a.flags["C_CONTIGUOUS"], "oracle arrays must be C-contiguous"
+                keep.append(a)
+                cargs.append(C.c_void_p(a.ctypes.data))
+        else:
+            cargs.append(_CT[s](int(a) if s != "d" else float(a)))
+    f.restype = restype
+    return f(*cargs)
+
+
+def _taps(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _tree(t) -> np.ndarray:
+    return np.ascontiguousarray(np.asarray(t).astype(np.uint8))
+
+
+class OracleAssertion(AssertionError):
+    """the reference's @assert would have fired"""
+
+
+# ------------------------------------------------------------------ filters / index algebra
+def makereverseqmfpair(q):
+    q = _taps(q); g = np.empty_like(q); h = np.empty_like(q)
+    _call("wx_makereverseqmfpair", "PiPP", q, len(q), g, h)
+    return g, h
+
+
+def make_acreverseqmfpair(q):
+    q = _taps(q); P = np.empty(2 * len(q) - 1); Q = np.empty(2 * len(q) - 1)
+    _call("wx_make_acreverseqmfpair", "PiPP", q, len(q), P, Q)
+    return P, Q
+
+
+def maxtransformlevels(n: int) -> int:
+    return _call("wx_maxtransformlevels", "l", n, restype=C.c_int)
+
+
+def getdepth(i: int, kind: str) -> int:
+    return _call("wx_ilog2" if kind == "binary" else "wx_quaddepth", "l", i, restype=C.c_int)
+
+
+def treelength2(nr, nc) -> int:
+    return _call("wx_treelength2", "ll", nr, nc, restype=C.c_long)
+
+
+def maketree1(n, L, s="full"):
+    t = np.zeros(max(n - 1, 0), np.uint8)
+    _call("wx_maketree1", "Plii", t, n, L, int(s == "dwt"))
+    return t.astype(bool)
+
+
+def maketree2(nr, nc, L, s="full"):
+    t = np.zeros(treelength2(nr, nc), np.uint8)
+    _call("wx_maketree2", "Pllii", t, nr, nc, L, int(s == "dwt"))
+    return t.astype(bool)
+
+
+def getleaf(tree, kind):
+    t = _tree(tree)
+    ar = 2 if kind == "binary" else 4
+    leaf = np.zeros(ar * len(t) + 1, np.uint8)
+    _call("wx_getleaf_binary" if ar == 2 else "wx_getleaf_quad", "PlP", t, len(t), leaf)
+    return leaf.astype(bool)
+
+
+def isvalidtree(tree, arity=2) -> bool:
+    t = _tree(tree)
+    return bool(_call("wx_isvalidtree", "Pli", t, len(t), arity, restype=C.c_int))
+
+
+def quadrange(m, n, idx):
+    out = (C.c_long * 4)()
+    f = lib().wx_quadrange
+    f.restype = None
+    f(C.c_long(m), C.c_long(n), C.c_long(idx), C.byref(out, 0), C.byref(out, 8), C.byref(out, 16), C.byref(out, 24))
+    return tuple(out)   # r0, c0, nr, nc (0-based start)
+
+
+def main2depthshift(sm, L):
+    sd = np.zeros(L + 1, np.int64)
+    if _call("wx_main2depthshift", "Pli", sd, sm, L, restype=C.c_int) != 0:
+        raise OracleAssertion("sm < 1<<L")
+    return sd
+
+
+# ------------------------------------------------------------------ single steps (1-D)
+def dwt_step(v, h, g):
+    v = np.ascontiguousarray(v); n = v.shape[-1]
+    w1 = np.empty(n // 2, v.dtype); w2 = np.empty(n // 2, v.dtype)
+    _call(f"wxo_dwt_step_{_sfx(v.dtype)}", "PlPlPllPPi", w1, 1, w2, 1, v, 1, n, _taps(h), _taps(g), len(h))
+    return w1, w2
+
+
+def idwt_step(w1, w2, h, g):
+    w1 = np.ascontiguousarray(w1); w2 = np.ascontiguousarray(w2); n = 2 * len(w1)
+    v = np.empty(n, w1.dtype)
+    _call(f"wxo_idwt_step_{_sfx(v.dtype)}", "PlPlPllPPi", v, 1, w1, 1, w2, 1, n, _taps(h), _taps(g), len(h))
+    return v
+
+
+def sdwt_step(v, d, h, g):
+    v = np.ascontiguousarray(v); n = len(v)
+    w1 = np.empty_like(v); w2 = np.empty_like(v)
+    _call(f"wxo_sdwt_step_{_sfx(v.dtype)}", "PlPlPlliPPi", w1, 1, w2, 1, v, 1, n, d, _taps(h), _taps(g), len(h))
+    return w1, w2
+
+
+def isdwt_step(w1, w2, d, h, g, sv=None, sw=None, v0=None, add2out=False):
+    """average based when sv is None, else shift based (positions outside the coset keep v0 / zeros)."""
+    w1 = np.ascontiguousarray(w1); w2 = np.ascontiguousarray(w2); n = len(w1)
+    v = np.zeros(n, w1.dtype) if v0 is None else np.array(v0, dtype=w1.dtype)
+    if sv is None:
+        _call(f"wxo_isdwt_step_avg_{_sfx(v.dtype)}", "PlPlPlliPPi", v, 1, w1, 1, w2, 1, n, d, _taps(h), _taps(g), len(h))
+    else:
+        rc = _call(f"wxo_isdwt_step_shift_{_sfx(v.dtype)}", "PlPlPllillPPii", v, 1, w1, 1, w2, 1, n, d, sv, sw,
+                   _taps(h), _taps(g), len(h), int(add2out), restype=C.c_int)
+        if rc != 0:
+            raise OracleAssertion("0 <= sv < 1<<d and sv <= sw < 1<<(d+1)")
+    return v
+
+
+def acdwt_step(v, d, h, g):
+    v = np.ascontiguousarray(v); n = len(v)
+    w1 = np.empty_like(v); w2 = np.empty_like(v)
+    _call(f"wxo_acdwt_step_{_sfx(v.dtype)}", "PlPlPlliPPi", w1, 1, w2, 1, v, 1, n, d, _taps(h), _taps(g), len(h))
+    return w1, w2
+
+
+def iacdwt_step(w1, w2):
+    w1 = np.ascontiguousarray(w1); w2 = np.ascontiguousarray(w2)
+    v = np.empty_like(w1)
+    _call(f"wxo_iacdwt_step_{_sfx(v.dtype)}", "PlPlPll", v, 1, w1, 1, w2, 1, len(w1))
+    return v
+
+
+# ------------------------------------------------------------------ single steps (2-D); arrays are (cols, rows)
+def dwt_step2(v, h, g):
+    v = np.ascontiguousarray(v); nc2, nr2 = v.shape
+    nr, nc = nr2 // 2, nc2 // 2
+    ws = [np.empty((nc, nr), v.dtype) for _ in range(4)]
+    temp = np.empty_like(v)
+    _call(f"wxo_dwt_step2_{_sfx(v.dtype)}", "PPPPlPlPlllPPi", *ws, nr, v, nr2, temp, nr2, nr, nc, _taps(h), _taps(g), len(h))
+    return ws
+
+
+def idwt_step2(w1, w2, w3, w4, h, g):
+    ws = [np.ascontiguousarray(w) for w in (w1, w2, w3, w4)]
+    nc, nr = ws[0].shape
+    v = np.empty((2 * nc, 2 * nr), ws[0].dtype); temp = np.empty_like(v)
+    _call(f"wxo_idwt_step2_{_sfx(v.dtype)}", "PlPPPPlPlllPPi", v, 2 * nr, *ws, nr, temp, 2 * nr, nr, nc, _taps(h), _taps(g), len(h))
+    return v
+
+
+def _rstep2(name, v, d, h, g):
+    v = np.ascontiguousarray(v); nc, nr = v.shape
+    ws = [np.empty_like(v) for _ in range(4)]
+    temp = np.empty((2, nc, nr), v.dtype)
+    _call(f"wxo_{name}_{_sfx(v.dtype)}", "PPPPPPlliPPi", *ws, v, temp, nr, nc, d, _taps(h), _taps(g), len(h))
+    return ws
+
+
+def sdwt_step2(v, d, h, g):
+    return _rstep2("sdwt_step2", v, d, h, g)
+
+
+def acdwt_step2(v, d, h, g):
+    return _rstep2("acdwt_step2", v, d, h, g)
+
+
+def isdwt_step2(w1, w2, w3, w4, d, h, g, sv=None, sw=None):
+    ws = [np.ascontiguousarray(w) for w in (w1, w2, w3, w4)]
+    nc, nr = ws[0].shape
+    v = np.zeros_like(ws[0]); temp = np.zeros((2, nc, nr), v.dtype)
+    if sv is None:
+        _call(f"wxo_isdwt_step2_avg_{_sfx(v.dtype)}", "PPPPPPlliPPi", v, *ws, temp, nr, nc, d, _taps(h), _taps(g), len(h))
+    else:
+        rc = _call(f"wxo_isdwt_step2_shift_{_sfx(v.dtype)}", "PPPPPPllillPPi", v, *ws, temp, nr, nc, d, sv, sw,
+                   _taps(h), _taps(g), len(h), restype=C.c_int)
+        if rc != 0:
+            raise OracleAssertion("0 <= sv < 1<<d and sv <= sw < 1<<(d+1)")
+    return v
+
+
+def iacdwt_step2(w1, w2, w3, w4):
+    ws = [np.ascontiguousarray(w) for w in (w1, w2, w3, w4)]
+    nc, nr = ws[0].shape
+    v = np.empty_like(ws[0]); temp = np.empty((2, nc, nr), v.dtype)
+    _call(f"wxo_iacdwt_step2_{_sfx(v.dtype)}", "PPPPPPll", v, *ws, temp, nr, nc)
+    return v
+
+
+# ------------------------------------------------------------------ decimated trees, single signal
+def wpd(x, h, g, L):
+    """1-D: x (n,) -> (L+1, n).  2-D: x (n, m) -> (L+1, n, m)  [Julia (m,n) -> (m,n,L+1)]"""
+    x = np.ascontiguousarray(x)
+    y = np.empty((L + 1,) + x.shape, x.dtype)
+    if x.ndim == 1:
+        _call(f"wxo_wpd1_{_sfx(x.dtype)}", "PPliPPi", y, x, x.shape[0], L, _taps(h), _taps(g), len(h))
+    else:
+        n, m = x.shape
+        _call(f"wxo_wpd2_{_sfx(x.dtype)}", "PPlliPPi", y, x, m, n, L, _taps(h), _taps(g), len(h))
+    return y
+
+
+def _tree_tf(name1, name2, x, tree, h, g):
+    x = np.ascontiguousarray(x); t = _tree(tree); y = np.empty_like(x)
+    if x.ndim == 1:
+        _call(f"wxo_{name1}_{_sfx(x.dtype)}", "PPlPlPPi", y, x, x.shape[0], t, len(t), _taps(h), _taps(g), len(h))
+    else:
+        n, m = x.shape
+        _call(f"wxo_{name2}_{_sfx(x.dtype)}", "PPllPlPPi", y, x, m, n, t, len(t), _taps(h), _taps(g), len(h))
+    return y
+
+
+def wpt(x, tree, h, g):
+    return _tree_tf("wpt1", "wpt2", x, tree, h, g)
+
+
+def iwpt(xw, tree, h, g):
+    return _tree_tf("iwpt1", "iwpt2", xw, tree, h, g)
+
+
+def getbasiscoef(Xw, tree):
+    Xw = np.ascontiguousarray(Xw); t = _tree(tree)
+    out = np.empty(Xw.shape[1:], Xw.dtype)
+    if Xw.ndim == 2:
+        K, n = Xw.shape
+        rc = _call(f"wxo_getbasiscoef1_{_sfx(Xw.dtype)}", "PPliPl", out, Xw, n, K, t, len(t), restype=C.c_int)
+    else:
+        K, n, m = Xw.shape
+        rc = _call(f"wxo_getbasiscoef2_{_sfx(Xw.dtype)}", "PPlliPl", out, Xw, m, n, K, t, len(t), restype=C.c_int)
+    if rc != 0:
+        raise ValueError("Not enough decomposition levels in Xw.")
+    return out
+
+
+def iwpd(Xw, tree, h, g):
+    Xw = np.ascontiguousarray(Xw); t = _tree(tree)
+    out = np.empty(Xw.shape[1:], Xw.dtype)
+    if Xw.ndim == 2:
+        K, n = Xw.shape
+        rc = _call(f"wxo_iwpd1_{_sfx(Xw.dtype)}", "PPliPlPPi", out, Xw, n, K, t, len(t), _taps(h), _taps(g), len(h), restype=C.c_int)
+        if rc != 0:
+            raise ValueError("Not enough decomposition levels in Xw.")
+    else:
+        K, n, m = Xw.shape
+        _call(f"wxo_iwpd2_{_sfx(Xw.dtype)}", "PPlliPlPPi", out, Xw, m, n, K, t, len(t), _taps(h), _taps(g), len(h))
+    return out
+
+
+# ------------------------------------------------------------------ redundant trees, single signal
+def _rfwd(kind, ac, x, L, h, g):
+    x = np.ascontiguousarray(x)
+    two = x.ndim == 2
+    ncol = {"dwt": (3 * L + 1) if two else (L + 1),
+            "wpt": (4 ** L) if two else (1 << L),
+            "wpd": ((4 ** (L + 1) - 1) // 3) if two else ((1 << (L + 1)) - 1)}[kind]
+    xw = np.empty((ncol,) + x.shape, x.dtype)
+    if not two:
+        _call(f"wxo_r{kind}1_{_sfx(x.dtype)}", "iPPliPPi", int(ac), xw, x, x.shape[0], L, _taps(h), _taps(g), len(h))
+    else:
+        nc, nr = x.shape
+        _call(f"wxo_r{kind}2_{_sfx(x.dtype)}", "iPPlliPPi", int(ac), xw, x, nr, nc, L, _taps(h), _taps(g), len(h))
+    return xw
+
+
+def sdwt(x, L, h, g): return _rfwd("dwt", 0, x, L, h, g)
+def swpt(x, L, h, g): return _rfwd("wpt", 0, x, L, h, g)
+def swpd(x, L, h, g): return _rfwd("wpd", 0, x, L, h, g)
+def acdwt(x, L, P, Q): return _rfwd("dwt", 1, x, L, Q, P)     # (h,g) = (Q,P)  ACWT.jl:131
+def acwpt(x, L, P, Q): return _rfwd("wpt", 1, x, L, Q, P)
+def acwpd(x, L, P, Q): return _rfwd("wpd", 1, x, L, Q, P)
+
+
+def _mode(ac, sm):
+    return 2 if ac else (0 if sm is None else 1)
+
+
+def _rinv_levels(kind, ac, xw, L, h, g, sm):
+    xw = np.ascontiguousarray(xw)
+    two = xw.ndim == 3
+    x = np.zeros(xw.shape[1:], xw.dtype)
+    sd = None if (ac or sm is None) else main2depthshift(sm, L)
+    hh = _taps(h) if h is not None else np.zeros(2); gg = _taps(g) if g is not None else np.zeros(2)
+    if not two:
+        rc = _call(f"wxo_ir{kind}1_{_sfx(xw.dtype)}", "iPPliPPPi", _mode(ac, sm), x, xw, xw.shape[1], L, sd, hh, gg, len(hh), restype=C.c_int)
+    else:
+        _, nc, nr = xw.shape
+        rc = _call(f"wxo_ir{kind}2_{_sfx(xw.dtype)}", "iPPlliPPPi", _mode(ac, sm), x, xw, nr, nc, L, sd, hh, gg, len(hh), restype=C.c_int)
+    if rc != 0:
+        raise OracleAssertion("shift assertion")
+    return x
+
+
+def isdwt(xw, h, g, sm=None):
+    L = (xw.shape[0] - 1) if xw.ndim == 2 else (xw.shape[0] - 1) // 3
+    return _rinv_levels("dwt", 0, xw, L, h, g, sm)
+
+
+def iswpt(xw, h, g, sm=None):
+    L = getdepth(xw.shape[0], "binary") if xw.ndim == 2 else getdepth(3 * xw.shape[0] - 2, "quad") - 0
+    if xw.ndim == 3:
+        L = int(round(np.log(xw.shape[0]) / np.log(4)))
+    return _rinv_levels("wpt", 0, xw, L, h, g, sm)
+
+
+def iacdwt(xw):
+    L = (xw.shape[0] - 1) if xw.ndim == 2 else (xw.shape[0] - 1) // 3
+    return _rinv_levels("dwt", 1, xw, L, None, None, None)
+
+
+def iacwpt(xw):
+    L = getdepth(xw.shape[0], "binary") if xw.ndim == 2 else int(round(np.log(xw.shape[0]) / np.log(4)))
+    return _rinv_levels("wpt", 1, xw, L, None, None, None)
+
+
+def _rinv_tree(ac, xw, tree, h, g, sm):
+    xw = np.ascontiguousarray(xw); t = _tree(tree)
+    two = xw.ndim == 3
+    x = np.zeros(xw.shape[1:], xw.dtype)
+    L = getdepth(xw.shape[0], "quad" if two else "binary")
+    sd = None if (ac or sm is None) else main2depthshift(sm, L)
+    hh = _taps(h) if h is not None else np.zeros(2); gg = _taps(g) if g is not None else np.zeros(2)
+    if not two:
+        rc = _call(f"wxo_irwpd1_{_sfx(xw.dtype)}", "iPPllPlPPPi", _mode(ac, sm), x, xw, xw.shape[1], xw.shape[0], t, len(t), sd, hh, gg, len(hh), restype=C.c_int)
+    else:
+        _, nc, nr = xw.shape
+        rc = _call(f"wxo_irwpd2_{_sfx(xw.dtype)}", "iPPlllPlPPPi", _mode(ac, sm), x, xw, nr, nc, xw.shape[0], t, len(t), sd, hh, gg, len(hh), restype=C.c_int)
+    if rc != 0:
+        raise OracleAssertion("iswpd/iacwpd assertion")
+    return x
+
+
+def iswpd(xw, tree, h, g, sm=None): return _rinv_tree(0, xw, tree, h, g, sm)
+def iacwpd(xw, tree): return _rinv_tree(1, xw, tree, None, None, None)
+
+
+# ------------------------------------------------------------------ batch drivers
+def wpdall(x, q, L, nthreads=1):
+    """x (N, n) or (N, n, m); q = qmf taps (the pair is rebuilt per signal like DWT.jl:141)"""
+    x = np.ascontiguousarray(x); q = _taps(q)
+    N = x.shape[0]
+    y = np.empty((N, L + 1) + x.shape[1:], x.dtype)
+    if x.ndim == 2:
+        _call(f"wxo_wpdall1_{_sfx(x.dtype)}", "PPlilPii", y, x, x.shape[1], L, N, q, len(q), nthreads)
+    else:
+        _, n, m = x.shape
+        _call(f"wxo_wpdall2_{_sfx(x.dtype)}", "PPllilPii", y, x, m, n, L, N, q, len(q), nthreads)
+    return y
+
+
+def wpdall_into(y, x, q, L, nthreads=1):
+    """timing variant: no allocation inside (1-D only)"""
+    _call(f"wxo_wpdall1_{_sfx(x.dtype)}", "PPlilPii", y, x, x.shape[1], L, x.shape[0], _taps(q), len(q), nthreads)
+
+
+def iwptall(xw, q, tree, nthreads=1):
+    xw = np.ascontiguousarray(xw); q = _taps(q); t = _tree(tree)
+    y = np.empty_like(xw)
+    _call(f"wxo_iwptall1_{_sfx(xw.dtype)}", "PPllPlPii", y, xw, xw.shape[1], xw.shape[0], t, len(t), q, len(q), nthreads)
+    return y
+
+
+def rwpdall(ac, x, L, h, g, nthreads=1):
+    x = np.ascontiguousarray(x)
+    N, n = x.shape
+    xw = np.empty((N, (1 << (L + 1)) - 1, n), x.dtype)
+    _call(f"wxo_rwpdall1_{_sfx(x.dtype)}", "iPPlilPPii", int(ac), xw, x, n, L, N, _taps(h), _taps(g), len(h), nthreads)
+    return xw
+
+
+def max_threads() -> int:
+    return _call("wxo_max_threads", "", restype=C.c_int)
+
+
+# ------------------------------------------------------------------ best basis
+def tree_costs_jbb(X, redundant=False, cost="loglp", p=2.0):
+    """X (N, K, n) or (N, K, n, m) -> costs (T)"""
+    X = np.ascontiguousarray(X)
+    kind = 0 if cost == "loglp" else 1
+    if X.ndim == 3:
+        N, K, n = X.shape
+        nc = K if redundant else (1 << K) - 1
+        costs = np.empty(nc, X.dtype)
+        rc = _call(f"wxo_tree_costs_jbb1_{_sfx(X.dtype)}", "PPllliid", costs, X, n, K, N, int(redundant), kind, p, restype=C.c_int)
+    else:
+        N, K, n, m = X.shape
+        nc = K if redundant else (4 ** K - 1) // 3
+        costs = np.empty(nc, X.dtype)
+        rc = _call(f"wxo_tree_costs_jbb2_{_sfx(X.dtype)}", "PPlllliid", costs, X, m, n, K, N, int(redundant), kind, p, restype=C.c_int)
+    if rc != 0:
+        raise OracleAssertion("all(sigma .>= 0)")
+    return costs
+
+
+def tree_costs_lsdb(X, redundant=False):
+    X = np.ascontiguousarray(X)
+    if X.ndim == 3:
+        N, K, n = X.shape
+        costs = np.empty(K if redundant else (1 << K) - 1, X.dtype)
+        _call(f"wxo_tree_costs_lsdb1_{_sfx(X.dtype)}", "PPllli", costs, X, n, K, N, int(redundant))
+    else:
+        N, K, n, m = X.shape
+        costs = np.empty(K if redundant else (4 ** K - 1) // 3, X.dtype)
+        _call(f"wxo_tree_costs_lsdb2_{_sfx(X.dtype)}", "PPlllli", costs, X, m, n, K, N, int(redundant))
+    return costs
+
+
+def diffentropy(x):
+    x = np.ascontiguousarray(x)
+    return _call(f"wxo_diffentropy_{_sfx(x.dtype)}", "Pll", x, 1, len(x), restype=C.c_double)
+
+
+def tree_select(costs, n, m=None, minmax="min"):
+    costs = np.array(costs)     # copy: modified in place like the reference
+    mm = 0 if minmax == "min" else 1
+    if m is None:
+        tree = np.zeros(n - 1, np.uint8)
+        _call(f"wxo_tree_select1_{_sfx(costs.dtype)}", "PPlli", tree, costs, len(costs), n, mm)
+    else:
+        tree = np.zeros(treelength2(n, m), np.uint8)
+        _call(f"wxo_tree_select2_{_sfx(costs.dtype)}", "PPllli", tree, costs, len(costs), n, m, mm)
+    return tree.astype(bool)
