@@ -1,0 +1,173 @@
+/*
+ * wx_b200.h -- C ABI of libwx_b200.so, the B200 (sm_100a) implementation of the filter-bank hot path
+ * of WaveletsExt.jl v0.2.3 (batched WPD / iWPT, SWT and ACWT families, 2-D WPD, JBB/LSDB cost trees).
+ *
+ * The reference has no FFI of its own (pure Julia, multiple dispatch); each entry point below is the
+ * device counterpart of one reference function and cites it (paths relative to src/mod/ of the
+ * reference).  INTEGRATION.md shows the Julia `ccall` binding for each.
+ *
+ * Conventions
+ *  - plain C types only; every function returns 0 on success, a WX_E* code otherwise, and never throws.
+ *    wx_last_error() returns a thread-local message for the last failure.
+ *  - signal data pointers are DEVICE pointers on the current CUDA device unless the function name ends
+ *    in `_host`; taps, trees and cost vectors are HOST pointers.
+ *  - memory layout is the reference's (Julia column-major): first index fastest, batch last.
+ *    x(n,N)  y(n,L+1,N)  x2(m,n,N)  y2(m,n,L+1,N)  xw(n,nodes,N) ...
+ *  - `stream` is a cudaStream_t (0 = default stream).  Calls are asynchronous on that stream unless the
+ *    result is returned in host memory (costs, trees), in which case the call synchronises the stream.
+ *  - taps are double precision like the reference's (WT.makereverseqmfpair default eltype); for
+ *    Float32 signals they are rounded once to Float32 and products are accumulated with FP32 FMAs.
+ *  - there is no CPU fallback: without a CUDA device every compute entry point returns WX_ECUDA.
+ */
+#ifndef WX_B200_H
+#define WX_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WX_OK 0
+#define WX_EINVAL 1    /* argument the reference would reject with @assert / ArgumentError */
+#define WX_ECUDA 2     /* CUDA runtime failure */
+#define WX_EUNSUPPORTED 3
+#define WX_ENOMEM 4
+
+#define WX_MAX_TAPS 64 /* orthogonal filters up to 32 taps; autocorrelation filters (2F-1) up to 63 */
+
+/* modes of the redundant (stationary / autocorrelation) drivers */
+#define WX_MODE_DWT 0 /* sdwt / acdwt   : xw (n, L+1, N)        SWT.jl:109-131, ACWT.jl:109-131 */
+#define WX_MODE_WPT 1 /* swpt / acwpt   : xw (n, 2^L, N)        SWT.jl:439-471, ACWT.jl:427-460 */
+#define WX_MODE_WPD 2 /* swpd / acwpd   : xw (n, 2^(L+1)-1, N)  SWT.jl:840-868, ACWT.jl:733-759 */
+
+/* ---- runtime ------------------------------------------------------------------------------------ */
+int wx_version(void);
+const char *wx_last_error(void);
+int wx_device_count(int *count);
+int wx_set_device(int dev);
+int wx_device_info(int *sm_count, int *cc_major, int *cc_minor, size_t *smem_optin, size_t *total_mem);
+int wx_malloc(void **dptr, size_t bytes);
+int wx_free(void *dptr);
+int wx_malloc_host(void **hptr, size_t bytes);      /* pinned host memory */
+int wx_free_host(void *hptr);
+int wx_h2d(void *dst_dev, const void *src_host, size_t bytes, void *stream);
+int wx_d2h(void *dst_host, const void *src_dev, size_t bytes, void *stream);
+int wx_stream_sync(void *stream);
+int wx_device_sync(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+unsigned long long wx_launch_count(void);
+
+/* ---- single steps, 1-D -------------------------------------------------------------------------- */
+/* dwt_step!(w1,w2,v,h,g)      dwt/dwt_one_level.jl:79-107 ; v(n) -> w1,w2 (n/2) */
+int wx_dwt_step_f64(double *w1, double *w2, const double *v, long n, const double *h, const double *g, int F, void *stream);
+int wx_dwt_step_f32(float *w1, float *w2, const float *v, long n, const double *h, const double *g, int F, void *stream);
+/* idwt_step!(v,w1,w2,h,g)     dwt/dwt_one_level.jl:192-223 */
+int wx_idwt_step_f64(double *v, const double *w1, const double *w2, long n, const double *h, const double *g, int F, void *stream);
+int wx_idwt_step_f32(float *v, const float *w1, const float *w2, long n, const double *h, const double *g, int F, void *stream);
+/* sdwt_step!(w1,w2,v,d,h,g)   swt/swt_one_level.jl:99-127 */
+int wx_sdwt_step_f64(double *w1, double *w2, const double *v, long n, int d, const double *h, const double *g, int F, void *stream);
+int wx_sdwt_step_f32(float *w1, float *w2, const float *v, long n, int d, const double *h, const double *g, int F, void *stream);
+/* isdwt_step!(v,w1,w2,d,sv,sw,h,g; add2out)  swt/swt_one_level.jl:279-318 (shift based) */
+int wx_isdwt_step_shift_f64(double *v, const double *w1, const double *w2, long n, int d, long sv, long sw, const double *h, const double *g, int F, int add2out, void *stream);
+int wx_isdwt_step_shift_f32(float *v, const float *w1, const float *w2, long n, int d, long sv, long sw, const double *h, const double *g, int F, int add2out, void *stream);
+/* isdwt_step!(v,w1,w2,d,h,g)  swt/swt_one_level.jl:257-277 (average based) */
+int wx_isdwt_step_avg_f64(double *v, const double *w1, const double *w2, long n, int d, const double *h, const double *g, int F, void *stream);
+int wx_isdwt_step_avg_f32(float *v, const float *w1, const float *w2, long n, int d, const double *h, const double *g, int F, void *stream);
+/* acdwt_step!(w1,w2,v,d,h,g)  acwt/acwt_one_level.jl:101-128 ; w1 uses g, w2 uses h, Lf taps */
+int wx_acdwt_step_f64(double *w1, double *w2, const double *v, long n, int d, const double *h, const double *g, int Lf, void *stream);
+int wx_acdwt_step_f32(float *w1, float *w2, const float *v, long n, int d, const double *h, const double *g, int Lf, void *stream);
+/* iacdwt_step!(v,w1,w2)       acwt/acwt_one_level.jl:217-224 */
+int wx_iacdwt_step_f64(double *v, const double *w1, const double *w2, long n, void *stream);
+int wx_iacdwt_step_f32(float *v, const float *w1, const float *w2, long n, void *stream);
+
+/* ---- single steps, 2-D (matrices (nr x nc) column-major, contiguous) ------------------------------ */
+/* dwt_step!(w1..w4,v,h,g,temp)  dwt/dwt_one_level.jl:319-354 ; v (2nr x 2nc) -> four (nr x nc) */
+int wx_dwt_step2_f64(double *w1, double *w2, double *w3, double *w4, const double *v, long nr, long nc, const double *h, const double *g, int F, void *stream);
+int wx_dwt_step2_f32(float *w1, float *w2, float *w3, float *w4, const float *v, long nr, long nc, const double *h, const double *g, int F, void *stream);
+/* idwt_step!(v,w1..w4,h,g,temp) dwt/dwt_one_level.jl:401-436 */
+int wx_idwt_step2_f64(double *v, const double *w1, const double *w2, const double *w3, const double *w4, long nr, long nc, const double *h, const double *g, int F, void *stream);
+int wx_idwt_step2_f32(float *v, const float *w1, const float *w2, const float *w3, const float *w4, long nr, long nc, const double *h, const double *g, int F, void *stream);
+/* sdwt_step! / acdwt_step! 2-D  swt/swt_one_level.jl:334-370, acwt/acwt_one_level.jl:240-276 ; all (nr x nc); ac!=0 selects AC */
+int wx_rdwt_step2_f64(int ac, double *w1, double *w2, double *w3, double *w4, const double *v, long nr, long nc, int d, const double *h, const double *g, int F, void *stream);
+int wx_rdwt_step2_f32(int ac, float *w1, float *w2, float *w3, float *w4, const float *v, long nr, long nc, int d, const double *h, const double *g, int F, void *stream);
+/* isdwt_step! 2-D  swt/swt_one_level.jl:395-469 (sv<0: average based) ; iacdwt_step! 2-D acwt/acwt_one_level.jl:288-322 (mode 2) */
+int wx_irdwt_step2_f64(int mode, double *v, const double *w1, const double *w2, const double *w3, const double *w4, long nr, long nc, int d, long sv, long sw, const double *h, const double *g, int F, void *stream);
+int wx_irdwt_step2_f32(int mode, float *v, const float *w1, const float *w2, const float *w3, const float *w4, long nr, long nc, int d, long sv, long sw, const double *h, const double *g, int F, void *stream);
+
+/* ---- batched decimated trees -------------------------------------------------------------------- */
+/* wpdall / wpd!  dwt/dwt_all.jl:260-282, DWT.jl:131-161 ; x(n,N) -> y(n,L+1,N) */
+int wx_wpd1d_f64(double *y, const double *x, long n, int L, long N, const double *h, const double *g, int F, void *stream);
+int wx_wpd1d_f32(float *y, const float *x, long n, int L, long N, const double *h, const double *g, int F, void *stream);
+/* wpdall on images  DWT.jl:164-209 ; x(m,n,N) -> y(m,n,L+1,N) */
+int wx_wpd2d_f64(double *y, const double *x, long m, long n, int L, long N, const double *h, const double *g, int F, void *stream);
+int wx_wpd2d_f32(float *y, const float *x, long m, long n, int L, long N, const double *h, const double *g, int F, void *stream);
+/* wptall / iwptall by tree (1-D: Wavelets.jl wpt!/iwpt! call sites dwt/dwt_all.jl:162,221) ; x(n,N) -> y(n,N);
+ * tree: ntree bytes (0/1), heap order, host memory */
+int wx_wpt1d_f64(double *y, const double *x, long n, long N, const unsigned char *tree, long ntree, const double *h, const double *g, int F, void *stream);
+int wx_wpt1d_f32(float *y, const float *x, long n, long N, const unsigned char *tree, long ntree, const double *h, const double *g, int F, void *stream);
+int wx_iwpt1d_f64(double *y, const double *xw, long n, long N, const unsigned char *tree, long ntree, const double *h, const double *g, int F, void *stream);
+int wx_iwpt1d_f32(float *y, const float *xw, long n, long N, const unsigned char *tree, long ntree, const double *h, const double *g, int F, void *stream);
+/* 2-D wpt!/iwpt! by quad tree  DWT.jl:500-548, 662-710 ; x(m,n,N) -> y(m,n,N) */
+int wx_wpt2d_f64(double *y, const double *x, long m, long n, long N, const unsigned char *tree, long ntree, const double *h, const double *g, int F, void *stream);
+int wx_wpt2d_f32(float *y, const float *x, long m, long n, long N, const unsigned char *tree, long ntree, const double *h, const double *g, int F, void *stream);
+int wx_iwpt2d_f64(double *y, const double *xw, long m, long n, long N, const unsigned char *tree, long ntree, const double *h, const double *g, int F, void *stream);
+int wx_iwpt2d_f32(float *y, const float *xw, long m, long n, long N, const unsigned char *tree, long ntree, const double *h, const double *g, int F, void *stream);
+/* getbasiscoefall  Utils.jl:169-197 ; Xw(n,K,N) -> out(n,N) (m>0: Xw(m,n,K,N) -> out(m,n,N)) */
+int wx_gather_basis_f64(double *out, const double *Xw, long m, long n, int K, long N, const unsigned char *tree, long ntree, void *stream);
+int wx_gather_basis_f32(float *out, const float *Xw, long m, long n, int K, long N, const unsigned char *tree, long ntree, void *stream);
+/* iwpdall by tree  dwt/dwt_all.jl:324-342, DWT.jl:337-401 ; Xw(n,K,N) -> x(n,N)  (m>0: 2-D) */
+int wx_iwpd_f64(double *x, const double *Xw, long m, long n, int K, long N, const unsigned char *tree, long ntree, const double *h, const double *g, int F, void *stream);
+int wx_iwpd_f32(float *x, const float *Xw, long m, long n, int K, long N, const unsigned char *tree, long ntree, const double *h, const double *g, int F, void *stream);
+
+/* ---- batched redundant trees (stationary: ac=0, taps (h,g); autocorrelation: ac=1, taps (Q,P) as (h,g)) ---- */
+/* sdwtall/swptall/swpdall swt/swt_all.jl:33,156,279 ; acdwtall/acwptall/acwpdall acwt/acwt_all.jl:33,136,239.
+ * 1-D: x(n,N) (m = 0).  2-D: x(m,n,N) with m rows. */
+int wx_rwt_f64(int ac, int mode, double *xw, const double *x, long m, long n, int L, long N, const double *h, const double *g, int F, void *stream);
+int wx_rwt_f32(int ac, int mode, float *xw, const float *x, long m, long n, int L, long N, const double *h, const double *g, int F, void *stream);
+/* inverses swt/swt_all.jl:89-248,343-390 ; acwt/acwt_all.jl:86,189,300.  sm < 0: average based; sm >= 0: shift based.
+ * mode WPD takes a tree (ntree bytes); modes DWT/WPT take L. ncols = size of the node dimension of xw. */
+int wx_irwt_f64(int ac, int mode, double *x, const double *xw, long m, long n, long ncols, int L, long N, const unsigned char *tree, long ntree, long sm, const double *h, const double *g, int F, void *stream);
+int wx_irwt_f32(int ac, int mode, float *x, const float *xw, long m, long n, long ncols, int L, long N, const unsigned char *tree, long ntree, long sm, const double *h, const double *g, int F, void *stream);
+
+/* ---- best basis ----------------------------------------------------------------------------------- */
+/* tree_costs(X, ::JBB) step 1  bestbasis/bestbasis_tree.jl:153-154 : per-position sum and sum of squares over the
+ * LOCAL batch; X(sz,K,N_local) -> sum(sz*K), sumsq(sz*K) device buffers (always Float64, deterministic order).
+ * The caller all-reduces (sum) these two buffers across ranks. */
+int wx_jbb_moments_f64(double *sum, double *sumsq, const double *X, long szK, long Nlocal, void *stream);
+int wx_jbb_moments_f32(double *sum, double *sumsq, const float *X, long szK, long Nlocal, void *stream);
+/* tree_costs(X, ::JBB) step 2  bestbasis/bestbasis_tree.jl:155-207 + coefcost bestbasis/bestbasis_costs.jl:127-132 :
+ * sigma and per-node costs from the (all-reduced) moments.  m = 0: 1-D (n,K) ; m > 0: 2-D (m,n,K).
+ * cost_kind 0 = LoglpCost(p), 1 = NormCost(p).  costs: HOST, 2^K-1 (1-D) / (4^K-1)/3 (2-D) entries, or K if redundant.
+ * elt = 8 or 4 selects the element type the reference would have computed sigma in. returns WX_EINVAL if any
+ * variance is negative/NaN (reference: DomainError / @assert all(sigma .>= 0)). */
+int wx_jbb_costs(double *costs_host, const double *sum, const double *sumsq, long Ntotal, long m, long n, int K, int redundant, int cost_kind, double p, int elt, void *stream);
+/* tree_costs(X, ::LSDB)  bestbasis/bestbasis_tree.jl:104-147 + DifferentialEntropyCost bestbasis/bestbasis_costs.jl:135-164,
+ * three passes over the local batch with all-reducible per-position state in between:
+ *  pass1: count,sum,sumsq-about-shift,min,max per position  -> stats(5, szK) device
+ *  pass2: ASH bin counts on the grid derived from the reduced stats -> counts(npts, szK) device
+ *  pass3: sum_k log pdf(x_k) per position -> logsum(szK) device
+ *  costs: per-node costs from the reduced logsum. */
+int wx_lsdb_pass1_f64(double *stats, const double *X, long szK, long Nlocal, void *stream);
+int wx_lsdb_pass1_f32(double *stats, const float *X, long szK, long Nlocal, void *stream);
+int wx_lsdb_grid(long Ntotal, long *nbins, long *mbins, long *npts);
+int wx_lsdb_pass2_f64(double *counts, const double *stats, const double *X, long szK, long Nlocal, long Ntotal, void *stream);
+int wx_lsdb_pass2_f32(double *counts, const double *stats, const float *X, long szK, long Nlocal, long Ntotal, void *stream);
+int wx_lsdb_pass3_f64(double *logsum, const double *counts, const double *stats, const double *X, long szK, long Nlocal, long Ntotal, void *stream);
+int wx_lsdb_pass3_f32(double *logsum, const double *counts, const double *stats, const float *X, long szK, long Nlocal, long Ntotal, void *stream);
+int wx_lsdb_costs(double *costs_host, const double *logsum, long Ntotal, long m, long n, int K, int redundant, void *stream);
+/* bestbasis_treeselection  BestBasis.jl:59-110 (host, O(n)); costs are modified in place like the reference.
+ * m = 0: binary tree with n-1 entries; m > 0: quad tree. minmax 0 = :min, 1 = :max */
+int wx_tree_select(unsigned char *tree_out, double *costs_host, long ncosts, long m, long n, int minmax);
+
+/* ---- host-buffer entry points (the call a drop-in user makes with host arrays) ----------------------- */
+/* wpdall with x and y in HOST memory: chunks the batch, overlaps H2D / kernel / D2H on internal streams.
+ * Synchronous.  chunk = signals per chunk (0 = auto). */
+int wx_wpdall_host_f64(double *y_host, const double *x_host, long n, int L, long N, const double *h, const double *g, int F, long chunk);
+int wx_wpdall_host_f32(float *y_host, const float *x_host, long n, int L, long N, const double *h, const double *g, int F, long chunk);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WX_B200_H */

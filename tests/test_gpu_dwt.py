@@ -1,0 +1,230 @@
+"""GPU parity tests for the decimated family: every result goes through the C ABI of libwx_b200.so and is compared
+with the CPU oracle on the same seeded inputs.  Tolerances are the north-star ones: Float64 <= 1e-12, Float32 <= 1e-5,
+relative to the max-norm of each signal's reference output."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+TOL = {np.float64: 1e-12, np.float32: 1e-5}
+
+
+def relerr(got, ref, batch_axes=(0,)):
+    got = np.asarray(got, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    red = tuple(i for i in range(ref.ndim) if i not in batch_axes)
+    den = np.abs(ref).max(axis=red) if red else np.abs(ref)
+    den = np.where(den == 0, 1.0, den)
+    return float((np.abs(got - ref).max(axis=red) / den).max()) if red else float((np.abs(got - ref) / den).max())
+
+
+def dev(a, cuda):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(cuda)
+
+
+def pair(wx, wt):
+    g, h = wx.makereverseqmfpair(wt, True)
+    return h, g
+
+
+# ------------------------------------------------------------------ golden vectors through the GPU path
+def test_golden_steps_gpu(wx, cuda):
+    """test/transforms.jl:3-22 known answers, computed by the CUDA kernels"""
+    wt = wx.wavelet(wx.WT.db4)
+    h, g = pair(wx, wt)
+    x = dev(np.array([2, 3, -4, 5.0]), cuda)
+    w1, w2 = wx.dwt_step(x, h, g)
+    assert np.round(torch.cat([w1, w2]).cpu().numpy(), 3).tolist() == [-0.524, 4.767, 1.803, 5.268]
+    assert np.round(wx.idwt_step(w1, w2, h, g).cpu().numpy(), 3).tolist() == [2, 3, -4, 5]
+    X = np.array([[2, 3], [-4, 5.0]])
+    ws = wx.dwt_step(dev(X.T, cuda), h, g)          # Julia memory order = transpose
+    assert [round(float(w.item()), 3) for w in ws] == [3, 5, -2, 4]
+    back = wx.idwt_step(*ws, h, g).cpu().numpy().T
+    assert np.round(back, 3).tolist() == X.tolist()
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+@pytest.mark.parametrize("name", ["haar", "db2", "db4", "coif4", "sym8", "db10", "db3", "db7"])
+@pytest.mark.parametrize("n,L", [(4096, 12), (1024, 10), (1024, 4), (64, 6), (8, 3), (16, 0), (96, 5), (24, 3)])
+def test_wpdall_parity(wx, O, cuda, dt, name, n, L):
+    wt = wx.wavelet(name)
+    rng = np.random.default_rng(20240 + n + L)
+    N = 5 if n >= 1024 else 37
+    x = rng.standard_normal((N, n)).astype(dt)
+    y = wx.wpdall(dev(x, cuda), wt, L)
+    ref = O.wpdall(x, wt.taps, L)
+    assert y.shape == ref.shape
+    assert relerr(y.cpu().numpy(), ref) <= TOL[dt]
+
+
+def test_wpdall_edge_cases(wx, O, cuda):
+    wt = wx.wavelet("db4")
+    # empty batch
+    y = wx.wpdall(torch.empty((0, 64), dtype=torch.float64, device=cuda), wt, 3)
+    assert tuple(y.shape) == (0, 4, 64)
+    # too many levels -> AssertionError like the reference (dwt_all.jl:266)
+    with pytest.raises(AssertionError):
+        wx.wpdall(torch.zeros((2, 24), dtype=torch.float64, device=cuda), wt, 4)
+    with pytest.raises(AssertionError):
+        wx.wpdall(torch.zeros(24, dtype=torch.float64, device=cuda), wt)      # ndims(x) > 1
+    # host tensors are rejected (no CPU fallback)
+    with pytest.raises(RuntimeError):
+        wx.wpdall(torch.zeros((2, 64), dtype=torch.float64), wt, 2)
+    # batch of one == single-signal wpd (test/transforms.jl:300-305 "batch == cat of singles")
+    x = np.random.default_rng(1).standard_normal((3, 256))
+    ya = wx.wpdall(dev(x, cuda), wt, 8).cpu().numpy()
+    for k in range(3):
+        yk = wx.wpd(dev(x[k], cuda), wt).cpu().numpy()
+        assert np.array_equal(ya[k], yk)
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+def test_wpd_long_signal(wx, O, cuda, dt):
+    """signals longer than the shared-memory ping-pong: leading levels run through the per-level kernel"""
+    wt = wx.wavelet("db4")
+    n = 1 << 16
+    x = np.random.default_rng(7).standard_normal((3, n)).astype(dt)
+    y = wx.wpdall(dev(x, cuda), wt, 16)
+    ref = O.wpdall(x, wt.taps, 16, nthreads=4)
+    assert relerr(y.cpu().numpy(), ref) <= TOL[dt]
+
+
+def test_wpd_structural_identity(wx, cuda):
+    """test/transforms.jl:25-30: wpd(x) columns == wpt(x, L) for each L"""
+    wt = wx.wavelet("db4")
+    x = dev(np.random.default_rng(3).standard_normal(8), cuda)
+    y = wx.wpd(x, wt)
+    for L in (1, 2, 3):
+        assert torch.allclose(y[L], wx.wpt(x, wt, L), rtol=1e-12, atol=1e-13)
+    assert torch.equal(y[0], x)
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+@pytest.mark.parametrize("n", [8, 256, 4096])
+def test_wpt_iwpt_trees(wx, O, cuda, dt, n):
+    wt = wx.wavelet("db4")
+    h, g = pair(wx, wt)
+    rng = np.random.default_rng(n)
+    x = rng.standard_normal((6, n)).astype(dt)
+    L = wx.maxtransformlevels(n)
+    trees = [wx.maketree(n, L, "full"), wx.maketree(n, L, "dwt"), wx.maketree(n, min(2, L), "full")]
+    # a random valid tree
+    t = np.zeros(n - 1, bool)
+    for i in range(1, n):
+        if (i == 1 or t[i // 2 - 1]) and rng.random() < 0.7:
+            t[i - 1] = True
+    trees.append(t)
+    for tree in trees:
+        yw = wx.wptall(dev(x, cuda), wt, tree)
+        ref = np.stack([O.wpt(x[k], tree, h, g) for k in range(x.shape[0])])
+        assert relerr(yw.cpu().numpy(), ref) <= TOL[dt]
+        xr = wx.iwptall(yw, wt, tree)
+        refi = np.stack([O.iwpt(ref[k], tree, h, g) for k in range(x.shape[0])])
+        assert relerr(xr.cpu().numpy(), refi) <= TOL[dt] * 10
+        assert relerr(xr.cpu().numpy(), x) <= (1e-10 if dt == np.float64 else 2e-4)
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+def test_getbasiscoef_and_iwpd(wx, O, cuda, dt):
+    """test/utils.jl:6-25 index vectors + iwpd round trips (test/transforms.jl:31-33)"""
+    Xw = np.arange(1, 13, dtype=dt).reshape(3, 4)          # Julia reshape(1:12,4,3) in memory order
+    d = dev(Xw, cuda)
+    assert wx.getbasiscoef(d, wx.maketree(4, 2, "dwt")).cpu().numpy().tolist() == [9, 10, 7, 8]
+    assert wx.getbasiscoef(d, wx.maketree(4, 2, "full")).cpu().numpy().tolist() == [9, 10, 11, 12]
+    Xw2 = np.arange(1, 25, dtype=dt).reshape(2, 3, 4)      # reshape(1:24,4,3,2)
+    t1, t2 = wx.maketree(4, 2, "dwt"), wx.maketree(4, 2, "full")
+    assert wx.getbasiscoefall(dev(Xw2, cuda), t1).cpu().numpy().T.tolist() == [[9, 21], [10, 22], [7, 19], [8, 20]]
+    assert wx.getbasiscoefall(dev(Xw2, cuda), t2).cpu().numpy().T.tolist() == [[9, 21], [10, 22], [11, 23], [12, 24]]
+    assert wx.getbasiscoefall(dev(Xw2, cuda), np.stack([t1, t2], 1)).cpu().numpy().T.tolist() == [[9, 21], [10, 22], [7, 23], [8, 24]]
+    with pytest.raises(AssertionError):
+        wx.getbasiscoef(d, np.array([0, 1, 0], bool))
+    with pytest.raises(ValueError):                          # ArgumentError: not enough levels
+        wx.getbasiscoef(torch.zeros((2, 4), dtype=torch.float64, device=cuda), wx.maketree(4, 2, "dwt"))
+    wt = wx.wavelet("db4")
+    h, g = pair(wx, wt)
+    x = np.random.default_rng(5).standard_normal((4, 64)).astype(dt)
+    y = wx.wpdall(dev(x, cuda), wt)
+    for arg in (None, 2, wx.maketree(64, 6, "dwt")):
+        xr = wx.iwpdall(y, wt, arg)
+        assert relerr(xr.cpu().numpy(), x) <= (1e-10 if dt == np.float64 else 2e-4)
+    tree = wx.maketree(64, 6, "dwt")
+    ref = np.stack([O.iwpd(y[k].cpu().numpy(), tree, h, g) for k in range(4)])
+    assert relerr(wx.iwpdall(y, wt, tree).cpu().numpy(), ref) <= TOL[dt] * 10
+
+
+# ------------------------------------------------------------------ 2-D
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+@pytest.mark.parametrize("name", ["haar", "db4"])
+@pytest.mark.parametrize("m,n,L", [(8, 8, 3), (32, 16, 3), (64, 64, 5), (24, 40, 3)])
+def test_wpd2d_parity(wx, O, cuda, dt, name, m, n, L):
+    wt = wx.wavelet(name)
+    h, g = pair(wx, wt)
+    x = np.random.default_rng(m * n).standard_normal((3, n, m)).astype(dt)     # (N, cols, rows)
+    y = wx.wpdall(dev(x, cuda), wt, L)
+    ref = np.stack([O.wpd(x[k], h, g, L) for k in range(3)])
+    assert relerr(y.cpu().numpy(), ref) <= TOL[dt]
+    xr = wx.iwpdall(y, wt, L)
+    assert relerr(xr.cpu().numpy(), x) <= (1e-10 if dt == np.float64 else 2e-4)
+    tree = wx.maketree(m, n, L, "dwt")
+    refi = np.stack([O.iwpd(ref[k], tree, h, g) for k in range(3)])
+    assert relerr(wx.iwpdall(y, wt, tree).cpu().numpy(), refi) <= TOL[dt] * 10
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+def test_wpt2d_trees(wx, O, cuda, dt):
+    wt = wx.wavelet("db4")
+    h, g = pair(wx, wt)
+    m = n = 16
+    x = np.random.default_rng(11).standard_normal((2, n, m)).astype(dt)
+    rng = np.random.default_rng(12)
+    t = np.zeros(wx.gettreelength(m, n), bool)
+    for i in range(1, len(t) + 1):
+        if (i == 1 or t[(i + 2) // 4 - 1]) and rng.random() < 0.6:
+            t[i - 1] = True
+    for tree in (wx.maketree(m, n, 4, "full"), wx.maketree(m, n, 3, "dwt"), wx.maketree(m, n, 2, "full"), t):
+        yw = wx.wptall(dev(x, cuda), wt, tree)
+        ref = np.stack([O.wpt(x[k], tree, h, g) for k in range(2)])
+        assert relerr(yw.cpu().numpy(), ref) <= TOL[dt]
+        xr = wx.iwptall(yw, wt, tree)
+        assert relerr(xr.cpu().numpy(), np.stack([O.iwpt(ref[k], tree, h, g) for k in range(2)])) <= TOL[dt] * 10
+        assert relerr(xr.cpu().numpy(), x) <= (1e-10 if dt == np.float64 else 2e-4)
+    # single-image API + structural identity wpd[:,:,L] == wpt(x, L)   (test/transforms.jl:36-43)
+    xs = dev(x[0], cuda)
+    y = wx.wpd(xs, wt)
+    for L in (1, 2, 3):
+        assert relerr(y[L].cpu().numpy()[None], wx.wpt(xs, wt, L).cpu().numpy()[None]) <= TOL[dt]
+
+
+# ------------------------------------------------------------------ size-independent properties at full bench size
+def test_wpdall_fullsize_properties(wx, cuda):
+    """config 2 shape (4096 samples, L = 12) on a slab of 2048 signals: energy conservation per level (orthonormal
+    filter bank), linearity, and exact agreement with a small-batch run of the same signals."""
+    wt = wx.wavelet("db4")
+    n, L, N = 4096, 12, 2048
+    gen = torch.Generator(device=cuda).manual_seed(20242)
+    x = torch.randn((N, n), dtype=torch.float64, device=cuda, generator=gen)
+    y = wx.wpdall(x, wt, L)
+    e0 = (x * x).sum(dim=1)
+    for lvl in range(L + 1):
+        el = (y[:, lvl] * y[:, lvl]).sum(dim=1)
+        assert torch.allclose(el, e0, rtol=1e-11)
+    x2 = torch.randn((N, n), dtype=torch.float64, device=cuda, generator=gen)
+    y2 = wx.wpdall(x2, wt, L)
+    ys = wx.wpdall(2.0 * x - 0.5 * x2, wt, L)
+    assert (ys - (2.0 * y - 0.5 * y2)).abs().max().item() <= 1e-11 * y.abs().max().item()
+    sub = wx.wpdall(x[100:103].contiguous(), wt, L)
+    assert torch.equal(sub, y[100:103])
+    xr = wx.iwptall(y[:, L].contiguous(), wt, L)
+    assert (xr - x).abs().max().item() <= 1e-10 * x.abs().max().item()
+
+
+def test_wpdall_host_pipeline(wx, O, cuda):
+    """host-buffer entry point == device path, including ragged last chunk"""
+    wt = wx.wavelet("db4")
+    x = np.random.default_rng(9).standard_normal((1000, 512))
+    y = wx.host.wpdall_host(x, wt, 9, chunk=300)
+    yd = wx.wpdall(dev(x, cuda), wt, 9).cpu().numpy()
+    assert np.array_equal(y, yd)
+    ref = O.wpdall(x[:8], wt.taps, 9)
+    assert relerr(y[:8], ref) <= 1e-12

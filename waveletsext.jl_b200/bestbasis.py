@@ -1,0 +1,160 @@
+"""Joint best basis (JBB) and least statistically dependent basis (LSDB) on the B200: host mirror of BestBasis.jl,
+bestbasis/bestbasis_tree.jl and bestbasis/bestbasis_costs.jl (JBB / LSDB rows of the hot path).
+
+``tree_costs`` runs the per-position reductions on the local shard of the batch, all-reduces the small
+per-position state over ``torch.distributed`` when a process group is initialised (dist.py), and returns the
+per-node costs as a numpy vector; ``bestbasis_treeselection`` is the O(n) host pass of the reference.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import ctypes as C
+import numpy as np
+import torch
+
+from . import _dev as D
+from . import _lib
+from . import dist
+from .utils import gettreelength
+
+__all__ = ["LoglpCost", "NormCost", "DifferentialEntropyCost", "JBB", "LSDB", "tree_costs", "bestbasis_treeselection",
+           "bestbasistree", "delete_subtree_"]
+
+
+@dataclass(frozen=True)
+class LoglpCost:
+    """bestbasis/bestbasis_costs.jl:44-46"""
+    p: float = 2
+
+
+@dataclass(frozen=True)
+class NormCost:
+    """bestbasis/bestbasis_costs.jl:55-57"""
+    p: float = 1
+
+
+@dataclass(frozen=True)
+class DifferentialEntropyCost:
+    """bestbasis/bestbasis_costs.jl:66"""
+
+
+@dataclass(frozen=True)
+class JBB:
+    """bestbasis/bestbasis_tree.jl:43-46"""
+    cost: object = field(default_factory=LoglpCost)
+    redundant: bool = False
+
+
+@dataclass(frozen=True)
+class LSDB:
+    """bestbasis/bestbasis_tree.jl:25-28"""
+    cost: object = field(default_factory=DifferentialEntropyCost)
+    redundant: bool = False
+
+
+def _geom(X):
+    """X (N, K, n) or (N, K, n_cols, m_rows) -> (m, n, K, Nlocal, szK)"""
+    assert 3 <= X.dim() <= 4, "AssertionError: 3 <= ndims(X) <= 4"
+    N, K = X.shape[0], X.shape[1]
+    if X.dim() == 3:
+        m, n = 0, X.shape[2]
+        sz = n
+    else:
+        n, m = X.shape[2], X.shape[3]
+        sz = n * m
+    return m, n, K, N, sz * K
+
+
+def _ncosts(m, K, redundant):
+    if redundant:
+        return K
+    return (4 ** K - 1) // 3 if m > 0 else (1 << K) - 1
+
+
+def tree_costs(X, method, group=None):
+    """``tree_costs(X, method)`` bestbasis/bestbasis_tree.jl:104-207.  X is the LOCAL shard (N_local, K, ...) of the
+    packet table; with an initialised process group the costs are those of the concatenated batch."""
+    X = D.dev(X, "X")
+    m, n, K, Nloc, szK = _geom(X)
+    Ntot = dist.total_count(Nloc, X.device, group)
+    elt = X.element_size()
+    costs = np.empty(_ncosts(m, K, method.redundant), np.float64)
+    st = D.stream(X)
+    if isinstance(method, JBB):
+        if isinstance(method.cost, LoglpCost):
+            kind = 0
+        elif isinstance(method.cost, NormCost):
+            kind = 1
+        else:
+            raise TypeError("JBB cost must be LoglpCost or NormCost")
+        mom = torch.empty((2, szK), dtype=torch.float64, device=X.device)
+        D.call("jbb_moments", X, D.ptr(mom[0]), D.ptr(mom[1]), D.ptr(X), szK, Nloc, st)
+        dist.allreduce_sum(mom, group)           # the only collective of the JBB path (2*n*K doubles)
+        with torch.cuda.device(X.device):
+            _lib.call("wx_jbb_costs", costs.ctypes.data, D.ptr(mom[0]), D.ptr(mom[1]), Ntot, m, n, K, int(method.redundant), kind,
+                      C.c_double(float(method.cost.p)), elt, st)
+    elif isinstance(method, LSDB):
+        assert Ntot >= 2, "LSDB needs at least two signals"
+        stats = torch.empty((5, szK), dtype=torch.float64, device=X.device)
+        first = X[0].reshape(-1).to(torch.float64) if Nloc > 0 else torch.zeros(szK, dtype=torch.float64, device=X.device)
+        stats[0] = dist.broadcast_from_first(first, group)       # common shift: first signal of the global batch
+        D.call("lsdb_pass1", X, D.ptr(stats), D.ptr(X), szK, Nloc, st)
+        dist.allreduce_sum(stats[1:3], group)
+        dist.allreduce_min(stats[3], group)
+        dist.allreduce_max(stats[4], group)
+        nb, mb, npts = C.c_long(), C.c_long(), C.c_long()
+        _lib.call("wx_lsdb_grid", Ntot, C.byref(nb), C.byref(mb), C.byref(npts))
+        counts = torch.empty((npts.value, szK), dtype=torch.float64, device=X.device)
+        D.call("lsdb_pass2", X, D.ptr(counts), D.ptr(stats), D.ptr(X), szK, Nloc, Ntot, st)
+        dist.allreduce_sum(counts, group)
+        logsum = torch.empty(szK, dtype=torch.float64, device=X.device)
+        D.call("lsdb_pass3", X, D.ptr(logsum), D.ptr(counts), D.ptr(stats), D.ptr(X), szK, Nloc, Ntot, st)
+        dist.allreduce_sum(logsum, group)
+        with torch.cuda.device(X.device):
+            _lib.call("wx_lsdb_costs", costs.ctypes.data, D.ptr(logsum), Ntot, m, n, K, int(method.redundant), st)
+    else:
+        raise TypeError(f"unsupported best-basis method {type(method).__name__} on the B200 path (JBB and LSDB)")
+    return costs
+
+
+def bestbasis_treeselection(costs, n, m=None, type="min"):
+    """``bestbasis_treeselection(costs, n[, m], type)`` BestBasis.jl:59-110.  ``costs`` is modified in place like the
+    reference's.  Returns the tree as a boolean vector."""
+    if isinstance(m, str):
+        m, type = None, m
+    if type not in ("min", "max"):
+        raise ValueError(f"ArgumentError: Unsupported type {type}.")
+    costs = np.ascontiguousarray(costs, dtype=np.float64)
+    if m is None:
+        assert len(costs) <= gettreelength(2 * n), "AssertionError: k <= gettreelength(2*n)"
+        tree = np.zeros(max(n - 1, 0), np.uint8)
+        _lib.call("wx_tree_select", tree.ctypes.data, costs.ctypes.data, len(costs), 0, n, 0 if type == "min" else 1)
+    else:
+        assert len(costs) <= gettreelength(2 * n, 2 * m), "AssertionError: k <= gettreelength(2*n,2*m)"
+        tree = np.zeros(gettreelength(n, m), np.uint8)
+        _lib.call("wx_tree_select", tree.ctypes.data, costs.ctypes.data, len(costs), n, m, 0 if type == "min" else 1)
+    return tree.astype(bool)
+
+
+def delete_subtree_(bt, i, tree_type):
+    """``delete_subtree!(bt, i, tree_type)`` BestBasis.jl:128-140"""
+    assert 1 <= i <= len(bt), "AssertionError: 1 <= i <= length(bt)"
+    assert tree_type in ("binary", "quad"), "AssertionError: tree_type in [:binary, :quad]"
+    bt[i - 1] = False
+    kids = (2 * i, 2 * i + 1) if tree_type == "binary" else (4 * i - 2, 4 * i - 1, 4 * i, 4 * i + 1)
+    for c in kids:
+        if c <= len(bt) and bt[c - 1]:
+            delete_subtree_(bt, c, tree_type)
+    return bt
+
+
+def bestbasistree(X, method=None, group=None):
+    """``bestbasistree(X, method)`` BestBasis.jl:185-217 for JBB / LSDB.  X: local shard (N_local, K, ...)."""
+    method = JBB() if method is None else method
+    X = D.dev(X, "X")
+    costs = tree_costs(X, method, group)
+    if X.dim() == 3:
+        return bestbasis_treeselection(costs, X.shape[2])
+    # Julia sz = (rows, cols) = (shape[3], shape[2])
+    return bestbasis_treeselection(costs, X.shape[3], X.shape[2])

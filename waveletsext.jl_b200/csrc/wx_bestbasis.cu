@@ -1,0 +1,461 @@
+// wx_bestbasis.cu -- JBB / LSDB cost-tree accumulation and best-basis tree selection.
+//
+// Reference: tree_costs(X, ::JBB) bestbasis/bestbasis_tree.jl:150-207, tree_costs(X, ::LSDB) :104-147,
+//            coefcost bestbasis/bestbasis_costs.jl:127-164, bestbasis_treeselection BestBasis.jl:59-110.
+//
+// X is a packet table (sz, K, N) [sz = n or m*n].  Everything that depends on the whole batch is expressed as
+// per-position state that can be all-reduced across ranks (sum / min / max), so the batch can be sharded:
+//   JBB : sum, sumsq                                  -> sigma -> per-node cost
+//   LSDB: shifted sums, min, max -> ASH bin counts -> sum of log pdf -> per-node cost
+// All floating-point reductions use a fixed two-stage order (no float atomics; the only atomics add 1.0 to
+// bin counters, which is exact and order independent), so results are run-to-run and rank-count reproducible
+// for a given shard size.
+#include "wx_steps.cuh"
+#include <vector>
+#include <cmath>
+
+namespace {
+
+constexpr int kT = 256;
+static inline unsigned gridf(long total) { return (unsigned)((total + kT - 1) / kT); }
+
+// ---- stage 1: per-position partial reductions over a slice of the batch ----------------------------------
+// grid.x covers positions (kT per block), grid.y = ksplit.  Partial results go to part[ks][q][e].
+template <typename T, int MODE>   // MODE 0: sum,sumsq   MODE 1: shifted sum, shifted sumsq, min, max
+__global__ void __launch_bounds__(kT) moments_part_k(double *part, const T *X, const double *shift, long szK, long N, long kchunk)
+{
+    const long e = (long)blockIdx.x * kT + threadIdx.x;
+    if (e >= szK) return;
+    const long k0 = (long)blockIdx.y * kchunk;
+    long k1 = k0 + kchunk; if (k1 > N) k1 = N;
+    const double c = (MODE == 1) ? shift[e] : 0.0;
+    double s0 = 0, s1 = 0, s2 = 0, s3 = 0, q0 = 0, q1 = 0, q2 = 0, q3 = 0;
+    double mn = INFINITY, mx = -INFINITY;
+    long k = k0;
+    const T *p = X + e;
+    for (; k + 4 <= k1; k += 4) {
+        double a = (double)p[k * szK] - c, b = (double)p[(k + 1) * szK] - c, cc = (double)p[(k + 2) * szK] - c, d = (double)p[(k + 3) * szK] - c;
+        s0 += a; s1 += b; s2 += cc; s3 += d;
+        q0 = fma(a, a, q0); q1 = fma(b, b, q1); q2 = fma(cc, cc, q2); q3 = fma(d, d, q3);
+        if (MODE == 1) { mn = fmin(mn, fmin(fmin(a, b), fmin(cc, d))); mx = fmax(mx, fmax(fmax(a, b), fmax(cc, d))); }
+    }
+    for (; k < k1; ++k) {
+        double a = (double)p[k * szK] - c;
+        s0 += a; q0 = fma(a, a, q0);
+        if (MODE == 1) { mn = fmin(mn, a); mx = fmax(mx, a); }
+    }
+    const long ks = blockIdx.y, nq = (MODE == 1) ? 4 : 2;
+    double *o = part + (ks * nq) * szK + e;
+    o[0] = (s0 + s1) + (s2 + s3);
+    o[szK] = (q0 + q1) + (q2 + q3);
+    if (MODE == 1) { o[2 * szK] = mn + c; o[3 * szK] = mx + c; }
+}
+
+// stage 2: combine the ksplit partials in index order
+template <int MODE>
+__global__ void __launch_bounds__(kT) moments_final_k(double *o0, double *o1, double *o2, double *o3, const double *part, long szK, int ksplit)
+{
+    const long e = (long)blockIdx.x * kT + threadIdx.x;
+    if (e >= szK) return;
+    const long nq = (MODE == 1) ? 4 : 2;
+    double s = 0, q = 0, mn = INFINITY, mx = -INFINITY;
+    for (int ks = 0; ks < ksplit; ++ks) {
+        const double *p = part + ((long)ks * nq) * szK + e;
+        s += p[0]; q += p[szK];
+        if (MODE == 1) { mn = fmin(mn, p[2 * szK]); mx = fmax(mx, p[3 * szK]); }
+    }
+    o0[e] = s; o1[e] = q;
+    if (MODE == 1) { o2[e] = mn; o3[e] = mx; }
+}
+
+static int pick_ksplit(long szK, long N, int sms)
+{
+    long blocks_x = (szK + kT - 1) / kT;
+    long want = (long)sms * 8;                       // ~8 resident CTAs of 256 threads per SM
+    long ks = (want + blocks_x - 1) / blocks_x;
+    if (ks < 1) ks = 1;
+    if (ks > 1024) ks = 1024;
+    if (ks > (N + 63) / 64) ks = (N + 63) / 64;      // at least 64 signals per slice
+    if (ks < 1) ks = 1;
+    return (int)ks;
+}
+
+template <typename T, int MODE>
+int moments(double *o0, double *o1, double *o2, double *o3, const T *X, const double *shift, long szK, long N, cudaStream_t s)
+{
+    WX_REQUIRE(szK >= 1 && N >= 0, "bad sizes");
+    WX_REQUIRE(o0 && o1 && (N == 0 || X), "null pointer");
+    WxDev dv; int rc = wx_devinfo(dv); if (rc) return rc;
+    const int ksplit = N > 0 ? pick_ksplit(szK, N, dv.sms) : 1;
+    const long kchunk = N > 0 ? (N + ksplit - 1) / ksplit : 1;
+    const long nq = (MODE == 1) ? 4 : 2;
+    double *part; rc = wx_scratch(&part, (size_t)ksplit * nq * szK, s); if (rc) return rc;
+    dim3 grid((unsigned)((szK + kT - 1) / kT), (unsigned)ksplit);
+    moments_part_k<T, MODE><<<grid, kT, 0, s>>>(part, X, shift, szK, N, kchunk);
+    WX_LAUNCHED();
+    moments_final_k<MODE><<<gridf(szK), kT, 0, s>>>(o0, o1, o2, o3, part, szK, ksplit);
+    WX_LAUNCHED();
+    return wx_scratch_free(part, s);
+}
+
+// ---- node geometry ---------------------------------------------------------------------------------------
+struct NodeGeom { long m, n; int K; int redundant; };   // m == 0: 1-D
+
+__device__ __forceinline__ int ilog2d(long i) { return 63 - __clzll((unsigned long long)i); }
+__device__ __forceinline__ int quaddepthd(long i) { int d = 0; long last = 1, w = 1; while (i > last) { w *= 4; last += w; ++d; } return d; }
+
+// element t of node q (0-based node, level/heap order) -> linear index into (sz, K); returns node size through cnt
+__device__ __forceinline__ long node_elem(const NodeGeom &g, long q, long t, long &cnt, double &scale)
+{
+    const long i = q + 1;
+    if (g.m == 0) {
+        const int d = ilog2d(i);
+        if (g.redundant) { cnt = g.n; scale = 1.0 / (double)(1L << d); return q * g.n + t; }
+        const long n0 = g.n >> d, j = i - (1L << d);
+        cnt = n0; scale = 1.0;
+        return (long)d * g.n + j * n0 + t;
+    }
+    const long img = g.m * g.n;
+    const int d = quaddepthd(i);
+    if (g.redundant) { cnt = img; scale = 1.0 / (double)(1L << (2 * d)); return q * img + t; }
+    // walk from the root: child c of parent p is 4p-2+c, c = 2*rowbit + colbit
+    long first = 1, w = 1;
+    for (int k = 0; k < d; ++k) { first += w; w *= 4; }      // first index of depth d
+    long off = i - first;                                     // position within the depth, base-4 digits = path
+    long r0 = 0, c0 = 0, nr = g.m, nc = g.n;
+    for (int k = d - 1; k >= 0; --k) {
+        const int dig = (int)((off >> (2 * k)) & 3);
+        nr >>= 1; nc >>= 1;
+        if (dig & 2) r0 += nr;
+        if (dig & 1) c0 += nc;
+    }
+    cnt = nr * nc; scale = 1.0;
+    const long r = t % nr, c = t / nr;
+    return (long)d * img + (c0 + c) * g.m + r0 + r;
+}
+
+// per-position JBB term from the (all-reduced) moments: log(sigma) or sigma^p ; flag bad variances
+__global__ void __launch_bounds__(kT) jbb_term_k(double *term, const double *sum, const double *sumsq, long szK, double Ntot, int kind, double p,
+                                                 int elt, int *bad)
+{
+    const long e = (long)blockIdx.x * kT + threadIdx.x;
+    if (e >= szK) return;
+    double ex = sum[e] / Ntot, ex2 = sumsq[e] / Ntot;
+    if (elt == 4) { ex = (double)(float)ex; ex2 = (double)(float)ex2; }
+    double var = ex2 - ex * ex;
+    if (elt == 4) var = (double)(float)var;
+    if (!(var >= 0.0)) atomicExch(bad, 1);
+    double sg = sqrt(var);
+    if (elt == 4) sg = (double)(float)sg;
+    term[e] = (kind == 0) ? log(fabs(sg)) : pow(fabs(sg), p);
+}
+
+// one warp per node, lane-strided partial sums + xor-shuffle tree (fixed order)
+__global__ void __launch_bounds__(kT) node_reduce_k(double *costs, const double *term, NodeGeom g, long nnodes, double mult)
+{
+    const long q = ((long)blockIdx.x * kT + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (q >= nnodes) return;
+    long cnt; double scale;
+    node_elem(g, q, 0, cnt, scale);
+    double acc = 0.0;
+    for (long t = lane; t < cnt; t += 32) {
+        long c2; double s2;
+        acc += term[node_elem(g, q, t, c2, s2)];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) costs[q] = mult * acc * scale;
+}
+
+static long count_nodes(long m, int K, int redundant)
+{
+    if (redundant) return K;
+    return m > 0 ? ((1L << (2 * K)) - 1) / 3 : (1L << K) - 1;
+}
+
+static int node_costs_to_host(double *costs_host, const double *term, long m, long n, int K, int redundant, double mult, int elt, cudaStream_t s)
+{
+    const long nn = count_nodes(m, K, redundant);
+    double *dc; int rc = wx_scratch(&dc, (size_t)nn, s); if (rc) return rc;
+    NodeGeom g{m, n, K, redundant};
+    node_reduce_k<<<gridf(nn * 32), kT, 0, s>>>(dc, term, g, nn, mult);
+    WX_LAUNCHED();
+    WX_CUDA(cudaMemcpyAsync(costs_host, dc, (size_t)nn * sizeof(double), cudaMemcpyDeviceToHost, s));
+    WX_CUDA(cudaStreamSynchronize(s));
+    if (elt == 4) for (long i = 0; i < nn; ++i) costs_host[i] = (double)(float)costs_host[i];
+    return wx_scratch_free(dc, s);
+}
+
+// ---- LSDB -----------------------------------------------------------------------------------------------
+struct LsdbGrid { long nbins, mbins, npts; };
+static LsdbGrid lsdb_grid(long N)
+{
+    LsdbGrid g;
+    g.nbins = (long)std::ceil(std::pow(30.0 * (double)N, 0.2));     // bestbasis_costs.jl:140
+    g.mbins = (long)std::ceil(50.0 / (double)g.nbins);              // :141
+    g.npts = (g.nbins + 1) * g.mbins;                               // length of rng (:147)
+    return g;
+}
+
+// per-position grid origin a and step delta from the reduced statistics  (bestbasis_costs.jl:143-147)
+// stats rows: 0 shift c, 1 sum(x-c), 2 sum((x-c)^2), 3 min, 4 max
+__device__ __forceinline__ void lsdb_axis(const double *stats, long szK, long e, double Ntot, long npts, double &a, double &delta)
+{
+    const double s1 = stats[szK + e], s2 = stats[2 * szK + e], mn = stats[3 * szK + e], mx = stats[4 * szK + e];
+    double var = (s2 - s1 * s1 / Ntot) / (Ntot - 1.0);               // Statistics.std (corrected)
+    if (var < 0) var = 0;
+    const double sg = sqrt(var);
+    delta = (mx - mn + sg) / (double)(npts - 1);
+    a = mn - 0.5 * sg;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kT) lsdb_hist_k(double *counts, const double *stats, const T *X, long szK, long N, long kchunk, double Ntot, long npts)
+{
+    const long e = (long)blockIdx.x * kT + threadIdx.x;
+    if (e >= szK) return;
+    double a, delta;
+    lsdb_axis(stats, szK, e, Ntot, npts, a, delta);
+    const double dinv = 1.0 / delta;
+    const long k0 = (long)blockIdx.y * kchunk;
+    long k1 = k0 + kchunk; if (k1 > N) k1 = N;
+    for (long k = k0; k < k1; ++k) {
+        const double xv = (double)X[k * szK + e];
+        const long ki = (long)floor((xv - a) * dinv + 1.5);          // AverageShiftedHistograms bin rule (1-based)
+        if (ki >= 1 && ki <= npts) atomicAdd(&counts[(ki - 1) * szK + e], 1.0);
+    }
+}
+
+// ASH density on the grid from the (all-reduced) counts, triangular kernel, normalised by 1/(sum(y)*delta)
+__global__ void __launch_bounds__(kT) lsdb_density_k(double *dens, const double *counts, const double *stats, long szK, double Ntot, long npts, long mb)
+{
+    const long e = (long)blockIdx.x * kT + threadIdx.x;
+    if (e >= szK) return;
+    double a, delta;
+    lsdb_axis(stats, szK, e, Ntot, npts, a, delta);
+    double tot = 0.0;
+    for (long i = 1; i <= npts; ++i) {
+        double y = 0.0;
+        long lo = i - mb + 1 < 1 ? 1 : i - mb + 1, hi = i + mb - 1 > npts ? npts : i + mb - 1;
+        for (long k = lo; k <= hi; ++k) {
+            const double u = fabs((double)(i - k) / (double)mb);
+            y += counts[(k - 1) * szK + e] * (1.0 - u);
+        }
+        dens[(i - 1) * szK + e] = y;
+        tot += y;
+    }
+    const double den = 1.0 / (tot * delta);
+    for (long i = 0; i < npts; ++i) dens[i * szK + e] *= den;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kT) lsdb_logpdf_part_k(double *part, const double *dens, const double *stats, const T *X, long szK, long N, long kchunk,
+                                                          double Ntot, long npts)
+{
+    const long e = (long)blockIdx.x * kT + threadIdx.x;
+    if (e >= szK) return;
+    double a, delta;
+    lsdb_axis(stats, szK, e, Ntot, npts, a, delta);
+    const double dinv = 1.0 / delta;
+    const long k0 = (long)blockIdx.y * kchunk;
+    long k1 = k0 + kchunk; if (k1 > N) k1 = N;
+    double acc = 0.0;
+    for (long k = k0; k < k1; ++k) {
+        const double xv = (double)X[k * szK + e];
+        long i = (long)floor((xv - a) * dinv) + 1;                   // searchsortedlast(rng, x), 1-based
+        while (i >= 1 && i <= npts && a + (double)(i - 1) * delta > xv) --i;
+        while (i + 1 <= npts && a + (double)i * delta <= xv) ++i;
+        double pdf = 0.0;
+        if (i >= 1 && i < npts) {
+            const double g0 = a + (double)(i - 1) * delta, g1 = a + (double)i * delta;
+            const double y0 = dens[(i - 1) * szK + e], y1 = dens[i * szK + e];
+            pdf = y0 + (y1 - y0) * (xv - g0) / (g1 - g0);
+        }
+        acc += log(pdf);
+    }
+    part[(long)blockIdx.y * szK + e] = acc;
+}
+
+__global__ void __launch_bounds__(kT) sum_parts_k(double *out, const double *part, long szK, int ksplit)
+{
+    const long e = (long)blockIdx.x * kT + threadIdx.x;
+    if (e >= szK) return;
+    double s = 0.0;
+    for (int ks = 0; ks < ksplit; ++ks) s += part[(long)ks * szK + e];
+    out[e] = s;
+}
+
+template <typename T>
+int lsdb_pass2(double *counts, const double *stats, const T *X, long szK, long Nlocal, long Ntotal, cudaStream_t s)
+{
+    WX_REQUIRE(szK >= 1 && Nlocal >= 0 && Ntotal >= 2, "LSDB needs at least two signals");
+    WX_REQUIRE(counts && stats && (Nlocal == 0 || X), "null pointer");
+    const LsdbGrid g = lsdb_grid(Ntotal);
+    WX_CUDA(cudaMemsetAsync(counts, 0, (size_t)g.npts * szK * sizeof(double), s));
+    if (Nlocal == 0) return WX_OK;
+    WxDev dv; int rc = wx_devinfo(dv); if (rc) return rc;
+    const int ksplit = pick_ksplit(szK, Nlocal, dv.sms);
+    const long kchunk = (Nlocal + ksplit - 1) / ksplit;
+    dim3 grid((unsigned)((szK + kT - 1) / kT), (unsigned)ksplit);
+    lsdb_hist_k<T><<<grid, kT, 0, s>>>(counts, stats, X, szK, Nlocal, kchunk, (double)Ntotal, g.npts);
+    WX_LAUNCHED();
+    return WX_OK;
+}
+
+template <typename T>
+int lsdb_pass3(double *logsum, const double *counts, const double *stats, const T *X, long szK, long Nlocal, long Ntotal, cudaStream_t s)
+{
+    WX_REQUIRE(szK >= 1 && Nlocal >= 0 && Ntotal >= 2, "LSDB needs at least two signals");
+    WX_REQUIRE(logsum && counts && stats && (Nlocal == 0 || X), "null pointer");
+    const LsdbGrid g = lsdb_grid(Ntotal);
+    if (Nlocal == 0) { WX_CUDA(cudaMemsetAsync(logsum, 0, (size_t)szK * sizeof(double), s)); return WX_OK; }
+    WxDev dv; int rc = wx_devinfo(dv); if (rc) return rc;
+    const int ksplit = pick_ksplit(szK, Nlocal, dv.sms);
+    const long kchunk = (Nlocal + ksplit - 1) / ksplit;
+    double *dens, *part;
+    rc = wx_scratch(&dens, (size_t)g.npts * szK, s); if (rc) return rc;
+    rc = wx_scratch(&part, (size_t)ksplit * szK, s); if (rc) return rc;
+    lsdb_density_k<<<gridf(szK), kT, 0, s>>>(dens, counts, stats, szK, (double)Ntotal, g.npts, g.mbins);
+    WX_LAUNCHED();
+    dim3 grid((unsigned)((szK + kT - 1) / kT), (unsigned)ksplit);
+    lsdb_logpdf_part_k<T><<<grid, kT, 0, s>>>(part, dens, stats, X, szK, Nlocal, kchunk, (double)Ntotal, g.npts);
+    WX_LAUNCHED();
+    sum_parts_k<<<gridf(szK), kT, 0, s>>>(logsum, part, szK, ksplit);
+    WX_LAUNCHED();
+    int rc2 = wx_scratch_free(dens, s), rc3 = wx_scratch_free(part, s);
+    return rc2 ? rc2 : rc3;
+}
+
+__global__ void __launch_bounds__(kT) scale_k(double *out, const double *in, long n, double f)
+{
+    const long e = (long)blockIdx.x * kT + threadIdx.x;
+    if (e < n) out[e] = in[e] * f;
+}
+
+}  // namespace
+
+extern "C" {
+
+int wx_jbb_moments_f64(double *sum, double *sumsq, const double *X, long szK, long Nlocal, void *stream)
+{
+    return moments<double, 0>(sum, sumsq, nullptr, nullptr, X, nullptr, szK, Nlocal, (cudaStream_t)stream);
+}
+int wx_jbb_moments_f32(double *sum, double *sumsq, const float *X, long szK, long Nlocal, void *stream)
+{
+    return moments<float, 0>(sum, sumsq, nullptr, nullptr, X, nullptr, szK, Nlocal, (cudaStream_t)stream);
+}
+
+int wx_jbb_costs(double *costs_host, const double *sum, const double *sumsq, long Ntotal, long m, long n, int K, int redundant, int cost_kind,
+                 double p, int elt, void *stream)
+{
+    cudaStream_t s = (cudaStream_t)stream;
+    WX_REQUIRE(costs_host && sum && sumsq, "null pointer");
+    WX_REQUIRE(Ntotal >= 1 && n >= 1 && m >= 0 && K >= 1, "bad sizes");
+    WX_REQUIRE(cost_kind == 0 || cost_kind == 1, "unknown JBB cost kind %d", cost_kind);
+    WX_REQUIRE(elt == 4 || elt == 8, "elt must be 4 or 8");
+    if (!redundant) WX_REQUIRE(m > 0 ? 2 * K < 62 : K < 62, "too many levels");
+    const long szK = (m > 0 ? m : 1) * n * K;
+    double *term; int *bad;
+    int rc = wx_scratch(&term, (size_t)szK, s); if (rc) return rc;
+    rc = wx_scratch(&bad, 1, s); if (rc) return rc;
+    WX_CUDA(cudaMemsetAsync(bad, 0, sizeof(int), s));
+    jbb_term_k<<<gridf(szK), kT, 0, s>>>(term, sum, sumsq, szK, (double)Ntotal, cost_kind, p, elt, bad);
+    WX_LAUNCHED();
+    const double mult = (cost_kind == 0) ? p : 1.0;       // LoglpCost: p * sum(log|x|) ; NormCost: norm(x,p)^p = sum |x|^p
+    rc = node_costs_to_host(costs_host, term, m, n, K, redundant, mult, elt, s);
+    int hbad = 0;
+    if (!rc) { WX_CUDA(cudaMemcpyAsync(&hbad, bad, sizeof(int), cudaMemcpyDeviceToHost, s)); WX_CUDA(cudaStreamSynchronize(s)); }
+    int rc2 = wx_scratch_free(term, s), rc3 = wx_scratch_free(bad, s);
+    if (rc) return rc;
+    if (rc2 || rc3) return rc2 ? rc2 : rc3;
+    if (hbad) return wx_fail(WX_EINVAL, "DomainError/AssertionError: negative variance, all(sigma .>= 0) failed");
+    return WX_OK;
+}
+
+int wx_lsdb_grid(long Ntotal, long *nbins, long *mbins, long *npts)
+{
+    WX_REQUIRE(Ntotal >= 1, "bad N");
+    const LsdbGrid g = lsdb_grid(Ntotal);
+    if (nbins) *nbins = g.nbins;
+    if (mbins) *mbins = g.mbins;
+    if (npts) *npts = g.npts;
+    return WX_OK;
+}
+
+// stats(5, szK): row 0 = shift (INPUT, caller-filled, e.g. the first signal of the global batch), rows 1..4 = outputs
+int wx_lsdb_pass1_f64(double *stats, const double *X, long szK, long Nlocal, void *stream)
+{
+    WX_REQUIRE(stats, "null pointer");
+    return moments<double, 1>(stats + szK, stats + 2 * szK, stats + 3 * szK, stats + 4 * szK, X, stats, szK, Nlocal, (cudaStream_t)stream);
+}
+int wx_lsdb_pass1_f32(double *stats, const float *X, long szK, long Nlocal, void *stream)
+{
+    WX_REQUIRE(stats, "null pointer");
+    return moments<float, 1>(stats + szK, stats + 2 * szK, stats + 3 * szK, stats + 4 * szK, X, stats, szK, Nlocal, (cudaStream_t)stream);
+}
+int wx_lsdb_pass2_f64(double *counts, const double *stats, const double *X, long szK, long Nlocal, long Ntotal, void *s) { return lsdb_pass2<double>(counts, stats, X, szK, Nlocal, Ntotal, (cudaStream_t)s); }
+int wx_lsdb_pass2_f32(double *counts, const double *stats, const float *X, long szK, long Nlocal, long Ntotal, void *s) { return lsdb_pass2<float>(counts, stats, X, szK, Nlocal, Ntotal, (cudaStream_t)s); }
+int wx_lsdb_pass3_f64(double *logsum, const double *counts, const double *stats, const double *X, long szK, long Nlocal, long Ntotal, void *s) { return lsdb_pass3<double>(logsum, counts, stats, X, szK, Nlocal, Ntotal, (cudaStream_t)s); }
+int wx_lsdb_pass3_f32(double *logsum, const double *counts, const double *stats, const float *X, long szK, long Nlocal, long Ntotal, void *s) { return lsdb_pass3<float>(logsum, counts, stats, X, szK, Nlocal, Ntotal, (cudaStream_t)s); }
+
+int wx_lsdb_costs(double *costs_host, const double *logsum, long Ntotal, long m, long n, int K, int redundant, void *stream)
+{
+    cudaStream_t s = (cudaStream_t)stream;
+    WX_REQUIRE(costs_host && logsum, "null pointer");
+    WX_REQUIRE(Ntotal >= 1 && n >= 1 && m >= 0 && K >= 1, "bad sizes");
+    const long szK = (m > 0 ? m : 1) * n * K;
+    double *term; int rc = wx_scratch(&term, (size_t)szK, s); if (rc) return rc;
+    scale_k<<<gridf(szK), kT, 0, s>>>(term, logsum, szK, -1.0 / (double)Ntotal);     // ent = -(1/N) sum log pdf
+    WX_LAUNCHED();
+    rc = node_costs_to_host(costs_host, term, m, n, K, redundant, 1.0, 8, s);
+    int rc2 = wx_scratch_free(term, s);
+    return rc ? rc : rc2;
+}
+
+// bestbasis_treeselection  BestBasis.jl:59-110 + delete_subtree! :128-140 (host)
+int wx_tree_select(unsigned char *tree_out, double *costs, long ncosts, long m, long n, int minmax)
+{
+    WX_REQUIRE(tree_out && costs, "null pointer");
+    WX_REQUIRE(n >= 1 && m >= 0 && ncosts >= 1, "bad sizes");
+    WX_REQUIRE(minmax == 0 || minmax == 1, "ArgumentError: Unsupported type");
+    const int ar = m > 0 ? 4 : 2;
+    long ntree, nfull;
+    int L;
+    if (m > 0) {
+        const int Lm = wx_maxlevels(m < n ? m : n);
+        ntree = ((1L << (2 * Lm)) - 1) / 3;
+        WX_REQUIRE(ncosts <= ((1L << (2 * (Lm + 1))) - 1) / 3, "AssertionError: k <= gettreelength(2n,2m)");
+        L = wx_quaddepthl(ncosts);
+        nfull = ((1L << (2 * L)) - 1) / 3;
+    } else {
+        ntree = n - 1;
+        WX_REQUIRE(ncosts <= (1L << (wx_maxlevels(2 * n))) - 1, "AssertionError: k <= gettreelength(2n)");
+        L = wx_ilog2l(ncosts);
+        nfull = (1L << L) - 1;
+    }
+    memset(tree_out, 0, (size_t)(ntree > 0 ? ntree : 0));
+    for (long i = 1; i <= nfull && i <= ntree; ++i) tree_out[i - 1] = 1;          // maketree(n, L, :full)
+    std::vector<long> stack;
+    for (long i = ntree; i >= 1; --i) {
+        if (!tree_out[i - 1]) continue;
+        const long c0 = (ar == 2) ? 2 * i : 4 * i - 2;
+        if (c0 + ar - 1 > ncosts) return wx_fail(WX_EINVAL, "cost vector too short for node %ld", i);
+        const double pc = costs[i - 1];
+        double cc = costs[c0 - 1] + costs[c0];
+        if (ar == 4) cc = (cc + costs[c0 + 1]) + costs[c0 + 2];
+        if ((minmax == 0 && cc < pc) || (minmax == 1 && cc > pc)) { costs[i - 1] = cc; continue; }
+        stack.assign(1, i);                                                         // delete_subtree!
+        while (!stack.empty()) {
+            const long q = stack.back(); stack.pop_back();
+            tree_out[q - 1] = 0;
+            for (int c = 0; c < ar; ++c) {
+                const long ch = (ar == 2) ? 2 * q + c : 4 * q - 2 + c;
+                if (ch <= ntree && tree_out[ch - 1]) stack.push_back(ch);
+            }
+        }
+    }
+    return WX_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,114 @@
+// wx_runtime.cu -- runtime part of the C ABI (device memory, copies, sync, error text).
+#include "wx_common.cuh"
+
+thread_local char wx_errbuf[512] = "";
+std::atomic<unsigned long long> wx_launches{0};
+
+int wx_devinfo(WxDev &d)
+{
+    static WxDev cache[64];
+    static bool have[64] = {false};
+    int dev = 0;
+    WX_CUDA(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < 64 && have[dev]) { d = cache[dev]; return WX_OK; }
+    int sms = 0, smem = 0;
+    WX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    WX_CUDA(cudaDeviceGetAttribute(&smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    d.sms = sms; d.smem_optin = (size_t)smem; d.dev = dev;
+    if (dev >= 0 && dev < 64) { cache[dev] = d; have[dev] = true; }
+    return WX_OK;
+}
+
+extern "C" {
+
+int wx_version(void) { return 100; }
+
+const char *wx_last_error(void) { return wx_errbuf; }
+
+unsigned long long wx_launch_count(void) { return wx_launches.load(); }
+
+int wx_device_count(int *count)
+{
+    WX_REQUIRE(count, "null count");
+    *count = 0;
+    WX_CUDA(cudaGetDeviceCount(count));
+    return WX_OK;
+}
+
+int wx_set_device(int dev)
+{
+    WX_CUDA(cudaSetDevice(dev));
+    return WX_OK;
+}
+
+int wx_device_info(int *sm_count, int *cc_major, int *cc_minor, size_t *smem_optin, size_t *total_mem)
+{
+    int dev = 0;
+    WX_CUDA(cudaGetDevice(&dev));
+    cudaDeviceProp p;
+    WX_CUDA(cudaGetDeviceProperties(&p, dev));
+    if (sm_count) *sm_count = p.multiProcessorCount;
+    if (cc_major) *cc_major = p.major;
+    if (cc_minor) *cc_minor = p.minor;
+    if (smem_optin) *smem_optin = p.sharedMemPerBlockOptin;
+    if (total_mem) *total_mem = p.totalGlobalMem;
+    return WX_OK;
+}
+
+int wx_malloc(void **dptr, size_t bytes)
+{
+    WX_REQUIRE(dptr, "null dptr");
+    *dptr = nullptr;
+    cudaError_t e = cudaMalloc(dptr, bytes ? bytes : 1);
+    if (e == cudaErrorMemoryAllocation) { cudaGetLastError(); return wx_fail(WX_ENOMEM, "cudaMalloc(%zu) out of memory", bytes); }
+    WX_CUDA(e);
+    return WX_OK;
+}
+
+int wx_free(void *dptr)
+{
+    if (dptr) WX_CUDA(cudaFree(dptr));
+    return WX_OK;
+}
+
+int wx_malloc_host(void **hptr, size_t bytes)
+{
+    WX_REQUIRE(hptr, "null hptr");
+    *hptr = nullptr;
+    cudaError_t e = cudaHostAlloc(hptr, bytes ? bytes : 1, cudaHostAllocDefault);
+    if (e == cudaErrorMemoryAllocation) { cudaGetLastError(); return wx_fail(WX_ENOMEM, "cudaHostAlloc(%zu) out of memory", bytes); }
+    WX_CUDA(e);
+    return WX_OK;
+}
+
+int wx_free_host(void *hptr)
+{
+    if (hptr) WX_CUDA(cudaFreeHost(hptr));
+    return WX_OK;
+}
+
+int wx_h2d(void *dst_dev, const void *src_host, size_t bytes, void *stream)
+{
+    WX_CUDA(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    return WX_OK;
+}
+
+int wx_d2h(void *dst_host, const void *src_dev, size_t bytes, void *stream)
+{
+    WX_CUDA(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    return WX_OK;
+}
+
+int wx_stream_sync(void *stream)
+{
+    WX_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return WX_OK;
+}
+
+int wx_device_sync(void)
+{
+    WX_CUDA(cudaDeviceSynchronize());
+    return WX_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,461 @@
+// wx_steps.cu -- generic one-level step kernels (strided, batched, any n / F) and the single-step C ABI.
+// One thread per output (pair); taps are read from kernel-parameter constant memory with a runtime
+// index.  These kernels favour generality; the bandwidth-critical batched trees have fused kernels of
+// their own (wx_wpd1d.cu, ...).
+#include "wx_steps.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+template <typename T>
+__device__ __forceinline__ long voff(const View<T> &v, long b0, long b1, long b2)
+{
+    return b0 * v.s0 + b1 * v.s1 + b2 * v.s2;
+}
+
+__device__ __forceinline__ bool decomp(long idx, long nout, const Batch &b, long &i, long &b0, long &b1, long &b2)
+{
+    long tot = nout * b.B0 * b.B1 * b.B2;
+    if (idx >= tot) return false;
+    if (b.batch_fast) { b0 = idx % b.B0; idx /= b.B0; i = idx % nout; idx /= nout; }
+    else              { i = idx % nout; idx /= nout; b0 = idx % b.B0; idx /= b.B0; }
+    b1 = idx % b.B1; b2 = idx / b.B1;
+    return true;
+}
+
+static inline unsigned grid_for(long total) { return (unsigned)((total + kThreads - 1) / kThreads); }
+
+// a1 dwt_step!  dwt/dwt_one_level.jl:94-105
+template <typename T>
+__global__ void __launch_bounds__(kThreads) dwt_step_k(View<T> w1, View<T> w2, View<const T> v, long n, Batch b, Taps<T> tp)
+{
+    long i, b0, b1, b2;
+    if (!decomp((long)blockIdx.x * kThreads + threadIdx.x, n / 2, b, i, b0, b1, b2)) return;
+    const T *pv = v.p + voff(v, b0, b1, b2);
+    const int F = tp.F;
+    long k1 = 2 * i, k2 = 2 * i + 1;
+    if (k2 >= n) k2 -= n;
+    T a1 = tp.g[F - 1] * pv[k1 * v.es];
+    T a2 = tp.h[0] * pv[k2 * v.es];
+    for (int j = 1; j < F; ++j) {
+        k1 += 1; if (k1 >= n) k1 -= n;
+        k2 -= 1; if (k2 < 0) k2 += n;
+        a1 = fma(tp.g[F - 1 - j], pv[k1 * v.es], a1);
+        a2 = fma(tp.h[j], pv[k2 * v.es], a2);
+    }
+    w1.p[voff(w1, b0, b1, b2) + i * w1.es] = a1;
+    w2.p[voff(w2, b0, b1, b2) + i * w2.es] = a2;
+}
+
+// a2 idwt_step! dwt/dwt_one_level.jl:207-221
+template <typename T>
+__global__ void __launch_bounds__(kThreads) idwt_step_k(View<T> v, View<const T> w1, View<const T> w2, long n, Batch b, Taps<T> tp)
+{
+    long i0b, b0, b1, b2;
+    if (!decomp((long)blockIdx.x * kThreads + threadIdx.x, n, b, i0b, b0, b1, b2)) return;
+    const T *p1 = w1.p + voff(w1, b0, b1, b2);
+    const T *p2 = w2.p + voff(w2, b0, b1, b2);
+    const int F = tp.F;
+    const long n1 = n / 2;
+    long i = i0b + 1;                              // Julia's 1-based i
+    int j0 = (i & 1) ? 1 : 2;
+    int j1 = F - j0 + 1;
+    int j2 = ((i + 1) & 1) ? 1 : 2;
+    long k1 = (i + 1) >> 1, k2 = k1;
+    T acc = fma(tp.g[j1 - 1], p1[(k1 - 1) * w1.es], tp.h[j2 - 1] * p2[(k2 - 1) * w2.es]);
+    for (int j = j0 + 2; j <= F; j += 2) {
+        j1 = F - j + 1;
+        j2 = j + ((j & 1) ? 1 : -1);
+        k1 -= 1; if (k1 <= 0) k1 += n1;
+        k2 += 1; if (k2 > n1) k2 -= n1;
+        acc += fma(tp.g[j1 - 1], p1[(k1 - 1) * w1.es], tp.h[j2 - 1] * p2[(k2 - 1) * w2.es]);
+    }
+    v.p[voff(v, b0, b1, b2) + i0b * v.es] = acc;
+}
+
+// a9 sdwt_step! swt/swt_one_level.jl:114-125  /  a16 acdwt_step! acwt/acwt_one_level.jl:115-126
+template <typename T, int AC>
+__global__ void __launch_bounds__(kThreads) rdwt_step_k(View<T> w1, View<T> w2, View<const T> v, long n, long D, Batch b, Taps<T> tp)
+{
+    long i, b0, b1, b2;
+    if (!decomp((long)blockIdx.x * kThreads + threadIdx.x, n, b, i, b0, b1, b2)) return;
+    const T *pv = v.p + voff(v, b0, b1, b2);
+    const int F = tp.F;
+    const long Dm = D % n;
+    if (AC == 0) {
+        long k1 = wx_wrapl(i - D, n), k2 = i;
+        T a1 = tp.g[F - 1] * pv[k1 * v.es];
+        T a2 = tp.h[0] * pv[k2 * v.es];
+        for (int j = 1; j < F; ++j) {
+            k1 += Dm; if (k1 >= n) k1 -= n;
+            k2 -= Dm; if (k2 < 0) k2 += n;
+            a1 = fma(tp.g[F - 1 - j], pv[k1 * v.es], a1);
+            a2 = fma(tp.h[j], pv[k2 * v.es], a2);
+        }
+        w1.p[voff(w1, b0, b1, b2) + i * w1.es] = a1;
+        w2.p[voff(w2, b0, b1, b2) + i * w2.es] = a2;
+    } else {
+        long t = wx_wrapl(i + D, n);                                   // 0-based image of t = i+2^d
+        long io = wx_wrapl(i + (long)(F / 2 + 1) * D, n);              // output position
+        T xv = pv[t * v.es];
+        T a1 = tp.g[0] * xv, a2 = tp.h[0] * xv;
+        for (int k = 1; k < F; ++k) {
+            t += Dm; if (t >= n) t -= n;
+            xv = pv[t * v.es];
+            a1 = fma(tp.g[k], xv, a1);
+            a2 = fma(tp.h[k], xv, a2);
+        }
+        w1.p[voff(w1, b0, b1, b2) + io * w1.es] = a1;
+        w2.p[voff(w2, b0, b1, b2) + io * w2.es] = a2;
+    }
+}
+
+// one output of the shift-based inverse stationary step, swt/swt_one_level.jl:301-315 ; t is 1-based
+template <typename T>
+__device__ __forceinline__ T isdwt_elem(const T *p1, long e1, const T *p2, long e2, long n, int d, long sw, long t,
+                                        const Taps<T> &tp, bool has_init, T init)
+{
+    const int F = tp.F;
+    const long sc = 1L << (d + 1), ic = sw + 1;
+    int i0 = (t & 1) ? 1 : 2;
+    int i1 = F - i0 + 1;
+    int i2 = ((t + 1) & 1) ? 1 : 2;
+    long k1 = ((t - 1) >> 1) * sc + ic, k2 = k1;
+    T acc;
+    if (has_init) acc = fma(tp.h[i2 - 1], p2[(k2 - 1) * e2], fma(tp.g[i1 - 1], p1[(k1 - 1) * e1], init));
+    else          acc = fma(tp.g[i1 - 1], p1[(k1 - 1) * e1], tp.h[i2 - 1] * p2[(k2 - 1) * e2]);
+    for (int i = i0 + 2; i <= F; i += 2) {
+        i1 = F - i + 1;
+        i2 = i + ((i & 1) ? 1 : -1);
+        k1 -= sc; if (k1 <= 0) k1 = wx_wrapl(k1 - 1, n) + 1;
+        k2 += sc; if (k2 > n) k2 = wx_wrapl(k2 - 1, n) + 1;
+        acc += fma(tp.g[i1 - 1], p1[(k1 - 1) * e1], tp.h[i2 - 1] * p2[(k2 - 1) * e2]);
+    }
+    return acc;
+}
+
+// a10 isdwt_step! shift based: one thread per coset element
+template <typename T>
+__global__ void __launch_bounds__(kThreads) isdwt_shift_k(View<T> v, View<const T> w1, View<const T> w2, long n, int d, long sv, long sw,
+                                                           int add2out, long cnt, Batch b, Taps<T> tp)
+{
+    long t0, b0, b1, b2;
+    if (!decomp((long)blockIdx.x * kThreads + threadIdx.x, cnt, b, t0, b0, b1, b2)) return;
+    const T *p1 = w1.p + voff(w1, b0, b1, b2);
+    const T *p2 = w2.p + voff(w2, b0, b1, b2);
+    T *pv = v.p + voff(v, b0, b1, b2);
+    const long D = 1L << d;
+    long t = t0 + 1, m = sv + 1 + t0 * D;                              // 1-based
+    long j = (sw == sv) ? wx_wrapl(m - D - 1, n) : wx_wrapl(m - 1, n); // 0-based write position
+    T init = add2out ? pv[j * v.es] : (T)0;
+    pv[j * v.es] = isdwt_elem(p1, w1.es, p2, w2.es, n, d, sw, t, tp, add2out != 0, init);
+}
+
+// a10 isdwt_step! average based: one thread per output position (requires n % 2^(d+1) == 0)
+template <typename T>
+__global__ void __launch_bounds__(kThreads) isdwt_avg_k(View<T> v, View<const T> w1, View<const T> w2, long n, int d, Batch b, Taps<T> tp)
+{
+    long pos, b0, b1, b2;
+    if (!decomp((long)blockIdx.x * kThreads + threadIdx.x, n, b, pos, b0, b1, b2)) return;
+    const T *p1 = w1.p + voff(w1, b0, b1, b2);
+    const T *p2 = w2.p + voff(w2, b0, b1, b2);
+    const long D = 1L << d;
+    const long sv = pos % D;
+    long m1 = pos + 1 + D; if (m1 > n) m1 -= n;          // first call (sw = sv) writes position m-D
+    long t1 = (m1 - 1 - sv) / D + 1;
+    long t2 = (pos - sv) / D + 1;                        // second call (sw = sv+D) adds at position m
+    T a = isdwt_elem(p1, w1.es, p2, w2.es, n, d, sv, t1, tp, false, (T)0);
+    a = isdwt_elem(p1, w1.es, p2, w2.es, n, d, sv + D, t2, tp, true, a);
+    v.p[voff(v, b0, b1, b2) + pos * v.es] = a / (T)2;
+}
+
+// a17 iacdwt_step! acwt/acwt_one_level.jl:221-223
+template <typename T>
+__global__ void __launch_bounds__(kThreads) iacdwt_step_k(View<T> v, View<const T> w1, View<const T> w2, long n, Batch b)
+{
+    long i, b0, b1, b2;
+    if (!decomp((long)blockIdx.x * kThreads + threadIdx.x, n, b, i, b0, b1, b2)) return;
+    T a = w1.p[voff(w1, b0, b1, b2) + i * w1.es] + w2.p[voff(w2, b0, b1, b2) + i * w2.es];
+    v.p[voff(v, b0, b1, b2) + i * v.es] = a / (T)1.4142135623730951;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) copy_k(View<T> dst, View<const T> src, long n, Batch b)
+{
+    long i, b0, b1, b2;
+    if (!decomp((long)blockIdx.x * kThreads + threadIdx.x, n, b, i, b0, b1, b2)) return;
+    dst.p[voff(dst, b0, b1, b2) + i * dst.es] = src.p[voff(src, b0, b1, b2) + i * src.es];
+}
+
+static inline long btot(const Batch &b) { return b.B0 * b.B1 * b.B2; }
+
+}  // namespace
+
+template <typename T>
+int wx_launch_dwt_step(View<T> w1, View<T> w2, View<const T> v, long n, Batch b, const Taps<T> &t, cudaStream_t s)
+{
+    WX_REQUIRE(n >= 2 && n % 2 == 0, "dwt_step: parent length %ld must be even and >= 2", n);
+    long total = (n / 2) * btot(b);
+    if (total == 0) return WX_OK;
+    dwt_step_k<T><<<grid_for(total), kThreads, 0, s>>>(w1, w2, v, n, b, t);
+    WX_LAUNCHED();
+    return WX_OK;
+}
+
+template <typename T>
+int wx_launch_idwt_step(View<T> v, View<const T> w1, View<const T> w2, long n, Batch b, const Taps<T> &t, cudaStream_t s)
+{
+    WX_REQUIRE(n >= 2 && n % 2 == 0, "idwt_step: parent length %ld must be even and >= 2", n);
+    long total = n * btot(b);
+    if (total == 0) return WX_OK;
+    idwt_step_k<T><<<grid_for(total), kThreads, 0, s>>>(v, w1, w2, n, b, t);
+    WX_LAUNCHED();
+    return WX_OK;
+}
+
+template <typename T>
+int wx_launch_rdwt_step(int ac, View<T> w1, View<T> w2, View<const T> v, long n, int d, Batch b, const Taps<T> &t, cudaStream_t s)
+{
+    WX_REQUIRE(n >= 1 && d >= 0 && d < 62, "rdwt_step: bad n=%ld or d=%d", n, d);
+    long total = n * btot(b);
+    if (total == 0) return WX_OK;
+    if (ac) rdwt_step_k<T, 1><<<grid_for(total), kThreads, 0, s>>>(w1, w2, v, n, 1L << d, b, t);
+    else    rdwt_step_k<T, 0><<<grid_for(total), kThreads, 0, s>>>(w1, w2, v, n, 1L << d, b, t);
+    WX_LAUNCHED();
+    return WX_OK;
+}
+
+template <typename T>
+int wx_launch_isdwt_shift(View<T> v, View<const T> w1, View<const T> w2, long n, int d, long sv, long sw, int add2out, Batch b,
+                          const Taps<T> &t, cudaStream_t s)
+{
+    // the reference's @assert (swt/swt_one_level.jl:289-290)
+    WX_REQUIRE(d >= 0 && d < 61, "isdwt_step: bad depth %d", d);
+    WX_REQUIRE(0 <= sv && sv < (1L << d), "AssertionError: 0 <= sv < 1<<d (sv=%ld, d=%d)", sv, d);
+    WX_REQUIRE(sv <= sw && sw < (1L << (d + 1)), "AssertionError: sv <= sw < 1<<(d+1) (sv=%ld, sw=%ld, d=%d)", sv, sw, d);
+    WX_REQUIRE(n % (1L << (d + 1)) == 0, "isdwt_step: n=%ld must be a multiple of 2^(d+1)", n);
+    long cnt = (n - 1 - sv) / (1L << d) + 1;
+    long total = cnt * btot(b);
+    if (total <= 0) return WX_OK;
+    isdwt_shift_k<T><<<grid_for(total), kThreads, 0, s>>>(v, w1, w2, n, d, sv, sw, add2out, cnt, b, t);
+    WX_LAUNCHED();
+    return WX_OK;
+}
+
+template <typename T>
+int wx_launch_isdwt_avg(View<T> v, View<const T> w1, View<const T> w2, long n, int d, Batch b, const Taps<T> &t, cudaStream_t s)
+{
+    WX_REQUIRE(d >= 0 && d < 61, "isdwt_step: bad depth %d", d);
+    WX_REQUIRE(n % (1L << (d + 1)) == 0, "isdwt_step: n=%ld must be a multiple of 2^(d+1)", n);
+    long total = n * btot(b);
+    if (total == 0) return WX_OK;
+    isdwt_avg_k<T><<<grid_for(total), kThreads, 0, s>>>(v, w1, w2, n, d, b, t);
+    WX_LAUNCHED();
+    return WX_OK;
+}
+
+template <typename T>
+int wx_launch_iacdwt_step(View<T> v, View<const T> w1, View<const T> w2, long n, Batch b, cudaStream_t s)
+{
+    long total = n * btot(b);
+    if (total == 0) return WX_OK;
+    iacdwt_step_k<T><<<grid_for(total), kThreads, 0, s>>>(v, w1, w2, n, b);
+    WX_LAUNCHED();
+    return WX_OK;
+}
+
+template <typename T>
+int wx_launch_copy(View<T> dst, View<const T> src, long n, Batch b, cudaStream_t s)
+{
+    long total = n * btot(b);
+    if (total == 0) return WX_OK;
+    copy_k<T><<<grid_for(total), kThreads, 0, s>>>(dst, src, n, b);
+    WX_LAUNCHED();
+    return WX_OK;
+}
+
+#define WX_INST(T)                                                                                                               \
+    template int wx_launch_dwt_step<T>(View<T>, View<T>, View<const T>, long, Batch, const Taps<T> &, cudaStream_t);             \
+    template int wx_launch_idwt_step<T>(View<T>, View<const T>, View<const T>, long, Batch, const Taps<T> &, cudaStream_t);      \
+    template int wx_launch_rdwt_step<T>(int, View<T>, View<T>, View<const T>, long, int, Batch, const Taps<T> &, cudaStream_t);  \
+    template int wx_launch_isdwt_shift<T>(View<T>, View<const T>, View<const T>, long, int, long, long, int, Batch,              \
+                                          const Taps<T> &, cudaStream_t);                                                        \
+    template int wx_launch_isdwt_avg<T>(View<T>, View<const T>, View<const T>, long, int, Batch, const Taps<T> &, cudaStream_t); \
+    template int wx_launch_iacdwt_step<T>(View<T>, View<const T>, View<const T>, long, Batch, cudaStream_t);                     \
+    template int wx_launch_copy<T>(View<T>, View<const T>, long, Batch, cudaStream_t);
+WX_INST(double)
+WX_INST(float)
+
+// ================================================================================================
+// C ABI: single steps
+// ================================================================================================
+namespace {
+
+template <typename T> static View<const T> cview1(const T *p) { return View<const T>{p, 1, 0, 0, 0}; }
+
+template <typename T>
+int dwt_step_1d(T *w1, T *w2, const T *v, long n, const double *h, const double *g, int F, void *stream)
+{
+    WX_REQUIRE(w1 && w2 && v, "null signal pointer");
+    Taps<T> t; int rc = wx_make_taps(t, h, g, F); if (rc) return rc;
+    return wx_launch_dwt_step<T>(view1(w1), view1(w2), cview1(v), n, batch1(), t, (cudaStream_t)stream);
+}
+template <typename T>
+int idwt_step_1d(T *v, const T *w1, const T *w2, long n, const double *h, const double *g, int F, void *stream)
+{
+    WX_REQUIRE(w1 && w2 && v, "null signal pointer");
+    Taps<T> t; int rc = wx_make_taps(t, h, g, F); if (rc) return rc;
+    return wx_launch_idwt_step<T>(view1(v), cview1(w1), cview1(w2), n, batch1(), t, (cudaStream_t)stream);
+}
+template <typename T>
+int rdwt_step_1d(int ac, T *w1, T *w2, const T *v, long n, int d, const double *h, const double *g, int F, void *stream)
+{
+    WX_REQUIRE(w1 && w2 && v, "null signal pointer");
+    Taps<T> t; int rc = wx_make_taps(t, h, g, F); if (rc) return rc;
+    return wx_launch_rdwt_step<T>(ac, view1(w1), view1(w2), cview1(v), n, d, batch1(), t, (cudaStream_t)stream);
+}
+template <typename T>
+int isdwt_shift_1d(T *v, const T *w1, const T *w2, long n, int d, long sv, long sw, const double *h, const double *g, int F,
+                   int add2out, void *stream)
+{
+    WX_REQUIRE(w1 && w2 && v, "null signal pointer");
+    Taps<T> t; int rc = wx_make_taps(t, h, g, F); if (rc) return rc;
+    return wx_launch_isdwt_shift<T>(view1(v), cview1(w1), cview1(w2), n, d, sv, sw, add2out, batch1(), t, (cudaStream_t)stream);
+}
+template <typename T>
+int isdwt_avg_1d(T *v, const T *w1, const T *w2, long n, int d, const double *h, const double *g, int F, void *stream)
+{
+    WX_REQUIRE(w1 && w2 && v, "null signal pointer");
+    Taps<T> t; int rc = wx_make_taps(t, h, g, F); if (rc) return rc;
+    return wx_launch_isdwt_avg<T>(view1(v), cview1(w1), cview1(w2), n, d, batch1(), t, (cudaStream_t)stream);
+}
+
+// 2-D steps on contiguous column-major matrices -------------------------------------------------
+// dwt_step! 2-D  dwt/dwt_one_level.jl:335-352 : columns into temp, then rows
+template <typename T>
+int dwt_step_2d(T *w1, T *w2, T *w3, T *w4, const T *v, long nr, long nc, const double *h, const double *g, int F, void *stream)
+{
+    WX_REQUIRE(w1 && w2 && w3 && w4 && v, "null signal pointer");
+    WX_REQUIRE(nr >= 1 && nc >= 1, "dwt_step 2-D: empty child");
+    cudaStream_t s = (cudaStream_t)stream;
+    Taps<T> t; int rc = wx_make_taps(t, h, g, F); if (rc) return rc;
+    T *temp; rc = wx_scratch(&temp, (size_t)4 * nr * nc, s); if (rc) return rc;
+    const long ld = 2 * nr;
+    // columns: problem b0 = column j (stride ld), contiguous elements
+    rc = wx_launch_dwt_step<T>(View<T>{temp, 1, ld, 0, 0}, View<T>{temp + nr, 1, ld, 0, 0}, View<const T>{v, 1, ld, 0, 0}, 2 * nr,
+                               Batch{2 * nc, 1, 1, false}, t, s);
+    // rows: problem b0 = row i (stride 1), element stride = leading dimension
+    if (!rc) rc = wx_launch_dwt_step<T>(View<T>{w1, nr, 1, 0, 0}, View<T>{w2, nr, 1, 0, 0}, View<const T>{temp, ld, 1, 0, 0}, 2 * nc,
+                                        Batch{nr, 1, 1, true}, t, s);
+    if (!rc) rc = wx_launch_dwt_step<T>(View<T>{w3, nr, 1, 0, 0}, View<T>{w4, nr, 1, 0, 0}, View<const T>{temp + nr, ld, 1, 0, 0}, 2 * nc,
+                                        Batch{nr, 1, 1, true}, t, s);
+    int rc2 = wx_scratch_free(temp, s);
+    return rc ? rc : rc2;
+}
+
+// idwt_step! 2-D  dwt/dwt_one_level.jl:417-434 : rows into temp, then columns
+template <typename T>
+int idwt_step_2d(T *v, const T *w1, const T *w2, const T *w3, const T *w4, long nr, long nc, const double *h, const double *g, int F,
+                 void *stream)
+{
+    WX_REQUIRE(w1 && w2 && w3 && w4 && v, "null signal pointer");
+    WX_REQUIRE(nr >= 1 && nc >= 1, "idwt_step 2-D: empty child");
+    cudaStream_t s = (cudaStream_t)stream;
+    Taps<T> t; int rc = wx_make_taps(t, h, g, F); if (rc) return rc;
+    T *temp; rc = wx_scratch(&temp, (size_t)4 * nr * nc, s); if (rc) return rc;
+    const long ld = 2 * nr;
+    rc = wx_launch_idwt_step<T>(View<T>{temp, ld, 1, 0, 0}, View<const T>{w1, nr, 1, 0, 0}, View<const T>{w2, nr, 1, 0, 0}, 2 * nc,
+                                Batch{nr, 1, 1, true}, t, s);
+    if (!rc) rc = wx_launch_idwt_step<T>(View<T>{temp + nr, ld, 1, 0, 0}, View<const T>{w3, nr, 1, 0, 0}, View<const T>{w4, nr, 1, 0, 0},
+                                         2 * nc, Batch{nr, 1, 1, true}, t, s);
+    if (!rc) rc = wx_launch_idwt_step<T>(View<T>{v, 1, ld, 0, 0}, View<const T>{temp, 1, ld, 0, 0}, View<const T>{temp + nr, 1, ld, 0, 0},
+                                         2 * nr, Batch{2 * nc, 1, 1, false}, t, s);
+    int rc2 = wx_scratch_free(temp, s);
+    return rc ? rc : rc2;
+}
+
+// sdwt_step!/acdwt_step! 2-D  swt/swt_one_level.jl:352-368, acwt/acwt_one_level.jl:258-274 ; all (nr x nc)
+template <typename T>
+int rdwt_step_2d(int ac, T *w1, T *w2, T *w3, T *w4, const T *v, long nr, long nc, int d, const double *h, const double *g, int F,
+                 void *stream)
+{
+    WX_REQUIRE(w1 && w2 && w3 && w4 && v, "null signal pointer");
+    cudaStream_t s = (cudaStream_t)stream;
+    Taps<T> t; int rc = wx_make_taps(t, h, g, F); if (rc) return rc;
+    T *temp; rc = wx_scratch(&temp, (size_t)2 * nr * nc, s); if (rc) return rc;
+    T *t1 = temp, *t2 = temp + nr * nc;
+    rc = wx_launch_rdwt_step<T>(ac, View<T>{t1, 1, nr, 0, 0}, View<T>{t2, 1, nr, 0, 0}, View<const T>{v, 1, nr, 0, 0}, nr, d,
+                                Batch{nc, 1, 1, false}, t, s);
+    if (!rc) rc = wx_launch_rdwt_step<T>(ac, View<T>{w1, nr, 1, 0, 0}, View<T>{w2, nr, 1, 0, 0}, View<const T>{t1, nr, 1, 0, 0}, nc, d,
+                                         Batch{nr, 1, 1, true}, t, s);
+    if (!rc) rc = wx_launch_rdwt_step<T>(ac, View<T>{w3, nr, 1, 0, 0}, View<T>{w4, nr, 1, 0, 0}, View<const T>{t2, nr, 1, 0, 0}, nc, d,
+                                         Batch{nr, 1, 1, true}, t, s);
+    int rc2 = wx_scratch_free(temp, s);
+    return rc ? rc : rc2;
+}
+
+// isdwt_step! 2-D swt/swt_one_level.jl:395-469 (mode 0 average, 1 shift) ; iacdwt_step! 2-D acwt/acwt_one_level.jl:288-322 (mode 2)
+template <typename T>
+int irdwt_step_2d(int mode, T *v, const T *w1, const T *w2, const T *w3, const T *w4, long nr, long nc, int d, long sv, long sw,
+                  const double *h, const double *g, int F, void *stream)
+{
+    WX_REQUIRE(w1 && w2 && w3 && w4 && v, "null signal pointer");
+    WX_REQUIRE(mode >= 0 && mode <= 2, "bad inverse mode %d", mode);
+    cudaStream_t s = (cudaStream_t)stream;
+    Taps<T> t;
+    int rc;
+    if (mode == 2) { memset(&t, 0, sizeof(t)); t.F = 1; }
+    else { rc = wx_make_taps(t, h, g, F); if (rc) return rc; }
+    T *temp; rc = wx_scratch(&temp, (size_t)2 * nr * nc, s); if (rc) return rc;
+    T *t1 = temp, *t2 = temp + nr * nc;
+    if (mode == 1) WX_CUDA(cudaMemsetAsync(temp, 0, (size_t)2 * nr * nc * sizeof(T), s));   // positions off the coset stay defined
+    auto step = [&](View<T> vo, View<const T> a, View<const T> b, long n, Batch bt) -> int {
+        if (mode == 2) return wx_launch_iacdwt_step<T>(vo, a, b, n, bt, s);
+        if (mode == 1) return wx_launch_isdwt_shift<T>(vo, a, b, n, d, sv, sw, 0, bt, t, s);
+        return wx_launch_isdwt_avg<T>(vo, a, b, n, d, bt, t, s);
+    };
+    rc = step(View<T>{t1, nr, 1, 0, 0}, View<const T>{w1, nr, 1, 0, 0}, View<const T>{w2, nr, 1, 0, 0}, nc, Batch{nr, 1, 1, true});
+    if (!rc) rc = step(View<T>{t2, nr, 1, 0, 0}, View<const T>{w3, nr, 1, 0, 0}, View<const T>{w4, nr, 1, 0, 0}, nc, Batch{nr, 1, 1, true});
+    if (!rc) rc = step(View<T>{v, 1, nr, 0, 0}, View<const T>{t1, 1, nr, 0, 0}, View<const T>{t2, 1, nr, 0, 0}, nr, Batch{nc, 1, 1, false});
+    int rc2 = wx_scratch_free(temp, s);
+    return rc ? rc : rc2;
+}
+
+}  // namespace
+
+extern "C" {
+
+int wx_dwt_step_f64(double *w1, double *w2, const double *v, long n, const double *h, const double *g, int F, void *s) { return dwt_step_1d<double>(w1, w2, v, n, h, g, F, s); }
+int wx_dwt_step_f32(float *w1, float *w2, const float *v, long n, const double *h, const double *g, int F, void *s) { return dwt_step_1d<float>(w1, w2, v, n, h, g, F, s); }
+int wx_idwt_step_f64(double *v, const double *w1, const double *w2, long n, const double *h, const double *g, int F, void *s) { return idwt_step_1d<double>(v, w1, w2, n, h, g, F, s); }
+int wx_idwt_step_f32(float *v, const float *w1, const float *w2, long n, const double *h, const double *g, int F, void *s) { return idwt_step_1d<float>(v, w1, w2, n, h, g, F, s); }
+int wx_sdwt_step_f64(double *w1, double *w2, const double *v, long n, int d, const double *h, const double *g, int F, void *s) { return rdwt_step_1d<double>(0, w1, w2, v, n, d, h, g, F, s); }
+int wx_sdwt_step_f32(float *w1, float *w2, const float *v, long n, int d, const double *h, const double *g, int F, void *s) { return rdwt_step_1d<float>(0, w1, w2, v, n, d, h, g, F, s); }
+int wx_acdwt_step_f64(double *w1, double *w2, const double *v, long n, int d, const double *h, const double *g, int Lf, void *s) { return rdwt_step_1d<double>(1, w1, w2, v, n, d, h, g, Lf, s); }
+int wx_acdwt_step_f32(float *w1, float *w2, const float *v, long n, int d, const double *h, const double *g, int Lf, void *s) { return rdwt_step_1d<float>(1, w1, w2, v, n, d, h, g, Lf, s); }
+int wx_isdwt_step_shift_f64(double *v, const double *w1, const double *w2, long n, int d, long sv, long sw, const double *h, const double *g, int F, int add2out, void *s) { return isdwt_shift_1d<double>(v, w1, w2, n, d, sv, sw, h, g, F, add2out, s); }
+int wx_isdwt_step_shift_f32(float *v, const float *w1, const float *w2, long n, int d, long sv, long sw, const double *h, const double *g, int F, int add2out, void *s) { return isdwt_shift_1d<float>(v, w1, w2, n, d, sv, sw, h, g, F, add2out, s); }
+int wx_isdwt_step_avg_f64(double *v, const double *w1, const double *w2, long n, int d, const double *h, const double *g, int F, void *s) { return isdwt_avg_1d<double>(v, w1, w2, n, d, h, g, F, s); }
+int wx_isdwt_step_avg_f32(float *v, const float *w1, const float *w2, long n, int d, const double *h, const double *g, int F, void *s) { return isdwt_avg_1d<float>(v, w1, w2, n, d, h, g, F, s); }
+int wx_iacdwt_step_f64(double *v, const double *w1, const double *w2, long n, void *s)
+{
+    WX_REQUIRE(w1 && w2 && v, "null signal pointer");
+    return wx_launch_iacdwt_step<double>(view1(v), cview1(w1), cview1(w2), n, batch1(), (cudaStream_t)s);
+}
+int wx_iacdwt_step_f32(float *v, const float *w1, const float *w2, long n, void *s)
+{
+    WX_REQUIRE(w1 && w2 && v, "null signal pointer");
+    return wx_launch_iacdwt_step<float>(view1(v), cview1(w1), cview1(w2), n, batch1(), (cudaStream_t)s);
+}
+
+int wx_dwt_step2_f64(double *w1, double *w2, double *w3, double *w4, const double *v, long nr, long nc, const double *h, const double *g, int F, void *s) { return dwt_step_2d<double>(w1, w2, w3, w4, v, nr, nc, h, g, F, s); }
+int wx_dwt_step2_f32(float *w1, float *w2, float *w3, float *w4, const float *v, long nr, long nc, const double *h, const double *g, int F, void *s) { return dwt_step_2d<float>(w1, w2, w3, w4, v, nr, nc, h, g, F, s); }
+int wx_idwt_step2_f64(double *v, const double *w1, const double *w2, const double *w3, const double *w4, long nr, long nc, const double *h, const double *g, int F, void *s) { return idwt_step_2d<double>(v, w1, w2, w3, w4, nr, nc, h, g, F, s); }
+int wx_idwt_step2_f32(float *v, const float *w1, const float *w2, const float *w3, const float *w4, long nr, long nc, const double *h, const double *g, int F, void *s) { return idwt_step_2d<float>(v, w1, w2, w3, w4, nr, nc, h, g, F, s); }
+int wx_rdwt_step2_f64(int ac, double *w1, double *w2, double *w3, double *w4, const double *v, long nr, long nc, int d, const double *h, const double *g, int F, void *s) { return rdwt_step_2d<double>(ac, w1, w2, w3, w4, v, nr, nc, d, h, g, F, s); }
+int wx_rdwt_step2_f32(int ac, float *w1, float *w2, float *w3, float *w4, const float *v, long nr, long nc, int d, const double *h, const double *g, int F, void *s) { return rdwt_step_2d<float>(ac, w1, w2, w3, w4, v, nr, nc, d, h, g, F, s); }
+int wx_irdwt_step2_f64(int mode, double *v, const double *w1, const double *w2, const double *w3, const double *w4, long nr, long nc, int d, long sv, long sw, const double *h, const double *g, int F, void *s) { return irdwt_step_2d<double>(mode, v, w1, w2, w3, w4, nr, nc, d, sv, sw, h, g, F, s); }
+int wx_irdwt_step2_f32(int mode, float *v, const float *w1, const float *w2, const float *w3, const float *w4, long nr, long nc, int d, long sv, long sw, const double *h, const double *g, int F, void *s) { return irdwt_step_2d<float>(mode, v, w1, w2, w3, w4, nr, nc, d, sv, sw, h, g, F, s); }
+
+}  // extern "C"

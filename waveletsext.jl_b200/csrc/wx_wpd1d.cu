@@ -1,0 +1,310 @@
+// wx_wpd1d.cu -- batched 1-D wavelet packet decomposition, all levels fused in one launch.
+//
+// Reference: wpdall dwt/dwt_all.jl:260-282 -> wpd! DWT.jl:131-161 -> dwt_step! dwt/dwt_one_level.jl:79-107.
+//   x(n,N) -> y(n,L+1,N);  level 0 = x;  level d+1 node 2j / 2j+1 = low / high of level d node j.
+//
+// Design (B200, HBM-bound: algorithmic traffic = (L+2)*n*sizeof(T) per signal, 2*F*L flops per sample):
+//  * persistent CTAs, one signal (or one depth-d0 node of a long signal) per CTA iteration;
+//  * the node lives in shared memory (ping-pong, 16-byte-chunk XOR swizzle so both the strided window reads
+//    and the packed output writes are bank-conflict free); intermediate levels never round-trip HBM;
+//  * "wide" levels (node half-length multiple of K): each thread loads a register window of 2S+2K samples with
+//    128-bit LDS and produces K low + K high outputs with fully unrolled FMAs (taps come straight from the
+//    kernel-parameter constant bank).  The high-pass outputs are taken S positions ahead of the low-pass ones so
+//    both filters read the same window;  smem traffic is (2S+2K)/(2K*F) loads per FMA instead of 1;
+//  * "small" levels (node length 2,4,8): one thread owns whole nodes in registers, periodic wrap resolved at
+//    compile time;
+//  * every level row is written to HBM straight from registers with 128-bit streaming stores (32 B / thread,
+//    contiguous across the warp), level 0 is copied while the signal is staged.
+//  * accumulation order per output is the reference's tap order (j ascending); products use FMA.
+#include "wx_steps.cuh"
+
+namespace {
+
+template <typename T, int F>
+struct WpdCfg {
+    static constexpr int V = WxVec<T>::N;                              // elements per 16 B chunk
+    static constexpr int K = 2 * V;                                    // output pairs per window
+    static constexpr int S = (((F - 2) / 2) + V - 1) / V * V;          // high-pass look-ahead (multiple of V)
+    static constexpr int W = 2 * S + 2 * K;                            // window length (elements)
+};
+
+template <typename T> __device__ __forceinline__ typename WxVec<T>::type wx_ldg_stream(const T *p);
+template <> __device__ __forceinline__ double2 wx_ldg_stream<double>(const double *p) { return __ldcs(reinterpret_cast<const double2 *>(p)); }
+template <> __device__ __forceinline__ float4 wx_ldg_stream<float>(const float *p) { return __ldcs(reinterpret_cast<const float4 *>(p)); }
+__device__ __forceinline__ void wx_stg_stream(double *p, double2 v) { __stcs(reinterpret_cast<double2 *>(p), v); }
+__device__ __forceinline__ void wx_stg_stream(float *p, float4 v) { __stcs(reinterpret_cast<float4 *>(p), v); }
+
+__device__ __forceinline__ void wx_unpack(double *d, double2 v) { d[0] = v.x; d[1] = v.y; }
+__device__ __forceinline__ void wx_unpack(float *d, float4 v) { d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w; }
+__device__ __forceinline__ double2 wx_pack(const double *d) { return make_double2(d[0], d[1]); }
+__device__ __forceinline__ float4 wx_pack(const float *d) { return make_float4(d[0], d[1], d[2], d[3]); }
+
+// store one 16 B chunk of outputs (element index e, chunk aligned) to the next-level smem buffer and to HBM
+template <typename T>
+__device__ __forceinline__ void wx_put_chunk(T *dst, T *grow, int e, const T *vals, bool last)
+{
+    constexpr int V = WxVec<T>::N;
+    using VT = typename WxVec<T>::type;
+    VT v = wx_pack(vals);
+    if (!last) *reinterpret_cast<VT *>(dst + wx_swz_chunk(e / V) * V) = v;
+    wx_stg_stream(grow + e, v);
+}
+
+// ---- wide level: node half-length is a multiple of K -------------------------------------------------
+template <typename T, int F, bool POW2>
+__device__ __forceinline__ void wpd_wide_level(const T *__restrict__ src, T *__restrict__ dst, T *__restrict__ grow, int n0, int p,
+                                               bool last, const Taps<T> &tp, int tid, int nthreads)
+{
+    using C = WpdCfg<T, F>;
+    using VT = typename WxVec<T>::type;
+    constexpr int V = C::V, K = C::K, S = C::S, W = C::W;
+    const int half = p >> 1;
+    const int units = n0 / (2 * K);
+    const int lgh = 31 - __clz(half);
+    for (int u = tid; u < units; u += nthreads) {
+        const int gi = u * K;
+        const int j = POW2 ? (gi >> lgh) : (gi / half);
+        const int i = gi - j * half;
+        const int base = j * p;
+        T win[W];
+#pragma unroll
+        for (int c = 0; c < W / V; ++c) {
+            int off = 2 * i + c * V;
+            off = POW2 ? (off & (p - 1)) : (off % p);
+            const int e = base + off;
+            VT v = *reinterpret_cast<const VT *>(src + wx_swz_chunk(e / V) * V);
+            wx_unpack(&win[c * V], v);
+        }
+        T lo[K], hi[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            T a = tp.g[F - 1] * win[2 * k];
+            T b = tp.h[0] * win[2 * (S + k) + 1];
+#pragma unroll
+            for (int jj = 1; jj < F; ++jj) {
+                a = fma(tp.g[F - 1 - jj], win[2 * k + jj], a);
+                b = fma(tp.h[jj], win[2 * (S + k) + 1 - jj], b);
+            }
+            lo[k] = a;
+            hi[k] = b;
+        }
+#pragma unroll
+        for (int c = 0; c < K / V; ++c) {
+            wx_put_chunk<T>(dst, grow, base + i + c * V, &lo[c * V], last);
+            int io = i + S + c * V;
+            io = POW2 ? (io & (half - 1)) : (io % half);
+            wx_put_chunk<T>(dst, grow, base + half + io, &hi[c * V], last);
+        }
+    }
+}
+
+// ---- small level: node length P in {2,4,8}; a thread owns max(P,V) consecutive elements = whole nodes ----
+template <typename T, int F, int P>
+__device__ __forceinline__ void wpd_small_level(const T *__restrict__ src, T *__restrict__ dst, T *__restrict__ grow, int n0, bool last,
+                                                const Taps<T> &tp, int tid, int nthreads)
+{
+    using VT = typename WxVec<T>::type;
+    constexpr int V = WxVec<T>::N;
+    constexpr int G = P > V ? P : V;
+    const int groups = n0 / G;
+    for (int u = tid; u < groups; u += nthreads) {
+        const int e0 = u * G;
+        T v[G], o[G];
+#pragma unroll
+        for (int c = 0; c < G / V; ++c) {
+            VT q = *reinterpret_cast<const VT *>(src + wx_swz_chunk((e0 + c * V) / V) * V);
+            wx_unpack(&v[c * V], q);
+        }
+#pragma unroll
+        for (int nd = 0; nd < G / P; ++nd) {
+#pragma unroll
+            for (int i = 0; i < P / 2; ++i) {
+                T a = tp.g[F - 1] * v[nd * P + ((2 * i) & (P - 1))];
+                T b = tp.h[0] * v[nd * P + ((2 * i + 1) & (P - 1))];
+#pragma unroll
+                for (int jj = 1; jj < F; ++jj) {
+                    a = fma(tp.g[F - 1 - jj], v[nd * P + ((2 * i + jj) & (P - 1))], a);
+                    b = fma(tp.h[jj], v[nd * P + ((2 * i + 1 - jj) & (P - 1))], b);
+                }
+                o[nd * P + i] = a;
+                o[nd * P + P / 2 + i] = b;
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < G / V; ++c) wx_put_chunk<T>(dst, grow, e0 + c * V, &o[c * V], last);
+    }
+}
+
+// ---- generic level: any even node length, one output pair per thread ----------------------------------
+template <typename T, int F>
+__device__ __forceinline__ void wpd_generic_level(const T *__restrict__ src, T *__restrict__ dst, T *__restrict__ grow, int n0, int p,
+                                                  bool last, const Taps<T> &tp, int tid, int nthreads)
+{
+    const int half = p >> 1;
+    for (int gi = tid; gi < n0 / 2; gi += nthreads) {
+        const int j = gi / half;
+        const int i = gi - j * half;
+        const int base = j * p;
+        int k1 = (2 * i) % p, k2 = (2 * i + 1) % p;
+        T a = tp.g[F - 1] * src[wx_swz_elem<T>(base + k1)];
+        T b = tp.h[0] * src[wx_swz_elem<T>(base + k2)];
+#pragma unroll 4
+        for (int jj = 1; jj < F; ++jj) {
+            k1 += 1; if (k1 >= p) k1 -= p;
+            k2 -= 1; if (k2 < 0) k2 += p;
+            a = fma(tp.g[F - 1 - jj], src[wx_swz_elem<T>(base + k1)], a);
+            b = fma(tp.h[jj], src[wx_swz_elem<T>(base + k2)], b);
+        }
+        const int elo = base + i, ehi = base + half + i;
+        if (!last) { dst[wx_swz_elem<T>(elo)] = a; dst[wx_swz_elem<T>(ehi)] = b; }
+        grow[elo] = a;
+        grow[ehi] = b;
+    }
+}
+
+// ---- the fused kernel ----------------------------------------------------------------------------------
+// item = (signal k, node j0 of depth d0); the CTA computes levels d0+1..L of that node.
+template <typename T, int F>
+__global__ void __launch_bounds__(256) wpd1d_fused_k(T *__restrict__ y, const T *__restrict__ x, long n, int L, int d0, long items,
+                                                    int bufelems, Taps<T> tp)
+{
+    using C = WpdCfg<T, F>;
+    using VT = typename WxVec<T>::type;
+    constexpr int V = C::V, K = C::K;
+    extern __shared__ __align__(128) unsigned char wx_smem[];
+    T *buf0 = reinterpret_cast<T *>(wx_smem);
+    T *buf1 = buf0 + bufelems;
+    const int n0 = (int)(n >> d0);
+    const int tid = threadIdx.x, nthreads = blockDim.x;
+
+    for (long item = blockIdx.x; item < items; item += gridDim.x) {
+        const long k = item >> d0;
+        const long j0 = item & ((1L << d0) - 1);
+        T *ybase = y + k * n * (L + 1) + j0 * n0;
+        const T *src = (d0 == 0) ? (x + k * n) : (ybase + (long)d0 * n);
+
+        // stage the node (and emit level 0 when we start from the signal itself)
+        for (int c = tid; c < n0 / V; c += nthreads) {
+            VT v = wx_ldg_stream<T>(src + c * V);
+            *reinterpret_cast<VT *>(buf0 + wx_swz_chunk(c) * V) = v;
+            if (d0 == 0) wx_stg_stream(ybase + c * V, v);
+        }
+        __syncthreads();
+
+        T *a = buf0, *b = buf1;
+        const int nlev = L - d0;
+        for (int l = 0; l < nlev; ++l) {
+            const int p = n0 >> l;
+            const bool last = (l == nlev - 1);
+            T *grow = ybase + (long)(d0 + l + 1) * n;
+            const int half = p >> 1;
+            const bool pow2 = (p & (p - 1)) == 0;
+            if (half % K == 0) {
+                if (pow2) wpd_wide_level<T, F, true>(a, b, grow, n0, p, last, tp, tid, nthreads);
+                else      wpd_wide_level<T, F, false>(a, b, grow, n0, p, last, tp, tid, nthreads);
+            } else if (p == 2 && n0 % (V > 2 ? V : 2) == 0) {
+                wpd_small_level<T, F, 2>(a, b, grow, n0, last, tp, tid, nthreads);
+            } else if (p == 4) {
+                wpd_small_level<T, F, 4>(a, b, grow, n0, last, tp, tid, nthreads);
+            } else if (p == 8) {
+                wpd_small_level<T, F, 8>(a, b, grow, n0, last, tp, tid, nthreads);
+            } else {
+                wpd_generic_level<T, F>(a, b, grow, n0, p, last, tp, tid, nthreads);
+            }
+            __syncthreads();
+            T *t = a; a = b; b = t;
+        }
+    }
+}
+
+// one level for the whole batch through the generic step kernel:  level i of y -> level i+1 of y
+template <typename T>
+int wpd_level_generic(T *y, long n, int L, long N, int i, const Taps<T> &t, cudaStream_t s)
+{
+    const long np = n >> i, nr = np / 2, str = n * (L + 1);
+    const T *v = y + (long)i * n;
+    T *w = y + (long)(i + 1) * n;
+    return wx_launch_dwt_step<T>(View<T>{w, 1, np, str, 0}, View<T>{w + nr, 1, np, str, 0}, View<const T>{v, 1, np, str, 0}, np,
+                                 Batch{1L << i, N, 1, false}, t, s);
+}
+
+template <typename T, int F>
+int wpd1d_launch_fused(T *y, const T *x, long n, int L, long N, int d0, const Taps<T> &t, cudaStream_t s)
+{
+    using C = WpdCfg<T, F>;
+    WxDev dv; int rc = wx_devinfo(dv); if (rc) return rc;
+    const long n0 = n >> d0;
+    const long bufbytes = ((n0 * (long)sizeof(T) + 127) / 128) * 128;
+    const size_t smem = (size_t)2 * bufbytes;
+    long units = n0 / (2 * C::K);
+    int threads = (int)((units + 31) / 32 * 32);
+    if (threads < 64) threads = 64;
+    if (threads > 256) threads = 256;
+    auto kern = wpd1d_fused_k<T, F>;
+    WX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    WX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
+    if (occ < 1) return wx_fail(WX_EUNSUPPORTED, "wpd1d fused kernel does not fit (smem %zu)", smem);
+    const long items = N << d0;
+    long blocks = (long)dv.sms * occ;
+    if (blocks > items) blocks = items;
+    kern<<<(unsigned)blocks, threads, smem, s>>>(y, x, n, L, d0, items, (int)(bufbytes / sizeof(T)), t);
+    WX_LAUNCHED();
+    return WX_OK;
+}
+
+template <typename T>
+int wpd1d_impl(T *y, const T *x, long n, int L, long N, const double *h, const double *g, int F, void *stream)
+{
+    cudaStream_t s = (cudaStream_t)stream;
+    WX_REQUIRE(n >= 1 && N >= 0, "wpd: bad sizes n=%ld N=%ld", n, N);
+    // reference: @assert 0 <= L <= maxtransformlevels(x)   DWT.jl:137
+    WX_REQUIRE(L >= 0 && L <= wx_maxlevels(n), "AssertionError: 0 <= L <= maxtransformlevels(x) (n=%ld, L=%d)", n, L);
+    if (N == 0) return WX_OK;
+    WX_REQUIRE(y && x, "null signal pointer");
+    Taps<T> t; int rc = wx_make_taps(t, h, g, F); if (rc) return rc;
+    WxDev dv; rc = wx_devinfo(dv); if (rc) return rc;
+
+    constexpr int V = WxVec<T>::N;
+    const bool aligned = (((uintptr_t)y | (uintptr_t)x) & 15) == 0;
+    const bool fusedF = (F == 2 || F == 4 || F == 6 || F == 8 || F == 10 || F == 12 || F == 16 || F == 20);
+    // smallest start depth whose node fits the ping-pong buffers
+    int d0 = 0;
+    while (d0 < L && (size_t)2 * (((n >> d0) * sizeof(T) + 127) / 128 * 128) > dv.smem_optin) ++d0;
+    const long n0 = n >> d0;
+    const bool fits = (size_t)2 * ((n0 * sizeof(T) + 127) / 128 * 128) <= dv.smem_optin;
+    const bool fused = L > 0 && aligned && fusedF && fits && n0 % (2 * V) == 0 && n < (1L << 30) && d0 < L;
+
+    if (!fused || d0 > 0) {
+        // level 0 = x                                                                DWT.jl:142
+        rc = wx_launch_copy<T>(View<T>{y, 1, n * (L + 1), 0, 0}, View<const T>{x, 1, n, 0, 0}, n, Batch{N, 1, 1, false}, s);
+        if (rc) return rc;
+    }
+    const int pre = fused ? d0 : L;
+    for (int i = 0; i < pre; ++i) { rc = wpd_level_generic<T>(y, n, L, N, i, t, s); if (rc) return rc; }
+    if (!fused) return WX_OK;
+    switch (F) {
+        case 2:  return wpd1d_launch_fused<T, 2>(y, x, n, L, N, d0, t, s);
+        case 4:  return wpd1d_launch_fused<T, 4>(y, x, n, L, N, d0, t, s);
+        case 6:  return wpd1d_launch_fused<T, 6>(y, x, n, L, N, d0, t, s);
+        case 8:  return wpd1d_launch_fused<T, 8>(y, x, n, L, N, d0, t, s);
+        case 10: return wpd1d_launch_fused<T, 10>(y, x, n, L, N, d0, t, s);
+        case 12: return wpd1d_launch_fused<T, 12>(y, x, n, L, N, d0, t, s);
+        case 16: return wpd1d_launch_fused<T, 16>(y, x, n, L, N, d0, t, s);
+        case 20: return wpd1d_launch_fused<T, 20>(y, x, n, L, N, d0, t, s);
+    }
+    return wx_fail(WX_EUNSUPPORTED, "unreachable");
+}
+
+}  // namespace
+
+extern "C" {
+int wx_wpd1d_f64(double *y, const double *x, long n, int L, long N, const double *h, const double *g, int F, void *stream)
+{
+    return wpd1d_impl<double>(y, x, n, L, N, h, g, F, stream);
+}
+int wx_wpd1d_f32(float *y, const float *x, long n, int L, long N, const double *h, const double *g, int F, void *stream)
+{
+    return wpd1d_impl<float>(y, x, n, L, N, h, g, F, stream);
+}
+}
