@@ -112,3 +112,35 @@ int wx_device_sync(void)
 }
 
 }  // extern "C"
+
+// ---- TMA row maps (see wx_tma.cuh) ----------------------------------------------------------------------
+#include "wx_tma.cuh"
+typedef CUresult (*wx_encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                       const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                       CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int wx_make_rowmap(CUtensorMap *map, const void *base, size_t elt, long rows, long boxrows)
+{
+    static wx_encode_tiled_fn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (wx_encode_tiled_fn)p;
+        else
+            cudaGetLastError();
+    }
+    if (!fn) return wx_fail(WX_EUNSUPPORTED, "cuTensorMapEncodeTiled unavailable");
+    if (((uintptr_t)base & 15) != 0 || rows < 1 || boxrows < 1 || boxrows > 256) return wx_fail(WX_EUNSUPPORTED, "row map: bad geometry");
+    const cuuint64_t gdim[2] = {(cuuint64_t)(128 / elt), (cuuint64_t)rows};
+    const cuuint64_t gstr[1] = {128};
+    const cuuint32_t box[2] = {(cuuint32_t)(128 / elt), (cuuint32_t)boxrows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUtensorMapDataType dt = elt == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    CUresult r = fn(map, dt, 2, const_cast<void *>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return wx_fail(WX_EUNSUPPORTED, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return WX_OK;
+}

@@ -17,6 +17,8 @@
 //    contiguous across the warp), level 0 is copied while the signal is staged.
 //  * accumulation order per output is the reference's tap order (j ascending); products use FMA.
 #include "wx_steps.cuh"
+#include "wx_tma.cuh"
+#include <cstdlib>
 
 namespace {
 
@@ -40,18 +42,20 @@ __device__ __forceinline__ double2 wx_pack(const double *d) { return make_double
 __device__ __forceinline__ float4 wx_pack(const float *d) { return make_float4(d[0], d[1], d[2], d[3]); }
 
 // store one 16 B chunk of outputs (element index e, chunk aligned) to the next-level smem buffer and to HBM
-template <typename T>
+// GST = true : outputs go to HBM straight from registers (and to smem unless this is the last level)
+// GST = false: outputs go to smem only; the level row is written to HBM by a TMA bulk store of the smem buffer
+template <typename T, bool GST>
 __device__ __forceinline__ void wx_put_chunk(T *dst, T *grow, int e, const T *vals, bool last)
 {
     constexpr int V = WxVec<T>::N;
     using VT = typename WxVec<T>::type;
     VT v = wx_pack(vals);
-    if (!last) *reinterpret_cast<VT *>(dst + wx_swz_chunk(e / V) * V) = v;
-    wx_stg_stream(grow + e, v);
+    if (!GST || !last) *reinterpret_cast<VT *>(dst + wx_swz_chunk(e / V) * V) = v;
+    if (GST) wx_stg_stream(grow + e, v);
 }
 
 // ---- wide level: node half-length is a multiple of K -------------------------------------------------
-template <typename T, int F, bool POW2>
+template <typename T, int F, bool POW2, bool GST>
 __device__ __forceinline__ void wpd_wide_level(const T *__restrict__ src, T *__restrict__ dst, T *__restrict__ grow, int n0, int p,
                                                bool last, const Taps<T> &tp, int tid, int nthreads)
 {
@@ -90,16 +94,16 @@ __device__ __forceinline__ void wpd_wide_level(const T *__restrict__ src, T *__r
         }
 #pragma unroll
         for (int c = 0; c < K / V; ++c) {
-            wx_put_chunk<T>(dst, grow, base + i + c * V, &lo[c * V], last);
+            wx_put_chunk<T, GST>(dst, grow, base + i + c * V, &lo[c * V], last);
             int io = i + S + c * V;
             io = POW2 ? (io & (half - 1)) : (io % half);
-            wx_put_chunk<T>(dst, grow, base + half + io, &hi[c * V], last);
+            wx_put_chunk<T, GST>(dst, grow, base + half + io, &hi[c * V], last);
         }
     }
 }
 
 // ---- small level: node length P in {2,4,8}; a thread owns max(P,V) consecutive elements = whole nodes ----
-template <typename T, int F, int P>
+template <typename T, int F, int P, bool GST>
 __device__ __forceinline__ void wpd_small_level(const T *__restrict__ src, T *__restrict__ dst, T *__restrict__ grow, int n0, bool last,
                                                 const Taps<T> &tp, int tid, int nthreads)
 {
@@ -131,12 +135,12 @@ __device__ __forceinline__ void wpd_small_level(const T *__restrict__ src, T *__
             }
         }
 #pragma unroll
-        for (int c = 0; c < G / V; ++c) wx_put_chunk<T>(dst, grow, e0 + c * V, &o[c * V], last);
+        for (int c = 0; c < G / V; ++c) wx_put_chunk<T, GST>(dst, grow, e0 + c * V, &o[c * V], last);
     }
 }
 
 // ---- generic level: any even node length, one output pair per thread ----------------------------------
-template <typename T, int F>
+template <typename T, int F, bool GST>
 __device__ __forceinline__ void wpd_generic_level(const T *__restrict__ src, T *__restrict__ dst, T *__restrict__ grow, int n0, int p,
                                                   bool last, const Taps<T> &tp, int tid, int nthreads)
 {
@@ -156,9 +160,31 @@ __device__ __forceinline__ void wpd_generic_level(const T *__restrict__ src, T *
             b = fma(tp.h[jj], src[wx_swz_elem<T>(base + k2)], b);
         }
         const int elo = base + i, ehi = base + half + i;
-        if (!last) { dst[wx_swz_elem<T>(elo)] = a; dst[wx_swz_elem<T>(ehi)] = b; }
-        grow[elo] = a;
-        grow[ehi] = b;
+        if (!GST || !last) { dst[wx_swz_elem<T>(elo)] = a; dst[wx_swz_elem<T>(ehi)] = b; }
+        if (GST) { grow[elo] = a; grow[ehi] = b; }
+    }
+}
+
+// one decomposition level of every node of the staged signal: picks the wide / small / generic path
+template <typename T, int F, bool GST>
+__device__ __forceinline__ void wpd_level(const T *__restrict__ a, T *__restrict__ b, T *__restrict__ grow, int n0, int p, bool last,
+                                          const Taps<T> &tp, int tid, int nthreads)
+{
+    using C = WpdCfg<T, F>;
+    constexpr int V = C::V, K = C::K;
+    const int half = p >> 1;
+    const bool pow2 = (p & (p - 1)) == 0;
+    if (half % K == 0) {
+        if (pow2) wpd_wide_level<T, F, true, GST>(a, b, grow, n0, p, last, tp, tid, nthreads);
+        else      wpd_wide_level<T, F, false, GST>(a, b, grow, n0, p, last, tp, tid, nthreads);
+    } else if (p == 2 && n0 % (V > 2 ? V : 2) == 0) {
+        wpd_small_level<T, F, 2, GST>(a, b, grow, n0, last, tp, tid, nthreads);
+    } else if (p == 4) {
+        wpd_small_level<T, F, 4, GST>(a, b, grow, n0, last, tp, tid, nthreads);
+    } else if (p == 8) {
+        wpd_small_level<T, F, 8, GST>(a, b, grow, n0, last, tp, tid, nthreads);
+    } else {
+        wpd_generic_level<T, F, GST>(a, b, grow, n0, p, last, tp, tid, nthreads);
     }
 }
 
@@ -197,24 +223,78 @@ __global__ void __launch_bounds__(256) wpd1d_fused_k(T *__restrict__ y, const T 
             const int p = n0 >> l;
             const bool last = (l == nlev - 1);
             T *grow = ybase + (long)(d0 + l + 1) * n;
-            const int half = p >> 1;
-            const bool pow2 = (p & (p - 1)) == 0;
-            if (half % K == 0) {
-                if (pow2) wpd_wide_level<T, F, true>(a, b, grow, n0, p, last, tp, tid, nthreads);
-                else      wpd_wide_level<T, F, false>(a, b, grow, n0, p, last, tp, tid, nthreads);
-            } else if (p == 2 && n0 % (V > 2 ? V : 2) == 0) {
-                wpd_small_level<T, F, 2>(a, b, grow, n0, last, tp, tid, nthreads);
-            } else if (p == 4) {
-                wpd_small_level<T, F, 4>(a, b, grow, n0, last, tp, tid, nthreads);
-            } else if (p == 8) {
-                wpd_small_level<T, F, 8>(a, b, grow, n0, last, tp, tid, nthreads);
-            } else {
-                wpd_generic_level<T, F>(a, b, grow, n0, p, last, tp, tid, nthreads);
-            }
+            wpd_level<T, F, true>(a, b, grow, n0, p, last, tp, tid, nthreads);
             __syncthreads();
             T *t = a; a = b; b = t;
         }
     }
+}
+
+
+// ---- the fused kernel, TMA variant ----------------------------------------------------------------------
+// Same level code, but the SM's load/store units only ever touch shared memory: the node is staged by a TMA
+// tensor load (SWIZZLE_128B == wx_swz_chunk) and every level row -- including the level-0 copy -- leaves through
+// a TMA bulk tensor store of the smem buffer, issued by one thread and overlapped with the next level's math.
+// Buffer reuse: store S_l reads buffer b_l during level l+1; thread 0 waits for it (bulk wait_group.read) right
+// before the barrier that lets level l+2 overwrite that buffer, so the wait is normally already satisfied.
+// Tensor maps view x and y as 2-D arrays of 128-byte rows: coordinates {0, row}.
+template <typename T, int F>
+__global__ void __launch_bounds__(256) wpd1d_tma_k(const __grid_constant__ CUtensorMap mapx, const __grid_constant__ CUtensorMap mapy, long n, int L,
+                                                  int d0, long items, int bufelems, int boxrows, Taps<T> tp)
+{
+    constexpr int RE = 128 / (int)sizeof(T);          // elements per 128-byte row
+    extern __shared__ unsigned char wx_smem_raw[];
+    __shared__ __align__(8) unsigned long long bar;
+    T *buf0 = reinterpret_cast<T *>((reinterpret_cast<uintptr_t>(wx_smem_raw) + 1023) & ~(uintptr_t)1023);
+    T *buf1 = buf0 + bufelems;
+    const int n0 = (int)(n >> d0);
+    const int tid = threadIdx.x, nthreads = blockDim.x;
+    const int noderows = n0 / RE, nbox = noderows / boxrows;
+    const long sigrows = n / RE;
+
+    if (tid == 0) {
+        wx_mbar_init(&bar, 1);
+        wx_fence_mbar_init();
+    }
+    __syncthreads();
+    unsigned parity = 0;
+
+    for (long item = blockIdx.x; item < items; item += gridDim.x) {
+        const long k = item >> d0;
+        const long j0 = item & ((1L << d0) - 1);
+        const long yrow0 = k * sigrows * (L + 1) + j0 * noderows;      // row of level 0, this node
+        if (tid == 0) {
+            wx_bulk_wait_read0();                                      // stores of the previous item have released smem
+            wx_mbar_expect_tx(&bar, (unsigned)(n0 * sizeof(T)));
+            for (int bx = 0; bx < nbox; ++bx) {
+                if (d0 == 0) wx_tma_load_2d(buf0 + (long)bx * boxrows * RE, &mapx, 0, (int)(k * sigrows + (long)bx * boxrows), &bar);
+                else         wx_tma_load_2d(buf0 + (long)bx * boxrows * RE, &mapy, 0, (int)(yrow0 + (long)d0 * sigrows + (long)bx * boxrows), &bar);
+            }
+        }
+        wx_mbar_wait(&bar, parity);
+        parity ^= 1;
+        if (d0 == 0 && tid == 0) {                                     // level 0 = x   (DWT.jl:142)
+            for (int bx = 0; bx < nbox; ++bx) wx_tma_store_2d(&mapy, 0, (int)(yrow0 + (long)bx * boxrows), buf0 + (long)bx * boxrows * RE);
+            wx_bulk_commit();
+        }
+
+        T *a = buf0, *b = buf1;
+        const int nlev = L - d0;
+        for (int l = 0; l < nlev; ++l) {
+            const int p = n0 >> l;
+            wpd_level<T, F, false>(a, b, nullptr, n0, p, false, tp, tid, nthreads);
+            wx_fence_proxy_async();                                    // my smem writes -> visible to the TMA engine
+            if (tid == 0) wx_bulk_wait_read0();                        // buffer `a` is no longer being read by an older store
+            __syncthreads();
+            if (tid == 0) {
+                const long row = yrow0 + (long)(d0 + l + 1) * sigrows;
+                for (int bx = 0; bx < nbox; ++bx) wx_tma_store_2d(&mapy, 0, (int)(row + (long)bx * boxrows), b + (long)bx * boxrows * RE);
+                wx_bulk_commit();
+            }
+            T *t = a; a = b; b = t;
+        }
+    }
+    if (tid == 0) wx_bulk_wait_all();
 }
 
 // one level for the whole batch through the generic step kernel:  level i of y -> level i+1 of y
@@ -253,6 +333,46 @@ int wpd1d_launch_fused(T *y, const T *x, long n, int L, long N, int d0, const Ta
     return WX_OK;
 }
 
+
+template <typename T, int F>
+int wpd1d_launch_tma(T *y, const T *x, long n, int L, long N, int d0, const Taps<T> &t, cudaStream_t s, bool *handled)
+{
+    using C = WpdCfg<T, F>;
+    *handled = false;
+    constexpr long RE = 128 / (long)sizeof(T);
+    const long n0 = n >> d0;
+    if (n0 % RE != 0 || n % RE != 0) return WX_OK;
+    const long xrows = N * (n / RE), yrows = xrows * (L + 1);
+    if (yrows >= (1L << 31)) return WX_OK;
+    const long noderows = n0 / RE;
+    long boxrows = noderows < 256 ? noderows : 256;
+    while (noderows % boxrows) --boxrows;
+    if (noderows / boxrows > 64) return WX_OK;
+    CUtensorMap mx, my;
+    if (wx_make_rowmap(&mx, (const void *)x, sizeof(T), xrows, boxrows) != WX_OK) return WX_OK;   // no TMA -> LSU variant
+    if (wx_make_rowmap(&my, (const void *)y, sizeof(T), yrows, boxrows) != WX_OK) return WX_OK;
+    WxDev dv; int rc = wx_devinfo(dv); if (rc) return rc;
+    const long bufbytes = ((n0 * (long)sizeof(T) + 1023) / 1024) * 1024;
+    const size_t smem = (size_t)2 * bufbytes + 1024;
+    if (smem > dv.smem_optin) return WX_OK;
+    long units = n0 / (2 * C::K);
+    int threads = (int)((units + 31) / 32 * 32);
+    if (threads < 64) threads = 64;
+    if (threads > 256) threads = 256;
+    auto kern = wpd1d_tma_k<T, F>;
+    WX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    WX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
+    if (occ < 1) return WX_OK;
+    const long items = N << d0;
+    long blocks = (long)dv.sms * occ;
+    if (blocks > items) blocks = items;
+    kern<<<(unsigned)blocks, threads, smem, s>>>(mx, my, n, L, d0, items, (int)(bufbytes / sizeof(T)), (int)boxrows, t);
+    WX_LAUNCHED();
+    *handled = true;
+    return WX_OK;
+}
+
 template <typename T>
 int wpd1d_impl(T *y, const T *x, long n, int L, long N, const double *h, const double *g, int F, void *stream)
 {
@@ -283,16 +403,18 @@ int wpd1d_impl(T *y, const T *x, long n, int L, long N, const double *h, const d
     const int pre = fused ? d0 : L;
     for (int i = 0; i < pre; ++i) { rc = wpd_level_generic<T>(y, n, L, N, i, t, s); if (rc) return rc; }
     if (!fused) return WX_OK;
-    switch (F) {
-        case 2:  return wpd1d_launch_fused<T, 2>(y, x, n, L, N, d0, t, s);
-        case 4:  return wpd1d_launch_fused<T, 4>(y, x, n, L, N, d0, t, s);
-        case 6:  return wpd1d_launch_fused<T, 6>(y, x, n, L, N, d0, t, s);
-        case 8:  return wpd1d_launch_fused<T, 8>(y, x, n, L, N, d0, t, s);
-        case 10: return wpd1d_launch_fused<T, 10>(y, x, n, L, N, d0, t, s);
-        case 12: return wpd1d_launch_fused<T, 12>(y, x, n, L, N, d0, t, s);
-        case 16: return wpd1d_launch_fused<T, 16>(y, x, n, L, N, d0, t, s);
-        case 20: return wpd1d_launch_fused<T, 20>(y, x, n, L, N, d0, t, s);
+    static const bool no_tma = getenv("WX_B200_NO_TMA") != nullptr;       // debugging / A-B measurements only
+#define WX_WPD_CASE(FF)                                                                             \
+    case FF: {                                                                                      \
+        bool handled = false;                                                                       \
+        if (!no_tma) { rc = wpd1d_launch_tma<T, FF>(y, x, n, L, N, d0, t, s, &handled); if (rc) return rc; } \
+        if (handled) return WX_OK;                                                                  \
+        return wpd1d_launch_fused<T, FF>(y, x, n, L, N, d0, t, s);                                  \
     }
+    switch (F) {
+        WX_WPD_CASE(2) WX_WPD_CASE(4) WX_WPD_CASE(6) WX_WPD_CASE(8) WX_WPD_CASE(10) WX_WPD_CASE(12) WX_WPD_CASE(16) WX_WPD_CASE(20)
+    }
+#undef WX_WPD_CASE
     return wx_fail(WX_EUNSUPPORTED, "unreachable");
 }
 
