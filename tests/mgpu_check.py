@@ -1,0 +1,65 @@
+"""Multi-GPU check, one process per GPU (launch with torchrun): sharding the batch changes nothing bitwise for the
+transforms, and the NCCL all-reduced JBB / LSDB cost trees equal the single-GPU trees on the concatenated batch.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/mgpu_check.py
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    import waveletsext_b200 as wx
+    from test_gpu_bestbasis import signals
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    wt = wx.wavelet("db4")
+    n, N = 256, 1000
+    X = torch.from_numpy(signals(n, N, 77)).to(dev)             # same global batch everywhere
+    lo, hi = wx.dist.shard_range(N)
+    xl = X[lo:hi].contiguous()
+    yl = wx.wpdall(xl, wt)                                       # shard-local, no collective
+    yfull = wx.wpdall(X, wt)
+    assert torch.equal(yl, yfull[lo:hi]), "sharded wpdall differs from the single-GPU result"
+    for method in (wx.JBB(), wx.LSDB()):
+        c_sh = wx.tree_costs(yl, method)                         # all-reduce inside
+        dist.barrier()
+        # single-GPU reference on the concatenated batch: bypass the process group
+        saved = wx.dist.is_dist
+        wx.dist.is_dist = lambda group=None: False
+        try:
+            c_one = wx.tree_costs(yfull, method)
+        finally:
+            wx.dist.is_dist = saved
+        rel = np.abs(c_sh - c_one).max() / np.abs(c_one).max()
+        assert rel <= 1e-11, (type(method).__name__, rel)
+        t_sh = wx.bestbasis_treeselection(c_sh.copy(), n)
+        t_one = wx.bestbasis_treeselection(c_one.copy(), n)
+        assert np.array_equal(t_sh, t_one), type(method).__name__
+        tt = torch.from_numpy(t_sh.astype(np.int64)).to(dev)
+        a, b = tt.clone(), tt.clone()
+        dist.all_reduce(a, op=dist.ReduceOp.MIN); dist.all_reduce(b, op=dist.ReduceOp.MAX)
+        assert torch.equal(a, b), "ranks disagree on the tree"
+        # downstream: best-basis coefficients and inverse, shard-local
+        coef = wx.getbasiscoefall(yl, t_sh)
+        xr = wx.iwptall(coef, wt, t_sh)
+        assert (xr - xl).abs().max().item() <= 1e-10 * xl.abs().max().item()
+        if rank == 0:
+            print(f"{type(method).__name__}: sharded == single (rel {rel:.2e}), tree nodes {int(t_sh.sum())}", flush=True)
+    dist.barrier()
+    if rank == 0:
+        print(f"mgpu_check ok on {world} GPUs", flush=True)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

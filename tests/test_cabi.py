@@ -1,0 +1,64 @@
+"""The C-ABI library loads and exports every symbol include/wx_b200.h declares; without a GPU every compute entry point
+fails loudly (no CPU fallback).  CPU only: no compute call is expected to succeed here."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_header_symbols_exported(wx):
+    from waveletsext_b200 import _lib
+    protos = _lib.parse_header()
+    assert len(protos) >= 60
+    l = C.CDLL(_lib.LIBPATH)
+    missing = [n for n in protos if not hasattr(l, n)]
+    assert not missing, f"libwx_b200.so lacks {missing}"
+    for stem in ("wx_wpd1d", "wx_wpd2d", "wx_iwpt1d", "wx_rwt", "wx_irwt", "wx_dwt_step", "wx_idwt_step", "wx_sdwt_step", "wx_acdwt_step",
+                 "wx_gather_basis", "wx_jbb_moments", "wx_lsdb_pass1", "wx_wpdall_host"):
+        assert stem + "_f64" in protos and stem + "_f32" in protos
+    assert _lib.lib().wx_version() >= 100
+
+
+def test_library_is_sm100a_only():
+    """the product is built for sm_100a and nothing else (no multi-arch dispatch)"""
+    import shutil, subprocess
+    so = os.path.join(ROOT, "waveletsext.jl_b200", "libwx_b200.so")
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run([cuobjdump, "-lelf", so], capture_output=True, text=True).stdout
+    archs = {ln.split(".")[-2] for ln in out.splitlines() if ".cubin" in ln}
+    assert archs == {"sm_100a"}, archs
+
+
+def test_argument_validation_needs_no_gpu(wx):
+    """argument errors the reference raises with @assert are detected before any CUDA work"""
+    from waveletsext_b200 import _lib
+    h = np.ones(8); g = np.ones(8)
+    rc = _lib.lib().wx_wpd1d_f64(0, 0, 24, 4, 3, h.ctypes.data, g.ctypes.data, 8, 0)     # L > maxtransformlevels(24) = 3
+    assert rc == _lib.WX_EINVAL and "maxtransformlevels" in _lib.last_error()
+    rc = _lib.lib().wx_rwt_f64(0, 2, 0, 0, 0, 16, 0, 3, h.ctypes.data, g.ctypes.data, 8, 0)
+    assert rc == _lib.WX_EINVAL and "L must be >= 1" in _lib.last_error()
+    buf = np.zeros(8)
+    rc = _lib.lib().wx_isdwt_step_shift_f64(buf.ctypes.data, buf.ctypes.data, buf.ctypes.data, 8, 0, 1, 0, h.ctypes.data, g.ctypes.data, 8, 0, 0)
+    assert rc == _lib.WX_EINVAL and "sv" in _lib.last_error()
+    # empty batch: nothing to do, success even without a device
+    assert _lib.lib().wx_wpd1d_f64(0, 0, 16, 4, 0, h.ctypes.data, g.ctypes.data, 8, 0) == 0
+
+
+def test_compute_fails_loudly_without_gpu(wx):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from waveletsext_b200 import _lib
+    x = np.zeros(64); y = np.zeros(64 * 3)
+    h = np.ones(2); g = np.ones(2)
+    rc = _lib.lib().wx_wpd1d_f64(y.ctypes.data, x.ctypes.data, 64, 2, 1, h.ctypes.data, g.ctypes.data, 2, 0)
+    assert rc == _lib.WX_ECUDA
+    with pytest.raises(_lib.WxError):
+        _lib.check(rc)
+    with pytest.raises((_lib.WxError, RuntimeError, AssertionError)):
+        wx.host.wpdall_host(np.zeros((2, 8)), wx.wavelet("haar"), device=0)
