@@ -41,7 +41,11 @@ def main():
         finally:
             wx.dist.is_dist = saved
         rel = np.abs(c_sh - c_one).max() / np.abs(c_one).max()
-        assert rel <= 1e-11, (type(method).__name__, rel)
+        # JBB costs are smooth in the moments: reassociating the sum moves them by ~1e-16.  LSDB bins every sample on a
+        # grid derived from the moments, so a 1-ulp change of the grid can move a sample across a bin edge: costs agree
+        # to O(1/N) only (DESIGN.md "LSDB reproducibility"); the selected tree must still be identical.
+        tol = 1e-11 if isinstance(method, wx.JBB) else 2e-3
+        assert rel <= tol, (type(method).__name__, rel)
         t_sh = wx.bestbasis_treeselection(c_sh.copy(), n)
         t_one = wx.bestbasis_treeselection(c_one.copy(), n)
         assert np.array_equal(t_sh, t_one), type(method).__name__
