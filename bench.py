@@ -222,6 +222,9 @@ def main():
     e2e = None
     if not a.no_e2e:
         Ne = N
+        per_sig = (L + 2) * n * esz
+        while Ne > 1024 and Ne * per_sig * world > 48e9:        # keep the pinned host footprint of all ranks under ~48 GB
+            Ne //= 2
         xh = yh = None
         while Ne >= 1024:
             try:
