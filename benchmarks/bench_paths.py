@@ -1,0 +1,138 @@
+#!/usr/bin/env python
+"""Secondary measurements for the other hot-path rows of SURVEY.md section 8 (configs 2-5 of BASELINE.json): device-timed,
+inputs resident, algorithmic bytes / CUDA-event time against the measured HBM peak.  One JSON line per path.
+
+    python benchmarks/bench_paths.py [--only name,...] [--scale S]
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import waveletsext_b200 as wx  # noqa: E402
+
+
+def peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        return 6650.0
+
+
+def timeit(fn, steps=5, warmup=2):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    l0 = wx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps, (wx.launch_count() - l0) // steps
+
+
+def report(name, ms, launches, alg_bytes, units, unit_name, extra=None):
+    gbs = alg_bytes / (ms * 1e-3) / 1e9
+    out = {"path": name, "ms": round(ms, 4), "launches_per_call": launches, "algorithmic_GB": round(alg_bytes / 1e9, 3), "achieved_GBps": round(gbs, 1),
+           "frac_of_measured_hbm_peak": round(gbs / peak(), 4), unit_name: round(units / (ms * 1e-3) / 1e9, 3)}
+    if extra:
+        out.update(extra)
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default="")
+    ap.add_argument("--scale", type=float, default=1.0, help="scale the batch sizes (1.0 = the per-GPU sizes of BASELINE.json)")
+    a = ap.parse_args()
+    only = set(filter(None, a.only.split(",")))
+    dev = torch.device("cuda:0")
+    gen = torch.Generator(device=dev).manual_seed(7)
+    want = lambda nm: (not only) or nm in only
+
+    for dt, es in ((torch.float64, 8), (torch.float32, 4)):
+        tag = "f64" if es == 8 else "f32"
+        # config 2: wpdall + iwptall round trip, 65536 x 4096, L = 12
+        n, N, L = 4096, int(65536 * a.scale), 12
+        for wname in ("db4", "coif4", "sym8"):
+            if want(f"iwptall_{tag}_{wname}") or want(f"wpdall_{tag}_{wname}"):
+                wt = wx.wavelet(wname)
+                x = torch.randn((N, n), dtype=dt, device=dev, generator=gen)
+                y = torch.empty((N, L + 1, n), dtype=dt, device=dev)
+                if want(f"wpdall_{tag}_{wname}"):
+                    ms, nl = timeit(lambda: wx.dwt._wpd_batch(x, wt, L, y))
+                    report(f"wpdall_{tag}_{wname}", ms, nl, es * n * N * (L + 2), n * N, "GSamples_per_s")
+                if want(f"iwptall_{tag}_{wname}"):
+                    wx.dwt._wpd_batch(x, wt, L, y)
+                    leaves = y[:, L].contiguous()
+                    del y
+                    out = torch.empty_like(leaves)
+                    tree = wx.maketree(n, L, "full")
+                    ms, nl = timeit(lambda: wx.dwt._tree_batch("iwpt", leaves, wt, tree, out))
+                    err = float((out - x).abs().max() / x.abs().max())
+                    report(f"iwptall_{tag}_{wname}", ms, nl, 2 * es * n * N, n * N, "GSamples_per_s", {"roundtrip_relerr": err})
+                    del leaves, out
+                del x
+                torch.cuda.empty_cache()
+        # config 3: swpd / acwpd 2048 signals x 2048 samples per GPU (16384 over 8 GPUs), L = 8
+        n, N, L = 2048, int(2048 * a.scale), 8
+        for nm, fn in (("swpdall", wx.swt), ("acwpdall", wx.acwt)):
+            if want(f"{nm}_{tag}"):
+                wt = wx.wavelet("db4")
+                x = torch.randn((N, n), dtype=dt, device=dev, generator=gen)
+                xw = torch.empty((N, (1 << (L + 1)) - 1, n), dtype=dt, device=dev)
+                ac = nm.startswith("ac")
+                ms, nl = timeit(lambda: wx._rwt.forward(ac, "wpd", x, wt, L, xw), steps=3, warmup=1)
+                report(f"{nm}_{tag}", ms, nl, es * n * N * (1 << (L + 1)), n * N, "GSamples_per_s")
+                del x, xw
+                torch.cuda.empty_cache()
+        # config 4: 2-D wpd, 4096 images 512 x 512, L = 5
+        m = n2 = 512
+        N, L = int(4096 * a.scale), 5
+        for wname in ("haar", "db4"):
+            if want(f"wpd2d_{tag}_{wname}"):
+                wt = wx.wavelet(wname)
+                x = torch.randn((N, n2, m), dtype=dt, device=dev, generator=gen)
+                y = torch.empty((N, L + 1, n2, m), dtype=dt, device=dev)
+                ms, nl = timeit(lambda: wx.dwt._wpd_batch(x, wt, L, y), steps=3, warmup=1)
+                report(f"wpd2d_{tag}_{wname}", ms, nl, es * m * n2 * N * (L + 2), m * n2 * N, "GPixels_per_s")
+                del x, y
+                torch.cuda.empty_cache()
+    # config 5: JBB / LSDB best basis + getbasiscoefall + iwptall on 131072 signals x 1024 per GPU (1M over 8 GPUs)
+    n, N, L = 1024, int(131072 * a.scale), 10
+    if want("jbb") or want("lsdb") or want("basis_iwpt"):
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        wt = wx.wavelet("db4")
+        t = torch.arange(n, device=dev, dtype=torch.float64) / n
+        hs = 4 * torch.sin(4 * np.pi * t) - torch.sign(t - 0.3) - torch.sign(0.72 - t)
+        x = hs[None, :].repeat(N, 1)
+        idx = (torch.arange(n, device=dev)[None, :] - 2 * (torch.arange(N, device=dev)[:, None] % n)) % n
+        x = torch.gather(x, 1, idx) + 0.5 * torch.randn((N, n), dtype=torch.float64, device=dev, generator=gen)
+        Xw = wx.wpdall(x, wt, L)
+        K = L + 1
+        tree = None
+        if want("jbb"):
+            ms, nl = timeit(lambda: wx.tree_costs(Xw, wx.JBB()), steps=3, warmup=1)
+            report("jbb_tree_costs_f64", ms, nl, 8 * n * K * N, n * N, "GSamples_per_s")
+            tree = wx.bestbasistree(Xw, wx.JBB())
+        if want("lsdb"):
+            ms, nl = timeit(lambda: wx.tree_costs(Xw, wx.LSDB()), steps=2, warmup=1)
+            report("lsdb_tree_costs_f64", ms, nl, 3 * 8 * n * K * N, n * N, "GSamples_per_s")
+        if want("basis_iwpt"):
+            if tree is None:
+                tree = wx.bestbasistree(Xw, wx.JBB())
+            ms, nl = timeit(lambda: wx.iwptall(wx.getbasiscoefall(Xw, tree), wt, tree), steps=3, warmup=1)
+            xr = wx.iwptall(wx.getbasiscoefall(Xw, tree), wt, tree)
+            report("getbasiscoefall+iwptall_f64", ms, nl, 3 * 8 * n * N, n * N, "GSamples_per_s",
+                   {"tree_nodes": int(tree.sum()), "roundtrip_relerr": float((xr - x).abs().max() / x.abs().max())})
+
+
+if __name__ == "__main__":
+    main()
