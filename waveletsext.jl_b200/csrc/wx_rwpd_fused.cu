@@ -1,12 +1,251 @@
-// wx_rwpd_fused.cu -- fused 1-D swpd / acwpd kernel (placeholder until the fused kernel lands: reports "not handled"
-// so that wx_rwt.cu runs the per-depth path).
+// wx_rwpd_fused.cu -- fused 1-D redundant packet trees: swpd / swpt (SWT.jl:840-868, 439-471) and acwpd / acwpt
+// (ACWT.jl:733-759, 427-460) over sdwt_step! (swt/swt_one_level.jl:99-127) / acdwt_step! (acwt/acwt_one_level.jl:101-128).
+//
+// The table xw(n, 2^(L+1)-1, N) is pure write traffic (read x once, write 2^(L+1)-1 columns), so the kernel is built
+// around keeping every parent on chip:
+//  * a CTA walks the subtree of one node depth-first; the ancestors of the node being computed sit in a stack of
+//    shared-memory buffers (one per depth), so a parent is never re-read from HBM;
+//  * every finished node leaves through ONE 1-D bulk async copy (cp.async.bulk.global.shared::cta) issued by a single
+//    thread and overlapped with the computation of the next node; the SM's LSUs never touch global memory;
+//  * a-trous filtering with dilation D = 2^d splits a node into D independent cosets.  A thread owns K consecutive
+//    elements of one coset (positions base + k*D), loads a register window of K+F-1 coset samples and produces its K
+//    outputs with fully unrolled FMAs (taps from the kernel-parameter constant bank, accumulated in the reference's tap
+//    order).  Lanes of a warp walk consecutive positions, so shared-memory loads and stores are conflict free for D >= 16.
+//  * the two children of the deepest parent are computed in one pass from one window (the detail outputs are taken F-2
+//    coset positions ahead so both filters read the same samples);
+//  * long trees are split in two launches (top levels d < d0, then one item per depth-d0 node) so that the stack is short
+//    enough for two resident CTAs per SM.
 #include "wx_steps.cuh"
+#include "wx_tma.cuh"
+#include <cstdlib>
 
-template <typename T>
-int wx_rwpd1d_fused(int ac, T *xw, const T *x, long n, int L, long N, const Taps<T> &t, cudaStream_t s, bool *handled)
+namespace {
+
+template <typename T, int F>
+struct RwCfg {
+    static constexpr int LGK = (F <= 16) ? 4 : 3;
+    static constexpr int K = 1 << LGK;                 // outputs per thread (consecutive elements of one coset)
+};
+
+// window start (in coset steps relative to the first output) of each filter
+//   stationary w1: v[i - D + jD]     -> -1          swt/swt_one_level.jl:117-118
+//   stationary w2: v[i - jD]         -> -(F-1)      swt/swt_one_level.jl:121-122
+//   autocorr     : v[i + (t - c) D]  -> 1 - c, c = F/2 + 1   acwt/acwt_one_level.jl:118-124
+template <int F, int AC, int WHICH>
+struct RwWin { static constexpr int M0 = AC ? -(F / 2) : (WHICH == 0 ? -1 : -(F - 1)); };
+
+template <typename T, int F, int AC, int WHICH>
+__device__ __forceinline__ T rw_dot(const T *win, const Taps<T> &tp)
 {
-    *handled = false;
+    T a;
+    if (AC) {
+        a = (WHICH == 0 ? tp.g[0] : tp.h[0]) * win[0];
+#pragma unroll
+        for (int j = 1; j < F; ++j) a = fma(WHICH == 0 ? tp.g[j] : tp.h[j], win[j], a);
+    } else if (WHICH == 0) {
+        a = tp.g[F - 1] * win[0];
+#pragma unroll
+        for (int j = 1; j < F; ++j) a = fma(tp.g[F - 1 - j], win[j], a);
+    } else {
+        a = tp.h[0] * win[F - 1];
+#pragma unroll
+        for (int j = 1; j < F; ++j) a = fma(tp.h[j], win[F - 1 - j], a);
+    }
+    return a;
+}
+
+// one child (WHICH = 0: w1 / scaling / P, 1: w2 / detail / Q) of the node in src; parent depth d
+template <typename T, int F, int AC, int WHICH>
+__device__ __forceinline__ void rw_pass1(const T *__restrict__ src, T *__restrict__ dst, int n, int d, const Taps<T> &tp, int tid, int nthr)
+{
+    using C = RwCfg<T, F>;
+    constexpr int K = C::K, W = K + F - 1, M0 = RwWin<F, AC, WHICH>::M0;
+    const int D = 1 << d, mask = n - 1;
+    for (int u = tid; u < (n >> C::LGK); u += nthr) {
+        const int base = ((u >> d) << (d + C::LGK)) | (u & (D - 1));
+        T win[W];
+        int idx = (base + M0 * D) & mask;
+#pragma unroll
+        for (int m = 0; m < W; ++m) { win[m] = src[idx]; idx = (idx + D) & mask; }
+#pragma unroll
+        for (int k = 0; k < K; ++k) dst[base + k * D] = rw_dot<T, F, AC, WHICH>(&win[k], tp);
+    }
+}
+
+// both children in one pass
+template <typename T, int F, int AC>
+__device__ __forceinline__ void rw_pass2(const T *__restrict__ src, T *__restrict__ dst0, T *__restrict__ dst1, int n, int d, const Taps<T> &tp,
+                                         int tid, int nthr)
+{
+    using C = RwCfg<T, F>;
+    constexpr int K = C::K, W = K + F - 1, M0 = RwWin<F, AC, 0>::M0;
+    constexpr int SH = AC ? 0 : F - 2;                 // detail outputs are taken SH coset positions ahead
+    const int D = 1 << d, mask = n - 1;
+    for (int u = tid; u < (n >> C::LGK); u += nthr) {
+        const int base = ((u >> d) << (d + C::LGK)) | (u & (D - 1));
+        T win[W];
+        int idx = (base + M0 * D) & mask;
+#pragma unroll
+        for (int m = 0; m < W; ++m) { win[m] = src[idx]; idx = (idx + D) & mask; }
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            dst0[base + k * D] = rw_dot<T, F, AC, 0>(&win[k], tp);
+            dst1[(base + (k + SH) * D) & mask] = rw_dot<T, F, AC, 1>(&win[k], tp);
+        }
+    }
+}
+
+// column of node (depth d, index idx) in the output table
+__device__ __forceinline__ long rw_col(int wpt, int L, int d, long idx) { return wpt ? (idx << (L - d)) : ((1L << d) - 1 + idx); }
+
+// item = (signal k, node j0 of depth dstart); the CTA computes every descendant of that node down to depth dend.
+// wpt = 0: heap-ordered packet table, every node is stored.  wpt = 1: only depth-dend nodes are stored, at column
+// idx << (L - dend) (swpt!'s in-place order, SWT.jl:454-470).
+template <typename T, int F, int AC>
+__global__ void __launch_bounds__(256) rwpd_dfs_k(T *__restrict__ xw, const T *__restrict__ x, int n, long ncols, int dstart, int dend, int L,
+                                                 int wpt, long items, Taps<T> tp)
+{
+    extern __shared__ __align__(128) unsigned char wx_rw_smem[];
+    __shared__ __align__(8) unsigned long long bar;
+    T *bufs = reinterpret_cast<T *>(wx_rw_smem);
+    const int E = dend - dstart;
+    T *lb0 = bufs + (size_t)E * n, *lb1 = lb0 + n;
+    const unsigned nbytes = (unsigned)n * (unsigned)sizeof(T);
+    const int tid = threadIdx.x, nthr = blockDim.x;
+
+    if (tid == 0) {
+        wx_mbar_init(&bar, 1);
+        wx_fence_mbar_init();
+    }
+    __syncthreads();
+    unsigned parity = 0;
+
+    for (long item = blockIdx.x; item < items; item += gridDim.x) {
+        const long k = item >> dstart;
+        const long j0 = item & ((1L << dstart) - 1);
+        T *xk = xw + k * ncols * n;
+        const T *src = (dstart == 0) ? (x + k * n) : (xk + rw_col(wpt, L, dstart, j0) * n);
+        if (tid == 0) {
+            wx_bulk_wait_read0();                                      // stores of the previous item have released smem
+            wx_mbar_expect_tx(&bar, nbytes);
+            wx_bulk_load_1d(bufs, src, nbytes, &bar);
+        }
+        wx_mbar_wait(&bar, parity);
+        parity ^= 1;
+        if (dstart == 0 && !wpt && tid == 0) {                         // xw[:,1] = x    SWT.jl:857
+            wx_bulk_store_1d(xk, bufs, nbytes);
+            wx_bulk_commit();
+        }
+        const int npairs = 1 << (E - 1);
+        for (int c = 0; c < npairs; ++c) {
+            // internal nodes (relative depths 1..E-1) whose path prefix changed with c, top down
+            int es = 1;
+            if (c != 0) { es = E - 1 - (__ffs(c) - 1); if (es < 1) es = 1; }
+            for (int e = es; e < E; ++e) {
+                const int pe = c >> (E - 1 - e);
+                const T *par = bufs + (size_t)(e - 1) * n;
+                T *cur = bufs + (size_t)e * n;
+                if (pe & 1) rw_pass1<T, F, AC, 1>(par, cur, n, dstart + e - 1, tp, tid, nthr);
+                else        rw_pass1<T, F, AC, 0>(par, cur, n, dstart + e - 1, tp, tid, nthr);
+                wx_fence_proxy_async();
+                if (tid == 0) wx_bulk_wait_read0();                    // the store issued one node ago has drained its buffer
+                __syncthreads();
+                if (tid == 0 && !wpt) {
+                    wx_bulk_store_1d(xk + rw_col(0, L, dstart + e, (j0 << e) | pe) * n, cur, nbytes);
+                    wx_bulk_commit();
+                }
+            }
+            rw_pass2<T, F, AC>(bufs + (size_t)(E - 1) * n, lb0, lb1, n, dend - 1, tp, tid, nthr);
+            wx_fence_proxy_async();
+            if (tid == 0) wx_bulk_wait_read0();
+            __syncthreads();
+            if (tid == 0) {
+                const long idx = (j0 << E) | (2L * c);
+                wx_bulk_store_1d(xk + rw_col(wpt, L, dend, idx) * n, lb0, nbytes);
+                wx_bulk_store_1d(xk + rw_col(wpt, L, dend, idx + 1) * n, lb1, nbytes);
+                wx_bulk_commit();
+            }
+        }
+    }
+    if (tid == 0) wx_bulk_wait_all();
+}
+
+template <typename T, int F, int AC>
+int rwpd_launch(T *xw, const T *x, long n, long ncols, int dstart, int dend, int L, int wpt, long N, const Taps<T> &t, cudaStream_t s)
+{
+    using C = RwCfg<T, F>;
+    WxDev dv; int rc = wx_devinfo(dv); if (rc) return rc;
+    const size_t smem = (size_t)(dend - dstart + 2) * n * sizeof(T);
+    int threads = (int)(((n >> C::LGK) + 31) / 32 * 32);
+    if (threads > 256) threads = 256;
+    auto kern = rwpd_dfs_k<T, F, AC>;
+    WX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    WX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
+    if (occ < 1) return wx_fail(WX_EUNSUPPORTED, "rwpd fused kernel does not fit (smem %zu)", smem);
+    const long items = N << dstart;
+    long blocks = (long)dv.sms * occ;
+    if (blocks > items) blocks = items;
+    kern<<<(unsigned)blocks, threads, smem, s>>>(xw, x, (int)n, ncols, dstart, dend, L, wpt, items, t);
+    WX_LAUNCHED();
     return WX_OK;
 }
-template int wx_rwpd1d_fused<double>(int, double *, const double *, long, int, long, const Taps<double> &, cudaStream_t, bool *);
-template int wx_rwpd1d_fused<float>(int, float *, const float *, long, int, long, const Taps<float> &, cudaStream_t, bool *);
+
+template <typename T, int F, int AC>
+int rwpd_plan(T *xw, const T *x, long n, int L, int wpt, long N, const Taps<T> &t, cudaStream_t s, int *done)
+{
+    using C = RwCfg<T, F>;
+    WxDev dv; int rc = wx_devinfo(dv); if (rc) return rc;
+    const int lgn = wx_ilog2l(n);
+    if (lgn < C::LGK) return WX_OK;
+    int dend = lgn - C::LGK + 1;                       // deepest parent has K*2^d <= n
+    if (dend > L) dend = L;
+    if (wpt && dend < L) return WX_OK;                 // in-place leaf order is only produced for complete trees
+    const size_t buf = (size_t)n * sizeof(T);
+    const long ncols = wpt ? (1L << L) : ((1L << (L + 1)) - 1);
+    // stages: the last one (most of the table) gets a stack short enough for two CTAs per SM when that still fuses
+    // >= 3 levels; the levels above it run in stages of as many levels as fit one CTA per SM.
+    const long efull = (long)(dv.smem_optin / buf) - 2;
+    const long ehalf = (long)((dv.smem_optin / 2 - 1024) / buf) - 2;
+    if (efull < 1) return WX_OK;
+    long elast = (ehalf >= 3 || ehalf >= dend) ? ehalf : efull;
+    static const char *env = getenv("WX_B200_RWPD_ELAST");        // measurement knob
+    if (env && atol(env) >= 1 && atol(env) <= efull) elast = atol(env);
+    if (elast > dend) elast = dend;
+    int d = 0;
+    const int top = dend - (int)elast;
+    while (d < top) {
+        const int e = (top - d > efull) ? (int)efull : top - d;
+        rc = rwpd_launch<T, F, AC>(xw, x, n, ncols, d, d + e, L, wpt, N, t, s);
+        if (rc) return rc;
+        d += e;
+    }
+    rc = rwpd_launch<T, F, AC>(xw, x, n, ncols, top, dend, L, wpt, N, t, s);
+    if (rc) return rc;
+    *done = dend;
+    return WX_OK;
+}
+
+}  // namespace
+
+// Runs the leading `*done` levels of the tree (0 = nothing handled; the caller continues with the per-depth path).
+// wpt = 0: swpd/acwpd table (column 0 = x included), wpt = 1: swpt/acwpt leaves.
+template <typename T>
+int wx_rwpd1d_fused(int ac, int wpt, T *xw, const T *x, long n, int L, long N, const Taps<T> &t, cudaStream_t s, int *done)
+{
+    *done = 0;
+    if (L < 1 || N < 1 || !wx_ispow2(n) || n >= (1L << 30) || L > 30) return WX_OK;
+    if ((n * sizeof(T)) % 16 != 0 || ((((uintptr_t)xw) | ((uintptr_t)x)) & 15) != 0) return WX_OK;
+    static const bool off = getenv("WX_B200_NO_FUSED_RWPD") != nullptr;    // debugging / A-B measurements only
+    if (off) return WX_OK;
+#define WX_RW_CASE(FF, AA) case FF: return rwpd_plan<T, FF, AA>(xw, x, n, L, wpt, N, t, s, done);
+    if (ac) {
+        switch (t.F) { WX_RW_CASE(3, 1) WX_RW_CASE(7, 1) WX_RW_CASE(11, 1) WX_RW_CASE(15, 1) WX_RW_CASE(19, 1) WX_RW_CASE(23, 1) WX_RW_CASE(31, 1) WX_RW_CASE(39, 1) }
+    } else {
+        switch (t.F) { WX_RW_CASE(2, 0) WX_RW_CASE(4, 0) WX_RW_CASE(6, 0) WX_RW_CASE(8, 0) WX_RW_CASE(10, 0) WX_RW_CASE(12, 0) WX_RW_CASE(16, 0) WX_RW_CASE(20, 0) }
+    }
+#undef WX_RW_CASE
+    return WX_OK;
+}
+template int wx_rwpd1d_fused<double>(int, int, double *, const double *, long, int, long, const Taps<double> &, cudaStream_t, int *);
+template int wx_rwpd1d_fused<float>(int, int, float *, const float *, long, int, long, const Taps<float> &, cudaStream_t, int *);

@@ -10,7 +10,7 @@
 #include <vector>
 
 template <typename T>
-int wx_rwpd1d_fused(int ac, T *xw, const T *x, long n, int L, long N, const Taps<T> &t, cudaStream_t s, bool *handled);
+int wx_rwpd1d_fused(int ac, int wpt, T *xw, const T *x, long n, int L, long N, const Taps<T> &t, cudaStream_t s, int *done);
 
 namespace {
 
@@ -74,12 +74,12 @@ int rwt_fwd_1d(int ac, int mode, T *xw, const T *x, long n, int L, long N, const
 {
     int rc;
     if (mode == WX_MODE_WPD) {
-        bool handled = false;
-        rc = wx_rwpd1d_fused<T>(ac, xw, x, n, L, N, t, s, &handled);
-        if (rc || handled) return rc;
+        int done = 0;                                        // leading levels already produced by the fused kernel
+        rc = wx_rwpd1d_fused<T>(ac, 0, xw, x, n, L, N, t, s, &done);
+        if (rc || done == L) return rc;
         const long ncols = (1L << (L + 1)) - 1, str = n * ncols;
-        rc = wx_launch_copy<T>(View<T>{xw, 1, str, 0, 0}, View<const T>{x, 1, n, 0, 0}, n, Batch{N, 1, 1, false}, s);
-        for (int d = 0; d < L && !rc; ++d) {
+        if (done == 0) rc = wx_launch_copy<T>(View<T>{xw, 1, str, 0, 0}, View<const T>{x, 1, n, 0, 0}, n, Batch{N, 1, 1, false}, s);
+        for (int d = done; d < L && !rc; ++d) {
             const long nd = 1L << d;
             T *w1 = xw + ((1L << (d + 1)) - 1) * n;
             rc = wx_launch_rdwt_step<T>(ac, View<T>{w1, 1, 2 * n, str, 0}, View<T>{w1 + n, 1, 2 * n, str, 0},
@@ -89,6 +89,9 @@ int rwt_fwd_1d(int ac, int mode, T *xw, const T *x, long n, int L, long N, const
     }
     if (mode == WX_MODE_WPT) {
         // swpt! SWT.jl:454-470 : in place, parent column is copied before its children overwrite it
+        int done = 0;
+        rc = wx_rwpd1d_fused<T>(ac, 1, xw, x, n, L, N, t, s, &done);
+        if (rc || done == L) return rc;
         const long ncols = 1L << L, str = n * ncols;
         rc = wx_launch_copy<T>(View<T>{xw, 1, str, 0, 0}, View<const T>{x, 1, n, 0, 0}, n, Batch{N, 1, 1, false}, s);
         if (rc) return rc;

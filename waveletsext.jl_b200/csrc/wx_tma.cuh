@@ -47,3 +47,15 @@ __device__ __forceinline__ void wx_bulk_wait_all() { asm volatile("cp.async.bulk
 // host: tensor map over `rows` rows of 128 bytes starting at `base`, box = boxrows x 128 B, SWIZZLE_128B.
 // The driver entry point is looked up at run time so the library does not link against libcuda.
 int wx_make_rowmap(CUtensorMap *map, const void *base, size_t elt, long rows, long boxrows);
+
+// 1-D bulk copies (no tensor map): 16-byte aligned addresses, size a multiple of 16 bytes.
+__device__ __forceinline__ void wx_bulk_load_1d(void *smem_dst, const void *gsrc, unsigned bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(wx_smem_u32(smem_dst)), "l"(gsrc),
+                 "r"(bytes), "r"(wx_smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void wx_bulk_store_1d(void *gdst, const void *smem_src, unsigned bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(wx_smem_u32(smem_src)), "r"(bytes) : "memory");
+}
