@@ -125,6 +125,74 @@ def test_wpt_iwpt_trees(wx, O, cuda, dt, n):
         assert relerr(xr.cpu().numpy(), x) <= (1e-10 if dt == np.float64 else 2e-4)
 
 
+def random_tree(n, rng, pr=0.7, maxdepth=None):
+    t = np.zeros(n - 1, bool)
+    for i in range(1, n):
+        if maxdepth is not None and int(np.log2(i)) >= maxdepth:
+            break
+        if (i == 1 or t[i // 2 - 1]) and rng.random() < pr:
+            t[i - 1] = True
+    return t
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+@pytest.mark.parametrize("name", ["haar", "db2", "sym8", "db10"])
+@pytest.mark.parametrize("n", [16, 96, 48, 1024])
+def test_wpt_iwpt_trees_filters_and_lengths(wx, O, cuda, dt, name, n):
+    """fused all-level tree kernels: every supported filter length, non power-of-two lengths, random trees"""
+    wt = wx.wavelet(name)
+    h, g = pair(wx, wt)
+    rng = np.random.default_rng(n + len(name))
+    x = rng.standard_normal((5, n)).astype(dt)
+    L = wx.maxtransformlevels(n)
+    for tree in (wx.maketree(n, L, "full"), random_tree(n, rng, maxdepth=L), random_tree(n, rng, 0.9, maxdepth=L)):
+        yw = wx.wptall(dev(x, cuda), wt, tree)
+        ref = np.stack([O.wpt(x[k], tree, h, g) for k in range(x.shape[0])])
+        assert relerr(yw.cpu().numpy(), ref) <= TOL[dt]
+        xr = wx.iwptall(yw, wt, tree)
+        refi = np.stack([O.iwpt(ref[k], tree, h, g) for k in range(x.shape[0])])
+        assert relerr(xr.cpu().numpy(), refi) <= TOL[dt] * 10
+        assert relerr(xr.cpu().numpy(), x) <= (1e-10 if dt == np.float64 else 3e-4)
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+def test_tree_long_signal(wx, O, cuda, dt):
+    """a signal too long for shared memory: coarse levels per-level, deep levels fused (forward and inverse)"""
+    n = 1 << 16
+    wt = wx.wavelet("db4")
+    h, g = pair(wx, wt)
+    rng = np.random.default_rng(77)
+    x = rng.standard_normal((2, n)).astype(dt)
+    for tree in (wx.maketree(n, 9, "full"), random_tree(n, rng, 0.8, maxdepth=10)):
+        yw = wx.wptall(dev(x, cuda), wt, tree)
+        ref = np.stack([O.wpt(x[k], tree, h, g) for k in range(2)])
+        assert relerr(yw.cpu().numpy(), ref) <= TOL[dt]
+        xr = wx.iwptall(yw, wt, tree)
+        assert relerr(xr.cpu().numpy(), np.stack([O.iwpt(ref[k], tree, h, g) for k in range(2)])) <= TOL[dt] * 10
+        assert relerr(xr.cpu().numpy(), x) <= (1e-10 if dt == np.float64 else 3e-4)
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+@pytest.mark.parametrize("n", [64, 1024, 96])
+def test_iwpd_random_trees(wx, O, cuda, dt, n):
+    """iwpd by tree (DWT.jl:337-351): the getbasiscoef gather is fused into the inverse kernel's staging loads"""
+    wt = wx.wavelet("coif4")
+    h, g = pair(wx, wt)
+    rng = np.random.default_rng(n)
+    x = rng.standard_normal((7, n)).astype(dt)
+    L = wx.maxtransformlevels(n)
+    y = wx.wpdall(dev(x, cuda), wt, L)
+    yh = y.cpu().numpy()
+    for tree in (random_tree(n, rng, maxdepth=L), random_tree(n, rng, 0.95, maxdepth=L), wx.maketree(n, L, "full"), wx.maketree(n, min(3, L), "full")):
+        got = wx.iwpdall(y, wt, tree).cpu().numpy()
+        ref = np.stack([O.iwpd(yh[k], tree, h, g) for k in range(x.shape[0])])
+        assert relerr(got, ref) <= TOL[dt] * 10
+        assert relerr(got, x) <= (1e-10 if dt == np.float64 else 3e-4)
+        # == getbasiscoefall + iwptall
+        two = wx.iwptall(wx.getbasiscoefall(y, tree), wt, tree).cpu().numpy()
+        assert relerr(got, two) <= TOL[dt]
+
+
 @pytest.mark.parametrize("dt", [np.float64, np.float32])
 def test_getbasiscoef_and_iwpd(wx, O, cuda, dt):
     """test/utils.jl:6-25 index vectors + iwpd round trips (test/transforms.jl:31-33)"""

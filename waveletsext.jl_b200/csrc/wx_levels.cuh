@@ -1,0 +1,380 @@
+// wx_levels.cuh -- one decomposition / reconstruction level of every node of a signal staged in shared memory
+// (16-byte-chunk XOR swizzle, see wx_common.cuh).  Shared by the fused wpd kernel (wx_wpd1d.cu) and the fused
+// tree kernels (wx_tree1d.cu).
+//   forward: dwt_step!  dwt/dwt_one_level.jl:79-107      inverse: idwt_step!  dwt/dwt_one_level.jl:192-223
+// TREE = true: `tm[j]` (j < ntm) says whether node j of this depth is split; other nodes are copied through.
+#pragma once
+#include "wx_common.cuh"
+
+template <typename T, int F>
+struct WpdCfg {
+    static constexpr int V = WxVec<T>::N;                              // elements per 16 B chunk
+    static constexpr int K = 2 * V;                                    // output pairs per window
+    static constexpr int S = (((F - 2) / 2) + V - 1) / V * V;          // high-pass look-ahead (multiple of V)
+    static constexpr int W = 2 * S + 2 * K;                            // window length (elements)
+};
+
+// split flags of the nodes of one depth: node j is split iff j < ntm && tm[j]  (tm == nullptr: every node is split)
+struct TreeMask {
+    const unsigned char *tm;
+    long ntm;
+    __device__ __forceinline__ bool on(long j) const { return tm == nullptr || (j < ntm && tm[j]); }
+};
+
+template <typename T> __device__ __forceinline__ typename WxVec<T>::type wx_ldg_stream(const T *p);
+template <> __device__ __forceinline__ double2 wx_ldg_stream<double>(const double *p) { return __ldcs(reinterpret_cast<const double2 *>(p)); }
+template <> __device__ __forceinline__ float4 wx_ldg_stream<float>(const float *p) { return __ldcs(reinterpret_cast<const float4 *>(p)); }
+__device__ __forceinline__ void wx_stg_stream(double *p, double2 v) { __stcs(reinterpret_cast<double2 *>(p), v); }
+__device__ __forceinline__ void wx_stg_stream(float *p, float4 v) { __stcs(reinterpret_cast<float4 *>(p), v); }
+
+__device__ __forceinline__ void wx_unpack(double *d, double2 v) { d[0] = v.x; d[1] = v.y; }
+__device__ __forceinline__ void wx_unpack(float *d, float4 v) { d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w; }
+__device__ __forceinline__ double2 wx_pack(const double *d) { return make_double2(d[0], d[1]); }
+__device__ __forceinline__ float4 wx_pack(const float *d) { return make_float4(d[0], d[1], d[2], d[3]); }
+
+// store one 16 B chunk of outputs (element index e, chunk aligned) to the next-level smem buffer and to HBM
+// GST = true : outputs go to HBM straight from registers (and to smem unless this is the last level)
+// GST = false: outputs go to smem only; the level row is written to HBM by a TMA bulk store of the smem buffer
+template <typename T, bool GST>
+__device__ __forceinline__ void wx_put_chunk(T *dst, T *grow, int e, const T *vals, bool last)
+{
+    constexpr int V = WxVec<T>::N;
+    using VT = typename WxVec<T>::type;
+    VT v = wx_pack(vals);
+    if (!GST || !last) *reinterpret_cast<VT *>(dst + wx_swz_chunk(e / V) * V) = v;
+    if (GST) wx_stg_stream(grow + e, v);
+}
+
+// ---- wide level: node half-length is a multiple of K -------------------------------------------------
+template <typename T, int F, bool POW2, bool GST, bool TREE = false>
+__device__ __forceinline__ void wpd_wide_level(const T *__restrict__ src, T *__restrict__ dst, T *__restrict__ grow, int n0, int p,
+                                               bool last, const Taps<T> &tp, int tid, int nthreads, TreeMask tmk = TreeMask{nullptr, 0})
+{
+    using C = WpdCfg<T, F>;
+    using VT = typename WxVec<T>::type;
+    constexpr int V = C::V, K = C::K, S = C::S, W = C::W;
+    const int half = p >> 1;
+    const int units = n0 / (2 * K);
+    const int lgh = 31 - __clz(half);
+    for (int u = tid; u < units; u += nthreads) {
+        const int gi = u * K;
+        const int j = POW2 ? (gi >> lgh) : (gi / half);
+        const int i = gi - j * half;
+        const int base = j * p;
+        if (TREE && !tmk.on(j)) {                                      // leaf of the tree: pass the 2K samples through
+#pragma unroll
+            for (int c = 0; c < 2 * K / V; ++c) {
+                const int ch = wx_swz_chunk((base + 2 * i) / V + c) * V;
+                *reinterpret_cast<VT *>(dst + ch) = *reinterpret_cast<const VT *>(src + ch);
+            }
+            continue;
+        }
+        T win[W];
+#pragma unroll
+        for (int c = 0; c < W / V; ++c) {
+            int off = 2 * i + c * V;
+            off = POW2 ? (off & (p - 1)) : (off % p);
+            const int e = base + off;
+            VT v = *reinterpret_cast<const VT *>(src + wx_swz_chunk(e / V) * V);
+            wx_unpack(&win[c * V], v);
+        }
+        T lo[K], hi[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            T a = tp.g[F - 1] * win[2 * k];
+            T b = tp.h[0] * win[2 * (S + k) + 1];
+#pragma unroll
+            for (int jj = 1; jj < F; ++jj) {
+                a = fma(tp.g[F - 1 - jj], win[2 * k + jj], a);
+                b = fma(tp.h[jj], win[2 * (S + k) + 1 - jj], b);
+            }
+            lo[k] = a;
+            hi[k] = b;
+        }
+#pragma unroll
+        for (int c = 0; c < K / V; ++c) {
+            wx_put_chunk<T, GST>(dst, grow, base + i + c * V, &lo[c * V], last);
+            int io = i + S + c * V;
+            io = POW2 ? (io & (half - 1)) : (io % half);
+            wx_put_chunk<T, GST>(dst, grow, base + half + io, &hi[c * V], last);
+        }
+    }
+}
+
+// ---- small level: node length P in {2,4,8}; a thread owns max(P,V) consecutive elements = whole nodes ----
+template <typename T, int F, int P, bool GST, bool TREE = false>
+__device__ __forceinline__ void wpd_small_level(const T *__restrict__ src, T *__restrict__ dst, T *__restrict__ grow, int n0, bool last,
+                                                const Taps<T> &tp, int tid, int nthreads, TreeMask tmk = TreeMask{nullptr, 0})
+{
+    using VT = typename WxVec<T>::type;
+    constexpr int V = WxVec<T>::N;
+    constexpr int G = P > V ? P : V;
+    const int groups = n0 / G;
+    for (int u = tid; u < groups; u += nthreads) {
+        const int e0 = u * G;
+        T v[G], o[G];
+#pragma unroll
+        for (int c = 0; c < G / V; ++c) {
+            VT q = *reinterpret_cast<const VT *>(src + wx_swz_chunk((e0 + c * V) / V) * V);
+            wx_unpack(&v[c * V], q);
+        }
+#pragma unroll
+        for (int nd = 0; nd < G / P; ++nd) {
+            if (TREE && !tmk.on(e0 / P + nd)) {
+#pragma unroll
+                for (int i = 0; i < P; ++i) o[nd * P + i] = v[nd * P + i];
+                continue;
+            }
+#pragma unroll
+            for (int i = 0; i < P / 2; ++i) {
+                T a = tp.g[F - 1] * v[nd * P + ((2 * i) & (P - 1))];
+                T b = tp.h[0] * v[nd * P + ((2 * i + 1) & (P - 1))];
+#pragma unroll
+                for (int jj = 1; jj < F; ++jj) {
+                    a = fma(tp.g[F - 1 - jj], v[nd * P + ((2 * i + jj) & (P - 1))], a);
+                    b = fma(tp.h[jj], v[nd * P + ((2 * i + 1 - jj) & (P - 1))], b);
+                }
+                o[nd * P + i] = a;
+                o[nd * P + P / 2 + i] = b;
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < G / V; ++c) wx_put_chunk<T, GST>(dst, grow, e0 + c * V, &o[c * V], last);
+    }
+}
+
+// ---- generic level: any even node length, one output pair per thread ----------------------------------
+template <typename T, int F, bool GST, bool TREE = false>
+__device__ __forceinline__ void wpd_generic_level(const T *__restrict__ src, T *__restrict__ dst, T *__restrict__ grow, int n0, int p,
+                                                  bool last, const Taps<T> &tp, int tid, int nthreads, TreeMask tmk = TreeMask{nullptr, 0})
+{
+    const int half = p >> 1;
+    for (int gi = tid; gi < n0 / 2; gi += nthreads) {
+        const int j = gi / half;
+        const int i = gi - j * half;
+        const int base = j * p;
+        if (TREE && !tmk.on(j)) {
+            dst[wx_swz_elem<T>(base + 2 * i)] = src[wx_swz_elem<T>(base + 2 * i)];
+            dst[wx_swz_elem<T>(base + 2 * i + 1)] = src[wx_swz_elem<T>(base + 2 * i + 1)];
+            continue;
+        }
+        int k1 = (2 * i) % p, k2 = (2 * i + 1) % p;
+        T a = tp.g[F - 1] * src[wx_swz_elem<T>(base + k1)];
+        T b = tp.h[0] * src[wx_swz_elem<T>(base + k2)];
+#pragma unroll 4
+        for (int jj = 1; jj < F; ++jj) {
+            k1 += 1; if (k1 >= p) k1 -= p;
+            k2 -= 1; if (k2 < 0) k2 += p;
+            a = fma(tp.g[F - 1 - jj], src[wx_swz_elem<T>(base + k1)], a);
+            b = fma(tp.h[jj], src[wx_swz_elem<T>(base + k2)], b);
+        }
+        const int elo = base + i, ehi = base + half + i;
+        if (!GST || !last) { dst[wx_swz_elem<T>(elo)] = a; dst[wx_swz_elem<T>(ehi)] = b; }
+        if (GST) { grow[elo] = a; grow[ehi] = b; }
+    }
+}
+
+// one decomposition level of every node of the staged signal: picks the wide / small / generic path
+template <typename T, int F, bool GST, bool TREE = false>
+__device__ __forceinline__ void wpd_level(const T *__restrict__ a, T *__restrict__ b, T *__restrict__ grow, int n0, int p, bool last,
+                                          const Taps<T> &tp, int tid, int nthreads, TreeMask tmk = TreeMask{nullptr, 0})
+{
+    using C = WpdCfg<T, F>;
+    constexpr int V = C::V, K = C::K;
+    const int half = p >> 1;
+    const bool pow2 = (p & (p - 1)) == 0;
+    if (half % K == 0) {
+        if (pow2) wpd_wide_level<T, F, true, GST, TREE>(a, b, grow, n0, p, last, tp, tid, nthreads, tmk);
+        else      wpd_wide_level<T, F, false, GST, TREE>(a, b, grow, n0, p, last, tp, tid, nthreads, tmk);
+    } else if (p == 2 && n0 % (V > 2 ? V : 2) == 0) {
+        wpd_small_level<T, F, 2, GST, TREE>(a, b, grow, n0, last, tp, tid, nthreads, tmk);
+    } else if (p == 4) {
+        wpd_small_level<T, F, 4, GST, TREE>(a, b, grow, n0, last, tp, tid, nthreads, tmk);
+    } else if (p == 8) {
+        wpd_small_level<T, F, 8, GST, TREE>(a, b, grow, n0, last, tp, tid, nthreads, tmk);
+    } else {
+        wpd_generic_level<T, F, GST, TREE>(a, b, grow, n0, p, last, tp, tid, nthreads, tmk);
+    }
+}
+
+
+// =====================================================================================================
+// inverse levels: children (w1 = first half, w2 = second half of the node) -> parent, idwt_step!
+// dwt/dwt_one_level.jl:207-221.  With R = F/2 and 0-based pair index t (outputs 2t, 2t+1):
+//   v[2t]   = sum_r g[F-1-2r] w1[t-r] + h[2r+1] w2[t+r]
+//   v[2t+1] = sum_r g[F-2-2r] w1[t-r] + h[2r]   w2[t+r]          (indices mod p/2, r = 0..R-1 in the reference's order)
+// =====================================================================================================
+template <typename T, int F>
+struct IwptCfg {
+    static constexpr int V = WxVec<T>::N;
+    static constexpr int K = 2 * V;                                    // output pairs per thread
+    static constexpr int R = F / 2;
+    static constexpr int S = ((R - 1) + V - 1) / V * V;                // w1 look-behind (multiple of V)
+    static constexpr int W = K + S;                                    // window length of each child
+};
+
+// one output pair from the two windows: a[s + k - r] = w1[t-r], b[k + r] = w2[t+r]
+template <typename T, int F>
+__device__ __forceinline__ void iwpt_pair(const T *a, const T *b, const Taps<T> &tp, T &ev, T &od)
+{
+    constexpr int R = F / 2;
+    T e = tp.g[F - 1] * a[0];
+    T o = tp.g[F - 2] * a[0];
+    e = fma(tp.h[1], b[0], e);
+    o = fma(tp.h[0], b[0], o);
+#pragma unroll
+    for (int r = 1; r < R; ++r) {
+        e = fma(tp.g[F - 1 - 2 * r], a[-r], e);
+        o = fma(tp.g[F - 2 - 2 * r], a[-r], o);
+        e = fma(tp.h[2 * r + 1], b[r], e);
+        o = fma(tp.h[2 * r], b[r], o);
+    }
+    ev = e;
+    od = o;
+}
+
+template <typename T, int F, bool POW2, bool TREE>
+__device__ __forceinline__ void iwpt_wide_level(const T *__restrict__ src, T *__restrict__ dst, int n0, int p, const Taps<T> &tp, int tid,
+                                                int nthreads, TreeMask tmk)
+{
+    using C = IwptCfg<T, F>;
+    using VT = typename WxVec<T>::type;
+    constexpr int V = C::V, K = C::K, S = C::S, W = C::W;
+    const int half = p >> 1;
+    const int units = n0 / (2 * K);
+    const int lgh = 31 - __clz(half);
+    for (int u = tid; u < units; u += nthreads) {
+        const int gi = u * K;
+        const int j = POW2 ? (gi >> lgh) : (gi / half);
+        const int t0 = gi - j * half;
+        const int base = j * p;
+        if (TREE && !tmk.on(j)) {
+#pragma unroll
+            for (int c = 0; c < 2 * K / V; ++c) {
+                const int ch = wx_swz_chunk((base + 2 * t0) / V + c) * V;
+                *reinterpret_cast<VT *>(dst + ch) = *reinterpret_cast<const VT *>(src + ch);
+            }
+            continue;
+        }
+        T a[W], b[W];
+#pragma unroll
+        for (int c = 0; c < W / V; ++c) {
+            int o1 = t0 - S + c * V, o2 = t0 + c * V;
+            if (POW2) { o1 &= half - 1; o2 &= half - 1; }
+            else { o1 %= half; if (o1 < 0) o1 += half; o2 %= half; }
+            wx_unpack(&a[c * V], *reinterpret_cast<const VT *>(src + wx_swz_chunk((base + o1) / V) * V));
+            wx_unpack(&b[c * V], *reinterpret_cast<const VT *>(src + wx_swz_chunk((base + half + o2) / V) * V));
+        }
+        T out[2 * K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) iwpt_pair<T, F>(&a[S + k], &b[k], tp, out[2 * k], out[2 * k + 1]);
+#pragma unroll
+        for (int c = 0; c < 2 * K / V; ++c)
+            *reinterpret_cast<VT *>(dst + wx_swz_chunk((base + 2 * t0) / V + c) * V) = wx_pack(&out[c * V]);
+    }
+}
+
+// node length P in {2,4,8}: a thread owns max(P,V) consecutive elements = whole nodes, wraps resolved at compile time
+template <typename T, int F, int P, bool TREE>
+__device__ __forceinline__ void iwpt_small_level(const T *__restrict__ src, T *__restrict__ dst, int n0, const Taps<T> &tp, int tid, int nthreads,
+                                                 TreeMask tmk)
+{
+    using VT = typename WxVec<T>::type;
+    constexpr int V = WxVec<T>::N;
+    constexpr int G = P > V ? P : V;
+    constexpr int H = P / 2, R = F / 2;
+    const int groups = n0 / G;
+    for (int u = tid; u < groups; u += nthreads) {
+        const int e0 = u * G;
+        T v[G], o[G];
+#pragma unroll
+        for (int c = 0; c < G / V; ++c) wx_unpack(&v[c * V], *reinterpret_cast<const VT *>(src + wx_swz_chunk((e0 + c * V) / V) * V));
+#pragma unroll
+        for (int nd = 0; nd < G / P; ++nd) {
+            if (TREE && !tmk.on(e0 / P + nd)) {
+#pragma unroll
+                for (int i = 0; i < P; ++i) o[nd * P + i] = v[nd * P + i];
+                continue;
+            }
+#pragma unroll
+            for (int t = 0; t < H; ++t) {
+                const T *w1 = &v[nd * P], *w2 = &v[nd * P + H];
+                T e = tp.g[F - 1] * w1[t];
+                T od = tp.g[F - 2] * w1[t];
+                e = fma(tp.h[1], w2[t], e);
+                od = fma(tp.h[0], w2[t], od);
+#pragma unroll
+                for (int r = 1; r < R; ++r) {
+                    e = fma(tp.g[F - 1 - 2 * r], w1[(t - r) & (H - 1)], e);
+                    od = fma(tp.g[F - 2 - 2 * r], w1[(t - r) & (H - 1)], od);
+                    e = fma(tp.h[2 * r + 1], w2[(t + r) & (H - 1)], e);
+                    od = fma(tp.h[2 * r], w2[(t + r) & (H - 1)], od);
+                }
+                o[nd * P + 2 * t] = e;
+                o[nd * P + 2 * t + 1] = od;
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < G / V; ++c) *reinterpret_cast<VT *>(dst + wx_swz_chunk((e0 + c * V) / V) * V) = wx_pack(&o[c * V]);
+    }
+}
+
+// any even node length, one output pair per thread
+template <typename T, int F, bool TREE>
+__device__ __forceinline__ void iwpt_generic_level(const T *__restrict__ src, T *__restrict__ dst, int n0, int p, const Taps<T> &tp, int tid,
+                                                   int nthreads, TreeMask tmk)
+{
+    constexpr int R = F / 2;
+    const int half = p >> 1;
+    for (int gi = tid; gi < n0 / 2; gi += nthreads) {
+        const int j = gi / half;
+        const int t = gi - j * half;
+        const int base = j * p;
+        if (TREE && !tmk.on(j)) {
+            dst[wx_swz_elem<T>(base + 2 * t)] = src[wx_swz_elem<T>(base + 2 * t)];
+            dst[wx_swz_elem<T>(base + 2 * t + 1)] = src[wx_swz_elem<T>(base + 2 * t + 1)];
+            continue;
+        }
+        int k1 = t, k2 = t;
+        T x1 = src[wx_swz_elem<T>(base + k1)], x2 = src[wx_swz_elem<T>(base + half + k2)];
+        T e = tp.g[F - 1] * x1;
+        T od = tp.g[F - 2] * x1;
+        e = fma(tp.h[1], x2, e);
+        od = fma(tp.h[0], x2, od);
+#pragma unroll 4
+        for (int r = 1; r < R; ++r) {
+            k1 -= 1; if (k1 < 0) k1 += half;
+            k2 += 1; if (k2 >= half) k2 -= half;
+            x1 = src[wx_swz_elem<T>(base + k1)];
+            x2 = src[wx_swz_elem<T>(base + half + k2)];
+            e = fma(tp.g[F - 1 - 2 * r], x1, e);
+            od = fma(tp.g[F - 2 - 2 * r], x1, od);
+            e = fma(tp.h[2 * r + 1], x2, e);
+            od = fma(tp.h[2 * r], x2, od);
+        }
+        dst[wx_swz_elem<T>(base + 2 * t)] = e;
+        dst[wx_swz_elem<T>(base + 2 * t + 1)] = od;
+    }
+}
+
+template <typename T, int F, bool TREE>
+__device__ __forceinline__ void iwpt_level(const T *__restrict__ a, T *__restrict__ b, int n0, int p, const Taps<T> &tp, int tid, int nthreads,
+                                           TreeMask tmk)
+{
+    using C = IwptCfg<T, F>;
+    constexpr int V = C::V, K = C::K;
+    const int half = p >> 1;
+    const bool pow2 = (p & (p - 1)) == 0;
+    if (half % K == 0) {
+        if (pow2) iwpt_wide_level<T, F, true, TREE>(a, b, n0, p, tp, tid, nthreads, tmk);
+        else      iwpt_wide_level<T, F, false, TREE>(a, b, n0, p, tp, tid, nthreads, tmk);
+    } else if (p == 2 && n0 % (V > 2 ? V : 2) == 0) {
+        iwpt_small_level<T, F, 2, TREE>(a, b, n0, tp, tid, nthreads, tmk);
+    } else if (p == 4) {
+        iwpt_small_level<T, F, 4, TREE>(a, b, n0, tp, tid, nthreads, tmk);
+    } else if (p == 8) {
+        iwpt_small_level<T, F, 8, TREE>(a, b, n0, tp, tid, nthreads, tmk);
+    } else {
+        iwpt_generic_level<T, F, TREE>(a, b, n0, p, tp, tid, nthreads, tmk);
+    }
+}

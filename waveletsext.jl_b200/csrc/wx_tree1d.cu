@@ -1,0 +1,143 @@
+// wx_tree1d.cu -- fused 1-D wavelet packet transforms by tree: wpt / iwpt (Wavelets.jl wpt!/iwpt!, call sites
+// dwt/dwt_all.jl:162,221 -> wptall / iwptall) and iwpd (DWT.jl:337-351 = getbasiscoef + iwpt!), every level in ONE launch.
+//
+// A persistent CTA stages one signal (or one depth-d0 node of a signal too long for shared memory) in shared memory,
+// runs all levels between two swizzled ping-pong buffers (wx_levels.cuh) and writes the result once: HBM traffic is the
+// algorithmic 2*n*sizeof(T) per signal instead of 2*n*sizeof(T) per level.  Nodes the tree does not split are copied
+// through (children occupy exactly the parent's range).  For iwpd the getbasiscoef gather (Utils.jl:101-134) is fused
+// into the staging loads through a per-position leaf-depth map.
+#include "wx_steps.cuh"
+#include "wx_levels.cuh"
+
+namespace {
+
+// item = (signal k, node j0 of depth d0).  Levels d0..nlev-1 of that node are processed (forward: top down, inverse:
+// bottom up).  depth != nullptr: x is a packet table (n, Kx, N) and position e is read from level depth[e].
+template <typename T, int F, bool INV, bool TREE>
+__global__ void __launch_bounds__(256) tree1d_fused_k(T *__restrict__ y, const T *__restrict__ x, long n, int d0, int nlev, long items, int bufelems,
+                                                     const unsigned char *__restrict__ tree, long ntree, const unsigned char *__restrict__ depth,
+                                                     int Kx, int vecgather, Taps<T> tp)
+{
+    using VT = typename WxVec<T>::type;
+    constexpr int V = WxVec<T>::N;
+    extern __shared__ __align__(128) unsigned char wx_tr_smem[];
+    T *buf0 = reinterpret_cast<T *>(wx_tr_smem);
+    T *buf1 = buf0 + bufelems;
+    const int n0 = (int)(n >> d0);
+    const int tid = threadIdx.x, nthreads = blockDim.x;
+    const int nl = nlev - d0;
+
+    for (long item = blockIdx.x; item < items; item += gridDim.x) {
+        const long k = item >> d0;
+        const long j0 = item & ((1L << d0) - 1);
+        const long pos0 = j0 * n0;
+        // ---- stage in -------------------------------------------------------------------------------
+        if (depth == nullptr) {
+            const T *src = x + k * n + pos0;
+            for (int c = tid; c < n0 / V; c += nthreads)
+                *reinterpret_cast<VT *>(buf0 + wx_swz_chunk(c) * V) = wx_ldg_stream<T>(src + c * V);
+        } else if (vecgather) {                       // every leaf is at least one 16-byte chunk long
+            const T *src = x + k * (long)Kx * n + pos0;
+            for (int c = tid; c < n0 / V; c += nthreads) {
+                const long lv = depth[pos0 + (long)c * V];
+                *reinterpret_cast<VT *>(buf0 + wx_swz_chunk(c) * V) = wx_ldg_stream<T>(src + lv * n + c * V);
+            }
+        } else {
+            const T *src = x + k * (long)Kx * n + pos0;
+            for (int e = tid; e < n0; e += nthreads) buf0[wx_swz_elem<T>(e)] = src[(long)depth[pos0 + e] * n + e];
+        }
+        __syncthreads();
+        // ---- levels ---------------------------------------------------------------------------------
+        T *a = buf0, *b = buf1;
+        for (int q = 0; q < nl; ++q) {
+            const int l = INV ? nl - 1 - q : q;       // level relative to the staged node
+            const int d = d0 + l;
+            const long first = ((1L << d) - 1) + (j0 << l);               // 0-based heap position of the node's first depth-d descendant
+            TreeMask tm{TREE ? tree + first : nullptr, ntree - first};
+            if (INV) iwpt_level<T, F, TREE>(a, b, n0, n0 >> l, tp, tid, nthreads, tm);
+            else     wpd_level<T, F, false, TREE>(a, b, nullptr, n0, n0 >> l, false, tp, tid, nthreads, tm);
+            __syncthreads();
+            T *t = a; a = b; b = t;
+        }
+        // ---- stage out ------------------------------------------------------------------------------
+        T *dst = y + k * n + pos0;
+        for (int c = tid; c < n0 / V; c += nthreads)
+            wx_stg_stream(dst + c * V, *reinterpret_cast<const VT *>(a + wx_swz_chunk(c) * V));
+        __syncthreads();
+    }
+}
+
+template <typename T, int F, bool INV, bool TREE>
+int launch(T *y, const T *x, long n, long N, int d0, int nlev, const unsigned char *dtree, long ntree, const unsigned char *ddepth, int Kx,
+           int vecgather, const Taps<T> &t, cudaStream_t s)
+{
+    WxDev dv; int rc = wx_devinfo(dv); if (rc) return rc;
+    constexpr int V = WxVec<T>::N;
+    const long n0 = n >> d0;
+    const long bufbytes = ((n0 * (long)sizeof(T) + 127) / 128) * 128;
+    const size_t smem = (size_t)2 * bufbytes;
+    long units = n0 / (4 * V);
+    int threads = (int)((units + 31) / 32 * 32);
+    if (threads < 64) threads = 64;
+    if (threads > 256) threads = 256;
+    auto kern = tree1d_fused_k<T, F, INV, TREE>;
+    WX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    WX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
+    if (occ < 1) return wx_fail(WX_EUNSUPPORTED, "tree1d fused kernel does not fit (smem %zu)", smem);
+    const long items = N << d0;
+    long blocks = (long)dv.sms * occ;
+    if (blocks > items) blocks = items;
+    kern<<<(unsigned)blocks, threads, smem, s>>>(y, x, n, d0, nlev, items, (int)(bufbytes / sizeof(T)), dtree, ntree, ddepth, Kx, vecgather, t);
+    WX_LAUNCHED();
+    return WX_OK;
+}
+
+template <typename T, int F>
+int launch_f(bool inverse, bool full, T *y, const T *x, long n, long N, int d0, int nlev, const unsigned char *dtree, long ntree,
+             const unsigned char *ddepth, int Kx, int vecgather, const Taps<T> &t, cudaStream_t s)
+{
+    if (inverse) {
+        if (full) return launch<T, F, true, false>(y, x, n, N, d0, nlev, dtree, ntree, ddepth, Kx, vecgather, t, s);
+        return launch<T, F, true, true>(y, x, n, N, d0, nlev, dtree, ntree, ddepth, Kx, vecgather, t, s);
+    }
+    if (full) return launch<T, F, false, false>(y, x, n, N, d0, nlev, dtree, ntree, ddepth, Kx, vecgather, t, s);
+    return launch<T, F, false, true>(y, x, n, N, d0, nlev, dtree, ntree, ddepth, Kx, vecgather, t, s);
+}
+
+}  // namespace
+
+// smallest start depth whose node fits the ping-pong buffers, or -1 when the fused kernel does not cover the shape
+template <typename T>
+int wx_tree1d_fused_depth(const T *y, const T *x, long n, int nlev, int F)
+{
+    WxDev dv;
+    if (wx_devinfo(dv)) return -1;
+    constexpr int V = WxVec<T>::N;
+    const bool fusedF = (F == 2 || F == 4 || F == 6 || F == 8 || F == 10 || F == 12 || F == 16 || F == 20);
+    if (!fusedF || nlev < 1 || n >= (1L << 30) || ((((uintptr_t)y) | ((uintptr_t)x)) & 15) != 0) return -1;
+    int d0 = 0;
+    while (d0 < nlev && (size_t)2 * (((n >> d0) * sizeof(T) + 127) / 128 * 128) > dv.smem_optin) ++d0;
+    if (d0 >= nlev) return -1;
+    if ((n >> d0) % (2 * V) != 0) return -1;
+    return d0;
+}
+
+// levels d0..nlev-1 of the tree in one launch.  full: every node above depth nlev is split (dtree unused).
+// ddepth != nullptr: x is a packet table (n, Kx, N) gathered through the per-position leaf depth map (d0 must be 0).
+template <typename T>
+int wx_tree1d_fused(bool inverse, bool full, T *y, const T *x, long n, long N, int d0, int nlev, const unsigned char *dtree, long ntree,
+                    const unsigned char *ddepth, int Kx, int vecgather, const Taps<T> &t, cudaStream_t s)
+{
+#define WX_TR_CASE(FF) case FF: return launch_f<T, FF>(inverse, full, y, x, n, N, d0, nlev, dtree, ntree, ddepth, Kx, vecgather, t, s);
+    switch (t.F) { WX_TR_CASE(2) WX_TR_CASE(4) WX_TR_CASE(6) WX_TR_CASE(8) WX_TR_CASE(10) WX_TR_CASE(12) WX_TR_CASE(16) WX_TR_CASE(20) }
+#undef WX_TR_CASE
+    return wx_fail(WX_EUNSUPPORTED, "tree1d fused: filter length %d", t.F);
+}
+
+#define WX_TR_INST(T)                                                                                                                       \
+    template int wx_tree1d_fused_depth<T>(const T *, const T *, long, int, int);                                                            \
+    template int wx_tree1d_fused<T>(bool, bool, T *, const T *, long, long, int, int, const unsigned char *, long, const unsigned char *, \
+                                    int, int, const Taps<T> &, cudaStream_t);
+WX_TR_INST(double)
+WX_TR_INST(float)

@@ -7,6 +7,13 @@
 //            (call sites dwt/dwt_all.jl:162,221), restated as dwt_step!/idwt_step! applied over the tree.
 #include "wx_steps.cuh"
 #include <vector>
+#include <cstdlib>
+
+// fused all-levels-in-one-launch kernels (wx_tree1d.cu)
+template <typename T> int wx_tree1d_fused_depth(const T *y, const T *x, long n, int nlev, int F);
+template <typename T>
+int wx_tree1d_fused(bool inverse, bool full, T *y, const T *x, long n, long N, int d0, int nlev, const unsigned char *dtree, long ntree,
+                    const unsigned char *ddepth, int Kx, int vecgather, const Taps<T> &t, cudaStream_t s);
 
 namespace {
 
@@ -225,18 +232,37 @@ int tree1d(bool inverse, T *y, const T *x, long n, long N, const unsigned char *
         return WX_OK;
     }
     DevTree dt; rc = dt.upload(tree, ntree, s); if (rc) return rc;
+    // every node above depth nlev split?  then the kernels need no per-node test
+    bool full = ntree >= (1L << nlev) - 1;
+    for (long i = 0; full && i < (1L << nlev) - 1; ++i) full = tree[i] != 0;
+    static const bool nofuse = getenv("WX_B200_NO_FUSED_TREE") != nullptr;       // debugging / A-B measurements only
+    const int d0 = nofuse ? -1 : wx_tree1d_fused_depth<T>(y, x, n, nlev, F);
+    if (d0 == 0) return wx_tree1d_fused<T>(inverse, full, y, x, n, N, 0, nlev, dt.d, ntree, nullptr, 0, 0, t, s);
     T *tmp = nullptr;
     rc = wx_scratch(&tmp, (size_t)n * N, s); if (rc) return rc;
-    // ping-pong so that the last level lands in y
+    // levels the per-level kernel runs: all of them, or the d0 coarsest ones around the fused launch
+    const int ngen = d0 > 0 ? d0 : nlev;
     const T *cur = x;
-    for (int q = 0; q < nlev; ++q) {
-        const int d = inverse ? nlev - 1 - q : q;
-        T *nxt = ((nlev - 1 - q) % 2 == 0) ? y : tmp;
+    if (d0 > 0 && inverse) {                         // deep levels first, fused; lands where the ping-pong below expects it
+        T *fo = (ngen % 2 == 0) ? y : tmp;
+        rc = wx_tree1d_fused<T>(true, full, fo, x, n, N, d0, nlev, dt.d, ntree, nullptr, 0, 0, t, s);
+        if (rc) { wx_scratch_free(tmp, s); return rc; }
+        cur = fo;
+    }
+    // ping-pong so that the last level lands in y
+    for (int q = 0; q < ngen; ++q) {
+        const int d = inverse ? ngen - 1 - q : q;
+        T *nxt = ((ngen - 1 - q) % 2 == 0) ? y : tmp;
         if (nxt == cur) nxt = (nxt == y) ? tmp : y;     // only when x aliases y
         if (inverse) iwpt1_level_k<T><<<gridf(n * N), kT, 0, s>>>(nxt, cur, n, N, d, dt.d, ntree, t);
         else         wpt1_level_k<T><<<gridf((n / 2) * N), kT, 0, s>>>(nxt, cur, n, N, d, dt.d, ntree, t);
         WX_LAUNCHED();
         cur = nxt;
+    }
+    if (d0 > 0 && !inverse) {                        // remaining deep levels, fused (in place per node when cur == y)
+        rc = wx_tree1d_fused<T>(false, full, y, cur, n, N, d0, nlev, dt.d, ntree, nullptr, 0, 0, t, s);
+        if (rc) { wx_scratch_free(tmp, s); return rc; }
+        cur = y;
     }
     if (cur != y) WX_CUDA(cudaMemcpyAsync(y, cur, (size_t)n * N * sizeof(T), cudaMemcpyDeviceToDevice, s));
     return wx_scratch_free(tmp, s);
@@ -391,6 +417,24 @@ int iwpd_impl(T *x, const T *Xw, long m, long n, int K, long N, const unsigned c
     cudaStream_t s = (cudaStream_t)stream;
     if (N == 0) return WX_OK;
     const long sz = (m > 0 ? m : 1) * n;
+    if (m == 0 && x && Xw && (tree || ntree == 0) && n >= 1 && K >= 1) {
+        // 1-D: gather fused into the staging loads of the all-levels kernel
+        const int nlev = tree_maxdepth1(tree, ntree);
+        static const bool nofuse = getenv("WX_B200_NO_FUSED_TREE") != nullptr;
+        if (!nofuse && nlev >= 1 && nlev <= wx_maxlevels(n) && wx_tree1d_fused_depth<T>(x, Xw, n, nlev, F) == 0) {
+            Taps<T> t; int rc = wx_make_taps(t, h, g, F); if (rc) return rc;
+            std::vector<unsigned char> depth;
+            rc = leaf_depth_map(depth, 0, n, K, tree, ntree); if (rc) return rc;
+            long minleaf = n;
+            for (long e = 0; e < n;) { const long len = n >> depth[(size_t)e]; if (len < minleaf) minleaf = len; e += len; }
+            bool full = ntree >= (1L << nlev) - 1;
+            for (long i = 0; full && i < (1L << nlev) - 1; ++i) full = tree[i] != 0;
+            DevTree dt, dd;
+            rc = dt.upload(tree, ntree, s); if (rc) return rc;
+            rc = dd.upload(depth.data(), n, s); if (rc) return rc;
+            return wx_tree1d_fused<T>(true, full, x, Xw, n, N, 0, nlev, dt.d, ntree, dd.d, K, minleaf >= WxVec<T>::N ? 1 : 0, t, s);
+        }
+    }
     T *w; int rc = wx_scratch(&w, (size_t)sz * N, s); if (rc) return rc;
     rc = gather_impl<T>(w, Xw, m, n, K, N, tree, ntree, stream);
     if (!rc) rc = (m > 0) ? tree2d<T>(true, x, w, m, n, N, tree, ntree, h, g, F, stream)

@@ -18,175 +18,10 @@
 //  * accumulation order per output is the reference's tap order (j ascending); products use FMA.
 #include "wx_steps.cuh"
 #include "wx_tma.cuh"
+#include "wx_levels.cuh"
 #include <cstdlib>
 
 namespace {
-
-template <typename T, int F>
-struct WpdCfg {
-    static constexpr int V = WxVec<T>::N;                              // elements per 16 B chunk
-    static constexpr int K = 2 * V;                                    // output pairs per window
-    static constexpr int S = (((F - 2) / 2) + V - 1) / V * V;          // high-pass look-ahead (multiple of V)
-    static constexpr int W = 2 * S + 2 * K;                            // window length (elements)
-};
-
-template <typename T> __device__ __forceinline__ typename WxVec<T>::type wx_ldg_stream(const T *p);
-template <> __device__ __forceinline__ double2 wx_ldg_stream<double>(const double *p) { return __ldcs(reinterpret_cast<const double2 *>(p)); }
-template <> __device__ __forceinline__ float4 wx_ldg_stream<float>(const float *p) { return __ldcs(reinterpret_cast<const float4 *>(p)); }
-__device__ __forceinline__ void wx_stg_stream(double *p, double2 v) { __stcs(reinterpret_cast<double2 *>(p), v); }
-__device__ __forceinline__ void wx_stg_stream(float *p, float4 v) { __stcs(reinterpret_cast<float4 *>(p), v); }
-
-__device__ __forceinline__ void wx_unpack(double *d, double2 v) { d[0] = v.x; d[1] = v.y; }
-__device__ __forceinline__ void wx_unpack(float *d, float4 v) { d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w; }
-__device__ __forceinline__ double2 wx_pack(const double *d) { return make_double2(d[0], d[1]); }
-__device__ __forceinline__ float4 wx_pack(const float *d) { return make_float4(d[0], d[1], d[2], d[3]); }
-
-// store one 16 B chunk of outputs (element index e, chunk aligned) to the next-level smem buffer and to HBM
-// GST = true : outputs go to HBM straight from registers (and to smem unless this is the last level)
-// GST = false: outputs go to smem only; the level row is written to HBM by a TMA bulk store of the smem buffer
-template <typename T, bool GST>
-__device__ __forceinline__ void wx_put_chunk(T *dst, T *grow, int e, const T *vals, bool last)
-{
-    constexpr int V = WxVec<T>::N;
-    using VT = typename WxVec<T>::type;
-    VT v = wx_pack(vals);
-    if (!GST || !last) *reinterpret_cast<VT *>(dst + wx_swz_chunk(e / V) * V) = v;
-    if (GST) wx_stg_stream(grow + e, v);
-}
-
-// ---- wide level: node half-length is a multiple of K -------------------------------------------------
-template <typename T, int F, bool POW2, bool GST>
-__device__ __forceinline__ void wpd_wide_level(const T *__restrict__ src, T *__restrict__ dst, T *__restrict__ grow, int n0, int p,
-                                               bool last, const Taps<T> &tp, int tid, int nthreads)
-{
-    using C = WpdCfg<T, F>;
-    using VT = typename WxVec<T>::type;
-    constexpr int V = C::V, K = C::K, S = C::S, W = C::W;
-    const int half = p >> 1;
-    const int units = n0 / (2 * K);
-    const int lgh = 31 - __clz(half);
-    for (int u = tid; u < units; u += nthreads) {
-        const int gi = u * K;
-        const int j = POW2 ? (gi >> lgh) : (gi / half);
-        const int i = gi - j * half;
-        const int base = j * p;
-        T win[W];
-#pragma unroll
-        for (int c = 0; c < W / V; ++c) {
-            int off = 2 * i + c * V;
-            off = POW2 ? (off & (p - 1)) : (off % p);
-            const int e = base + off;
-            VT v = *reinterpret_cast<const VT *>(src + wx_swz_chunk(e / V) * V);
-            wx_unpack(&win[c * V], v);
-        }
-        T lo[K], hi[K];
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            T a = tp.g[F - 1] * win[2 * k];
-            T b = tp.h[0] * win[2 * (S + k) + 1];
-#pragma unroll
-            for (int jj = 1; jj < F; ++jj) {
-                a = fma(tp.g[F - 1 - jj], win[2 * k + jj], a);
-                b = fma(tp.h[jj], win[2 * (S + k) + 1 - jj], b);
-            }
-            lo[k] = a;
-            hi[k] = b;
-        }
-#pragma unroll
-        for (int c = 0; c < K / V; ++c) {
-            wx_put_chunk<T, GST>(dst, grow, base + i + c * V, &lo[c * V], last);
-            int io = i + S + c * V;
-            io = POW2 ? (io & (half - 1)) : (io % half);
-            wx_put_chunk<T, GST>(dst, grow, base + half + io, &hi[c * V], last);
-        }
-    }
-}
-
-// ---- small level: node length P in {2,4,8}; a thread owns max(P,V) consecutive elements = whole nodes ----
-template <typename T, int F, int P, bool GST>
-__device__ __forceinline__ void wpd_small_level(const T *__restrict__ src, T *__restrict__ dst, T *__restrict__ grow, int n0, bool last,
-                                                const Taps<T> &tp, int tid, int nthreads)
-{
-    using VT = typename WxVec<T>::type;
-    constexpr int V = WxVec<T>::N;
-    constexpr int G = P > V ? P : V;
-    const int groups = n0 / G;
-    for (int u = tid; u < groups; u += nthreads) {
-        const int e0 = u * G;
-        T v[G], o[G];
-#pragma unroll
-        for (int c = 0; c < G / V; ++c) {
-            VT q = *reinterpret_cast<const VT *>(src + wx_swz_chunk((e0 + c * V) / V) * V);
-            wx_unpack(&v[c * V], q);
-        }
-#pragma unroll
-        for (int nd = 0; nd < G / P; ++nd) {
-#pragma unroll
-            for (int i = 0; i < P / 2; ++i) {
-                T a = tp.g[F - 1] * v[nd * P + ((2 * i) & (P - 1))];
-                T b = tp.h[0] * v[nd * P + ((2 * i + 1) & (P - 1))];
-#pragma unroll
-                for (int jj = 1; jj < F; ++jj) {
-                    a = fma(tp.g[F - 1 - jj], v[nd * P + ((2 * i + jj) & (P - 1))], a);
-                    b = fma(tp.h[jj], v[nd * P + ((2 * i + 1 - jj) & (P - 1))], b);
-                }
-                o[nd * P + i] = a;
-                o[nd * P + P / 2 + i] = b;
-            }
-        }
-#pragma unroll
-        for (int c = 0; c < G / V; ++c) wx_put_chunk<T, GST>(dst, grow, e0 + c * V, &o[c * V], last);
-    }
-}
-
-// ---- generic level: any even node length, one output pair per thread ----------------------------------
-template <typename T, int F, bool GST>
-__device__ __forceinline__ void wpd_generic_level(const T *__restrict__ src, T *__restrict__ dst, T *__restrict__ grow, int n0, int p,
-                                                  bool last, const Taps<T> &tp, int tid, int nthreads)
-{
-    const int half = p >> 1;
-    for (int gi = tid; gi < n0 / 2; gi += nthreads) {
-        const int j = gi / half;
-        const int i = gi - j * half;
-        const int base = j * p;
-        int k1 = (2 * i) % p, k2 = (2 * i + 1) % p;
-        T a = tp.g[F - 1] * src[wx_swz_elem<T>(base + k1)];
-        T b = tp.h[0] * src[wx_swz_elem<T>(base + k2)];
-#pragma unroll 4
-        for (int jj = 1; jj < F; ++jj) {
-            k1 += 1; if (k1 >= p) k1 -= p;
-            k2 -= 1; if (k2 < 0) k2 += p;
-            a = fma(tp.g[F - 1 - jj], src[wx_swz_elem<T>(base + k1)], a);
-            b = fma(tp.h[jj], src[wx_swz_elem<T>(base + k2)], b);
-        }
-        const int elo = base + i, ehi = base + half + i;
-        if (!GST || !last) { dst[wx_swz_elem<T>(elo)] = a; dst[wx_swz_elem<T>(ehi)] = b; }
-        if (GST) { grow[elo] = a; grow[ehi] = b; }
-    }
-}
-
-// one decomposition level of every node of the staged signal: picks the wide / small / generic path
-template <typename T, int F, bool GST>
-__device__ __forceinline__ void wpd_level(const T *__restrict__ a, T *__restrict__ b, T *__restrict__ grow, int n0, int p, bool last,
-                                          const Taps<T> &tp, int tid, int nthreads)
-{
-    using C = WpdCfg<T, F>;
-    constexpr int V = C::V, K = C::K;
-    const int half = p >> 1;
-    const bool pow2 = (p & (p - 1)) == 0;
-    if (half % K == 0) {
-        if (pow2) wpd_wide_level<T, F, true, GST>(a, b, grow, n0, p, last, tp, tid, nthreads);
-        else      wpd_wide_level<T, F, false, GST>(a, b, grow, n0, p, last, tp, tid, nthreads);
-    } else if (p == 2 && n0 % (V > 2 ? V : 2) == 0) {
-        wpd_small_level<T, F, 2, GST>(a, b, grow, n0, last, tp, tid, nthreads);
-    } else if (p == 4) {
-        wpd_small_level<T, F, 4, GST>(a, b, grow, n0, last, tp, tid, nthreads);
-    } else if (p == 8) {
-        wpd_small_level<T, F, 8, GST>(a, b, grow, n0, last, tp, tid, nthreads);
-    } else {
-        wpd_generic_level<T, F, GST>(a, b, grow, n0, p, last, tp, tid, nthreads);
-    }
-}
 
 // ---- the fused kernel ----------------------------------------------------------------------------------
 // item = (signal k, node j0 of depth d0); the CTA computes levels d0+1..L of that node.
