@@ -36,6 +36,14 @@ __device__ __forceinline__ float4 wx_pack(const float *d) { return make_float4(d
 // GST = true : outputs go to HBM straight from registers (and to smem unless this is the last level)
 // GST = false: outputs go to smem only; the level row is written to HBM by a TMA bulk store of the smem buffer
 template <typename T, bool GST>
+__device__ __forceinline__ void wx_put_chunk(T *dst, int soff, T *grow, int e, const T *vals, bool last)   // soff = swizzled element offset of e
+{
+    using VT = typename WxVec<T>::type;
+    VT v = wx_pack(vals);
+    if (!GST || !last) *reinterpret_cast<VT *>(dst + soff) = v;
+    if (GST) wx_stg_stream(grow + e, v);
+}
+template <typename T, bool GST>
 __device__ __forceinline__ void wx_put_chunk(T *dst, T *grow, int e, const T *vals, bool last)
 {
     constexpr int V = WxVec<T>::N;
@@ -43,6 +51,15 @@ __device__ __forceinline__ void wx_put_chunk(T *dst, T *grow, int e, const T *va
     VT v = wx_pack(vals);
     if (!GST || !last) *reinterpret_cast<VT *>(dst + wx_swz_chunk(e / V) * V) = v;
     if (GST) wx_stg_stream(grow + e, v);
+}
+
+// element offset of the swizzled position of element e, for e a multiple of 4 chunks: the other chunks of that aligned
+// group of four (eight when e is a multiple of 8 chunks) are at  wx_swz_group(e) ^ (i * V)  -- one XOR per chunk.
+template <typename T>
+__device__ __forceinline__ int wx_swz_group(int e)
+{
+    constexpr int V = WxVec<T>::N;
+    return wx_swz_chunk(e / V) * V;
 }
 
 // ---- wide level: node half-length is a multiple of K -------------------------------------------------
@@ -64,20 +81,23 @@ __device__ __forceinline__ void wpd_wide_level(const T *__restrict__ src, T *__r
         if (TREE && !tmk.on(j)) {                                      // leaf of the tree: pass the 2K samples through
 #pragma unroll
             for (int c = 0; c < 2 * K / V; ++c) {
-                const int ch = wx_swz_chunk((base + 2 * i) / V + c) * V;
+                const int ch = wx_swz_group<T>(base + 2 * i) ^ (c * V);      // 2K elements = one aligned group of 4 chunks
                 *reinterpret_cast<VT *>(dst + ch) = *reinterpret_cast<const VT *>(src + ch);
             }
             continue;
         }
+        // the window starts on a 4-chunk boundary (2i is a multiple of 2K); one swizzle per aligned group of 4 chunks
+        constexpr int NG = (W / V + 3) / 4;
+        int gw[NG];
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+            int off = 2 * i + g * 4 * V;
+            off = POW2 ? (off & (p - 1)) : (off % p);
+            gw[g] = wx_swz_group<T>(base + off);
+        }
         T win[W];
 #pragma unroll
-        for (int c = 0; c < W / V; ++c) {
-            int off = 2 * i + c * V;
-            off = POW2 ? (off & (p - 1)) : (off % p);
-            const int e = base + off;
-            VT v = *reinterpret_cast<const VT *>(src + wx_swz_chunk(e / V) * V);
-            wx_unpack(&win[c * V], v);
-        }
+        for (int c = 0; c < W / V; ++c) wx_unpack(&win[c * V], *reinterpret_cast<const VT *>(src + (gw[c / 4] ^ ((c % 4) * V))));
         T lo[K], hi[K];
 #pragma unroll
         for (int k = 0; k < K; ++k) {
@@ -92,11 +112,11 @@ __device__ __forceinline__ void wpd_wide_level(const T *__restrict__ src, T *__r
             hi[k] = b;
         }
 #pragma unroll
-        for (int c = 0; c < K / V; ++c) {
-            wx_put_chunk<T, GST>(dst, grow, base + i + c * V, &lo[c * V], last);
+        for (int c = 0; c < K / V; ++c) {                              // K / V = 2 chunks, the low-pass pair is aligned
+            wx_put_chunk<T, GST>(dst, wx_swz_group<T>(base + i) ^ (c * V), grow, base + i + c * V, &lo[c * V], last);
             int io = i + S + c * V;
             io = POW2 ? (io & (half - 1)) : (io % half);
-            wx_put_chunk<T, GST>(dst, grow, base + half + io, &hi[c * V], last);
+            wx_put_chunk<T, GST>(dst, wx_swz_group<T>(base + half + io), grow, base + half + io, &hi[c * V], last);
         }
     }
 }
@@ -114,10 +134,9 @@ __device__ __forceinline__ void wpd_small_level(const T *__restrict__ src, T *__
         const int e0 = u * G;
         T v[G], o[G];
 #pragma unroll
-        for (int c = 0; c < G / V; ++c) {
-            VT q = *reinterpret_cast<const VT *>(src + wx_swz_chunk((e0 + c * V) / V) * V);
-            wx_unpack(&v[c * V], q);
-        }
+        const int g0 = wx_swz_chunk(e0 / V) * V;         // G/V <= 4 chunks, aligned: chunk c sits at g0 ^ (c * V)
+#pragma unroll
+        for (int c = 0; c < G / V; ++c) wx_unpack(&v[c * V], *reinterpret_cast<const VT *>(src + (g0 ^ (c * V))));
 #pragma unroll
         for (int nd = 0; nd < G / P; ++nd) {
             if (TREE && !tmk.on(e0 / P + nd)) {
@@ -139,7 +158,7 @@ __device__ __forceinline__ void wpd_small_level(const T *__restrict__ src, T *__
             }
         }
 #pragma unroll
-        for (int c = 0; c < G / V; ++c) wx_put_chunk<T, GST>(dst, grow, e0 + c * V, &o[c * V], last);
+        for (int c = 0; c < G / V; ++c) wx_put_chunk<T, GST>(dst, g0 ^ (c * V), grow, e0 + c * V, &o[c * V], last);
     }
 }
 
@@ -207,7 +226,7 @@ __device__ __forceinline__ void wpd_level(const T *__restrict__ a, T *__restrict
 template <typename T, int F>
 struct IwptCfg {
     static constexpr int V = WxVec<T>::N;
-    static constexpr int K = 2 * V;                                    // output pairs per thread
+    static constexpr int K = 4 * V;                                    // output pairs per thread (reads at a 4-chunk stride: conflict free)
     static constexpr int R = F / 2;
     static constexpr int S = ((R - 1) + V - 1) / V * V;                // w1 look-behind (multiple of V)
     static constexpr int W = K + S;                                    // window length of each child
@@ -240,6 +259,8 @@ __device__ __forceinline__ void iwpt_wide_level(const T *__restrict__ src, T *__
     using C = IwptCfg<T, F>;
     using VT = typename WxVec<T>::type;
     constexpr int V = C::V, K = C::K, S = C::S, W = C::W;
+    constexpr int GA = (S + K - 1) / K;                 // aligned groups of K elements behind t0 touched by the w1 window
+    constexpr int NB = (W + K - 1) / K;                 // groups touched by the w2 window
     const int half = p >> 1;
     const int units = n0 / (2 * K);
     const int lgh = 31 - __clz(half);
@@ -248,29 +269,39 @@ __device__ __forceinline__ void iwpt_wide_level(const T *__restrict__ src, T *__
         const int j = POW2 ? (gi >> lgh) : (gi / half);
         const int t0 = gi - j * half;
         const int base = j * p;
+        const int go = wx_swz_group<T>(base + 2 * t0);  // the 2K outputs fill one aligned run of 8 chunks
         if (TREE && !tmk.on(j)) {
 #pragma unroll
-            for (int c = 0; c < 2 * K / V; ++c) {
-                const int ch = wx_swz_chunk((base + 2 * t0) / V + c) * V;
-                *reinterpret_cast<VT *>(dst + ch) = *reinterpret_cast<const VT *>(src + ch);
-            }
+            for (int c = 0; c < 2 * K / V; ++c) *reinterpret_cast<VT *>(dst + (go ^ (c * V))) = *reinterpret_cast<const VT *>(src + (go ^ (c * V)));
             continue;
+        }
+        int ga[GA + 1], gb[NB];
+#pragma unroll
+        for (int g = 0; g <= GA; ++g) {
+            int o = t0 - (GA - g) * K;
+            if (POW2) o &= half - 1; else { o %= half; if (o < 0) o += half; }
+            ga[g] = wx_swz_group<T>(base + o);
+        }
+#pragma unroll
+        for (int g = 0; g < NB; ++g) {
+            int o = t0 + g * K;
+            if (POW2) o &= half - 1; else o %= half;
+            gb[g] = wx_swz_group<T>(base + half + o);
         }
         T a[W], b[W];
 #pragma unroll
         for (int c = 0; c < W / V; ++c) {
-            int o1 = t0 - S + c * V, o2 = t0 + c * V;
-            if (POW2) { o1 &= half - 1; o2 &= half - 1; }
-            else { o1 %= half; if (o1 < 0) o1 += half; o2 %= half; }
-            wx_unpack(&a[c * V], *reinterpret_cast<const VT *>(src + wx_swz_chunk((base + o1) / V) * V));
-            wx_unpack(&b[c * V], *reinterpret_cast<const VT *>(src + wx_swz_chunk((base + half + o2) / V) * V));
+            constexpr int dummy = 0; (void)dummy;
+            const int pa = GA * K - S + c * V;           // element position of this chunk relative to the first w1 group
+            const int pb = c * V;
+            wx_unpack(&a[c * V], *reinterpret_cast<const VT *>(src + (ga[pa / K] ^ (pa % K))));
+            wx_unpack(&b[c * V], *reinterpret_cast<const VT *>(src + (gb[pb / K] ^ (pb % K))));
         }
         T out[2 * K];
 #pragma unroll
         for (int k = 0; k < K; ++k) iwpt_pair<T, F>(&a[S + k], &b[k], tp, out[2 * k], out[2 * k + 1]);
 #pragma unroll
-        for (int c = 0; c < 2 * K / V; ++c)
-            *reinterpret_cast<VT *>(dst + wx_swz_chunk((base + 2 * t0) / V + c) * V) = wx_pack(&out[c * V]);
+        for (int c = 0; c < 2 * K / V; ++c) *reinterpret_cast<VT *>(dst + (go ^ (c * V))) = wx_pack(&out[c * V]);
     }
 }
 
@@ -287,8 +318,9 @@ __device__ __forceinline__ void iwpt_small_level(const T *__restrict__ src, T *_
     for (int u = tid; u < groups; u += nthreads) {
         const int e0 = u * G;
         T v[G], o[G];
+        const int g0 = wx_swz_chunk(e0 / V) * V;         // G/V <= 4 chunks, aligned: chunk c sits at g0 ^ (c * V)
 #pragma unroll
-        for (int c = 0; c < G / V; ++c) wx_unpack(&v[c * V], *reinterpret_cast<const VT *>(src + wx_swz_chunk((e0 + c * V) / V) * V));
+        for (int c = 0; c < G / V; ++c) wx_unpack(&v[c * V], *reinterpret_cast<const VT *>(src + (g0 ^ (c * V))));
 #pragma unroll
         for (int nd = 0; nd < G / P; ++nd) {
             if (TREE && !tmk.on(e0 / P + nd)) {
@@ -315,7 +347,7 @@ __device__ __forceinline__ void iwpt_small_level(const T *__restrict__ src, T *_
             }
         }
 #pragma unroll
-        for (int c = 0; c < G / V; ++c) *reinterpret_cast<VT *>(dst + wx_swz_chunk((e0 + c * V) / V) * V) = wx_pack(&o[c * V]);
+        for (int c = 0; c < G / V; ++c) *reinterpret_cast<VT *>(dst + (g0 ^ (c * V))) = wx_pack(&o[c * V]);
     }
 }
 
@@ -374,6 +406,8 @@ __device__ __forceinline__ void iwpt_level(const T *__restrict__ a, T *__restric
         iwpt_small_level<T, F, 4, TREE>(a, b, n0, tp, tid, nthreads, tmk);
     } else if (p == 8) {
         iwpt_small_level<T, F, 8, TREE>(a, b, n0, tp, tid, nthreads, tmk);
+    } else if (p == 16 && V == 4) {
+        iwpt_small_level<T, F, 16, TREE>(a, b, n0, tp, tid, nthreads, tmk);
     } else {
         iwpt_generic_level<T, F, TREE>(a, b, n0, p, tp, tid, nthreads, tmk);
     }

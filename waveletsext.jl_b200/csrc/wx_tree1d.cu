@@ -76,7 +76,7 @@ int launch(T *y, const T *x, long n, long N, int d0, int nlev, const unsigned ch
     const long n0 = n >> d0;
     const long bufbytes = ((n0 * (long)sizeof(T) + 127) / 128) * 128;
     const size_t smem = (size_t)2 * bufbytes;
-    long units = n0 / (4 * V);
+    long units = n0 / (8 * V);
     int threads = (int)((units + 31) / 32 * 32);
     if (threads < 64) threads = 64;
     if (threads > 256) threads = 256;
