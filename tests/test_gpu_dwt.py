@@ -240,6 +240,20 @@ def test_wpd2d_parity(wx, O, cuda, dt, name, m, n, L):
 
 
 @pytest.mark.parametrize("dt", [np.float64, np.float32])
+@pytest.mark.parametrize("name", ["haar", "db4", "sym8", "db10"])
+@pytest.mark.parametrize("m,n,L", [(256, 128, 4), (96, 160, 3), (512, 512, 5), (64, 1024, 2), (128, 128, 7)])
+def test_wpd2d_large_images(wx, O, cuda, dt, name, m, n, L):
+    """images larger than shared memory: halo-tile kernel for the coarse levels, whole-node kernel below"""
+    wt = wx.wavelet(name)
+    h, g = pair(wx, wt)
+    x = np.random.default_rng(m + n + L).standard_normal((2, n, m)).astype(dt)
+    y = wx.wpdall(dev(x, cuda), wt, L)
+    ref = np.stack([O.wpd(x[k], h, g, L) for k in range(2)])
+    assert relerr(y.cpu().numpy(), ref) <= TOL[dt]
+    assert torch.equal(y[:, 0], dev(x, cuda))                                      # level 0 is a bit copy of x
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
 def test_wpt2d_trees(wx, O, cuda, dt):
     wt = wx.wavelet("db4")
     h, g = pair(wx, wt)

@@ -15,6 +15,14 @@ int wx_devinfo(WxDev &d)
     WX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     WX_CUDA(cudaDeviceGetAttribute(&smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     d.sms = sms; d.smem_optin = (size_t)smem; d.dev = dev;
+    // stream-ordered scratch (wx_scratch) comes from the default pool: keep freed blocks cached across synchronisations
+    // instead of returning them to the driver (the default threshold of 0 makes every call after a sync re-map memory)
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        unsigned long long keep = ~0ULL;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    cudaGetLastError();
     if (dev >= 0 && dev < 64) { cache[dev] = d; have[dev] = true; }
     return WX_OK;
 }

@@ -15,6 +15,9 @@ template <typename T>
 int wx_tree1d_fused(bool inverse, bool full, T *y, const T *x, long n, long N, int d0, int nlev, const unsigned char *dtree, long ntree,
                     const unsigned char *ddepth, int Kx, int vecgather, const Taps<T> &t, cudaStream_t s);
 
+// fused 2-D packet decomposition (wx_wpd2d.cu)
+template <typename T> int wx_wpd2d_fused(T *y, const T *x, long m, long n, int L, long N, const Taps<T> &t, cudaStream_t s, bool *handled);
+
 namespace {
 
 constexpr int kT = 256;
@@ -308,6 +311,9 @@ int wpd2d_impl(T *y, const T *x, long m, long n, int L, long N, const double *h,
     WX_REQUIRE(y && x, "null signal pointer");
     Taps<T> t; int rc = wx_make_taps(t, h, g, F); if (rc) return rc;
     const long img = m * n, ys = img * (L + 1);
+    bool handled = false;
+    rc = wx_wpd2d_fused<T>(y, x, m, n, L, N, t, s, &handled);
+    if (rc || handled) return rc;
     rc = wx_launch_copy<T>(View<T>{y, 1, ys, 0, 0}, View<const T>{x, 1, img, 0, 0}, img, Batch{N, 1, 1, false}, s);
     if (rc || L == 0) return rc;
     const long Nc = chunk_images(m, n, sizeof(T), N);
