@@ -39,6 +39,16 @@ __device__ __forceinline__ void dwt_dots(const T *w, const Taps<T> &tp, T &lo, T
     hi = b;
 }
 
+// asynchronous global -> shared copy of one pair of elements (LDGSTS): many copies in flight per thread, no register staging
+template <typename T>
+__device__ __forceinline__ void cp_async_pair(T *smem_dst, const T *gsrc)
+{
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    if (sizeof(T) == 8) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gsrc) : "memory");
+    else                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); }
+
 struct FastDiv {                    // division by a runtime constant that is usually a power of two
     int d, lg;
     __host__ __device__ FastDiv() : d(1), lg(0) {}
@@ -50,21 +60,53 @@ struct FastDiv {                    // division by a runtime constant that is us
     __device__ __forceinline__ int mod(int x) const { return lg >= 0 ? (x & (d - 1)) : (x % d); }
 };
 
+// walks the index pairs (hi, lo), lo < len, of idx = tid, tid + kT2, ... without a division per step
+struct Walk2 {
+    int lo, hi, qlo, qhi, len;
+    __device__ __forceinline__ Walk2(int tid, int l) : len(l)
+    {
+        hi = tid / l; lo = tid - hi * l;
+        qhi = kT2 / l; qlo = kT2 - qhi * l;
+    }
+    __device__ __forceinline__ void next()
+    {
+        lo += qlo; hi += qhi;
+        if (lo >= len) { lo -= len; ++hi; }
+    }
+};
+
+// Two adjacent output pairs from one window: w[0..F+1] = v[2i .. 2i+F+1]
+template <typename T, int F>
+__device__ __forceinline__ void dwt_dots2(const T *w, const Taps<T> &tp, T &lo0, T &hi0, T &lo1, T &hi1)
+{
+    T a0 = tp.g[F - 1] * w[0], a1 = tp.g[F - 1] * w[2];
+    T b0 = tp.h[0] * w[F - 1], b1 = tp.h[0] * w[F + 1];
+#pragma unroll
+    for (int j = 1; j < F; ++j) {
+        a0 = fma(tp.g[F - 1 - j], w[j], a0);
+        a1 = fma(tp.g[F - 1 - j], w[j + 2], a1);
+        b0 = fma(tp.h[j], w[F - 1 - j], b0);
+        b1 = fma(tp.h[j], w[F + 1 - j], b1);
+    }
+    lo0 = a0; lo1 = a1; hi0 = b0; hi1 = b1;
+}
+
 // ---------------------------------------------------------------------------------------------------------
-// one level, tiles with halo
+// one level, tiles with halo.  Shared memory: P (PR+2 rows x PC) parent patch, Tm (2tr rows x PC+2) column-pass output;
+// the +2 padding lets the last thread of a row / column compute a (discarded) second pair without leaving the arrays.
 // ---------------------------------------------------------------------------------------------------------
 template <typename T, int F>
-__global__ void __launch_bounds__(kT2) wpd2d_tile_k(T *__restrict__ y, const T *__restrict__ x, long m, long n, int L, int d, int tr, int tc,
+__global__ void __launch_bounds__(kT2) wpd2d_tile_k(T *__restrict__ y, const T *__restrict__ x, int m, int n, int L, int d, int tr, int tc,
                                                    Taps<T> tp)
 {
     using P2 = typename Pair<T>::type;
     constexpr int S = (F - 2) / 2;
     extern __shared__ __align__(16) unsigned char wx_2d_smem[];
-    const int PR = 2 * tr + F - 2, PC = 2 * tc + F - 2;
-    T *P = reinterpret_cast<T *>(wx_2d_smem);           // (PR, PC) parent patch, column-major
-    T *Tm = P + (size_t)PR * PC;                         // (2tr, PC) after the column pass: rows [0,tr) scaling, [tr,2tr) detail
+    const int PR = 2 * tr + F - 2, PC = 2 * tc + F - 2, LDP = PR + 2, R2 = 2 * tr;
+    T *P = reinterpret_cast<T *>(wx_2d_smem);
+    T *Tm = P + LDP * PC;
     const int tid = threadIdx.x;
-    const int mp = (int)(m >> d), np = (int)(n >> d), hr = mp / 2, hc = np / 2;
+    const int mp = m >> d, np = n >> d, hr = mp / 2, hc = np / 2;
     const int tiles_r = hr / tr, tiles_c = hc / tc, nodes = 1 << d;
     // block -> (tile row, node row, tile col, node col, image); neighbouring CTAs walk down the rows of the image
     long bid = blockIdx.x;
@@ -73,149 +115,221 @@ __global__ void __launch_bounds__(kT2) wpd2d_tile_k(T *__restrict__ y, const T *
     const int tk = (int)(bid % tiles_c); bid /= tiles_c;
     const int jc = (int)(bid % nodes); bid /= nodes;
     const long k = bid;
-    const long img = m * n;
+    const long img = (long)m * n;
     T *yk = y + k * img * (L + 1);
     const bool from_x = (d == 0 && x != nullptr);
-    const T *par = from_x ? (x + k * img) : (yk + (long)d * img);
     const int nr0 = jr * mp, nc0 = jc * np;              // node origin in the image
     const int i0 = ti * tr, k0 = tk * tc;                // tile origin in child coordinates
+    const T *par = (from_x ? (x + k * img) : (yk + (long)d * img)) + (long)nc0 * m + nr0;
 
-    // ---- parent patch (periodic inside the node), two rows per thread ----
-    const int PR2 = PR / 2;
-    for (int idx = tid; idx < PR2 * PC; idx += kT2) {
-        const int b = idx / PR2, a = 2 * (idx - b * PR2);
-        int rr = 2 * i0 + a; rr %= mp;
-        int cc = 2 * k0 + b; cc %= np;
-        const P2 v = *reinterpret_cast<const P2 *>(par + (long)(nc0 + cc) * m + nr0 + rr);
-        *reinterpret_cast<P2 *>(P + (size_t)b * PR + a) = v;
-        if (from_x && a < 2 * tr && b < 2 * tc)          // y[:,:,1] = x   DWT.jl:176
-            *reinterpret_cast<P2 *>(yk + (long)(nc0 + 2 * k0 + b) * m + nr0 + 2 * i0 + a) = v;
-    }
-    __syncthreads();
-    // ---- column pass: every column of the patch, tr output pairs ----
-    for (int idx = tid; idx < tr * PC; idx += kT2) {
-        const int b = idx / tr, il = idx - b * tr;
-        T w[F];
-        const T *src = P + (size_t)b * PR + 2 * il;
-#pragma unroll
-        for (int q = 0; q < F / 2; ++q) {
-            const P2 v = *reinterpret_cast<const P2 *>(src + 2 * q);
-            w[2 * q] = v.x; w[2 * q + 1] = v.y;
+    // ---- parent patch (periodic inside the node), two rows per asynchronous copy ----
+    {
+        const int PR2 = PR / 2;
+        for (Walk2 w(tid, PR2); w.hi < PC; w.next()) {
+            const int b = w.hi, a = 2 * w.lo;
+            int rr = 2 * i0 + a; while (rr >= mp) rr -= mp;
+            int cc = 2 * k0 + b; while (cc >= np) cc -= np;
+            cp_async_pair<T>(P + b * LDP + a, par + cc * m + rr);
         }
-        T lo, hi;
-        dwt_dots<T, F>(w, tp, lo, hi);
-        Tm[(size_t)b * (2 * tr) + il] = lo;
-        Tm[(size_t)b * (2 * tr) + tr + il] = hi;
+        cp_async_wait_all();
     }
     __syncthreads();
-    // ---- row pass + store: (2tr rows) x (tc output pairs) ----
-    T *ynext = yk + (long)(d + 1) * img;
-    const int R2 = 2 * tr;
-    for (int idx = tid; idx < R2 * tc; idx += kT2) {
-        const int kl = idx / R2, r = idx - kl * R2;
-        T w[F];
+    if (from_x) {                                         // y[:,:,1] = x   DWT.jl:176 : the core of the patch
+        T *y0 = yk + (long)(nc0 + 2 * k0) * m + nr0 + 2 * i0;
+        for (Walk2 w(tid, tr); w.hi < 2 * tc; w.next())
+            *reinterpret_cast<P2 *>(y0 + w.hi * m + 2 * w.lo) = *reinterpret_cast<const P2 *>(P + w.hi * LDP + 2 * w.lo);
+    }
+    // ---- column pass: every column of the patch; a thread owns pairs il and il + ceil(tr/2) (lanes walk consecutive il:
+    //      conflict-free 16-byte loads) ----
+    {
+        const int trh = (tr + 1) / 2;
+        for (Walk2 w(tid, trh); w.hi < PC; w.next()) {
+            const int b = w.hi, il = w.lo;
+            const bool two = il + trh < tr;
+            T w0[F], w1[F];
+            const T *src = P + b * LDP + 2 * il;
 #pragma unroll
-        for (int j = 0; j < F; ++j) w[j] = Tm[(size_t)(2 * kl + j) * R2 + r];
-        T lo, hi;
-        dwt_dots<T, F>(w, tp, lo, hi);
-        int ci, qr;
-        if (r < tr) { ci = i0 + r; qr = 0; }
-        else { ci = (i0 + (r - tr) + S) % hr; qr = hr; }
-        const int ck_lo = k0 + kl, ck_hi = (k0 + kl + S) % hc;
-        T *o = ynext + nr0 + qr + ci;
-        o[(long)(nc0 + ck_lo) * m] = lo;                 // w1 / w3
-        o[(long)(nc0 + hc + ck_hi) * m] = hi;            // w2 / w4
+            for (int q = 0; q < F / 2; ++q) {
+                const P2 v = *reinterpret_cast<const P2 *>(src + 2 * q);
+                w0[2 * q] = v.x; w0[2 * q + 1] = v.y;
+                const P2 u = *reinterpret_cast<const P2 *>(src + (two ? 2 * trh : 0) + 2 * q);
+                w1[2 * q] = u.x; w1[2 * q + 1] = u.y;
+            }
+            T lo0, hi0, lo1, hi1;
+            dwt_dots<T, F>(w0, tp, lo0, hi0);
+            dwt_dots<T, F>(w1, tp, lo1, hi1);
+            T *dst = Tm + b * R2 + il;
+            dst[0] = lo0; dst[tr] = hi0;
+            if (two) { dst[trh] = lo1; dst[tr + trh] = hi1; }
+        }
+    }
+    __syncthreads();
+    // ---- row pass + store: (2tr rows) x (tc output pairs), two pairs per thread ----
+    {
+        T *ynext = yk + (long)(d + 1) * img + (long)nc0 * m + nr0;
+        const int tcq = (tc + 1) / 2;
+        for (Walk2 w(tid, R2); w.hi < tcq; w.next()) {
+            const int kl = 2 * w.hi, r = w.lo;
+            T win[F + 2];
+            const T *src = Tm + (2 * kl) * R2 + r;
+#pragma unroll
+            for (int j = 0; j < F + 2; ++j) win[j] = src[j * R2];
+            T lo0, hi0, lo1, hi1;
+            dwt_dots2<T, F>(win, tp, lo0, hi0, lo1, hi1);
+            int ci, qr;
+            if (r < tr) { ci = i0 + r; qr = 0; }
+            else { ci = i0 + (r - tr) + S; while (ci >= hr) ci -= hr; qr = hr; }
+            int ch0 = k0 + kl + S; while (ch0 >= hc) ch0 -= hc;
+            T *o = ynext + qr + ci;
+            o[(k0 + kl) * m] = lo0;                       // w1 / w3
+            o[(hc + ch0) * m] = hi0;                      // w2 / w4
+            if (kl + 1 < tc) {
+                int ch1 = ch0 + 1; if (ch1 >= hc) ch1 -= hc;
+                o[(k0 + kl + 1) * m] = lo1;
+                o[(hc + ch1) * m] = hi1;
+            }
+        }
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------
 // all remaining levels of a node that fits shared memory
 // ---------------------------------------------------------------------------------------------------------
+// one window of NW values starting at element 2*il of a periodic vector of length len (stride st)
+template <typename T, int NW>
+__device__ __forceinline__ void load_window(T *win, const T *src, int start, int len, int st)
+{
+    if (len >= NW) {                                       // at most one wrap
+#pragma unroll
+        for (int j = 0; j < NW; ++j) { int e = start + j; if (e >= len) e -= len; win[j] = src[e * st]; }
+    } else {
+#pragma unroll
+        for (int j = 0; j < NW; ++j) win[j] = src[((start + j) % len) * st];
+    }
+}
+
+// same for a contiguous vector, even start and even length: 16-byte (8-byte for Float32) loads of element pairs
+template <typename T, int NW>
+__device__ __forceinline__ void load_window_pairs(T *win, const T *src, int start, int len)
+{
+    using P2 = typename Pair<T>::type;
+    if (len >= NW) {
+#pragma unroll
+        for (int q = 0; q < NW / 2; ++q) {
+            int e = start + 2 * q; if (e >= len) e -= len;
+            const P2 v = *reinterpret_cast<const P2 *>(src + e);
+            win[2 * q] = v.x; win[2 * q + 1] = v.y;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < NW; ++j) win[j] = src[(start + j) % len];
+    }
+}
+
 template <typename T, int F>
-__global__ void __launch_bounds__(kT2) wpd2d_block_k(T *__restrict__ y, const T *__restrict__ x, long m, long n, int L, int db, int dend,
+__global__ void __launch_bounds__(kT2) wpd2d_block_k(T *__restrict__ y, const T *__restrict__ x, int m, int n, int L, int db, int dend,
                                                     Taps<T> tp)
 {
     using P2 = typename Pair<T>::type;
     constexpr int S = (F - 2) / 2;
     extern __shared__ __align__(16) unsigned char wx_2d_smem[];
-    const int BR = (int)(m >> db), BC = (int)(n >> db);
+    const int BR = m >> db, BC = n >> db;
     T *A = reinterpret_cast<T *>(wx_2d_smem);            // (BR, BC) column-major: the block at the current level
-    T *Tm = A + (size_t)BR * BC;                          // after the column pass
+    T *Tm = A + BR * BC;                                  // after the column pass
     const int tid = threadIdx.x;
     const int nodes = 1 << db;
     long bid = blockIdx.x;
     const int jr = (int)(bid % nodes); bid /= nodes;
     const int jc = (int)(bid % nodes); bid /= nodes;
     const long k = bid;
-    const long img = m * n;
+    const long img = (long)m * n;
     T *yk = y + k * img * (L + 1);
     const bool from_x = (db == 0 && x != nullptr);
-    const T *par = from_x ? (x + k * img) : (yk + (long)db * img);
     const long org = (long)(jc * BC) * m + jr * BR;       // block origin in the image
+    const T *par = (from_x ? (x + k * img) : (yk + (long)db * img)) + org;
     const int BR2 = BR / 2;
-    const FastDiv dBR2(BR2), dBR(BR);
 
-    for (int idx = tid; idx < BR2 * BC; idx += kT2) {
-        const int b = dBR2.div(idx), a = 2 * (idx - b * BR2);
-        const P2 v = *reinterpret_cast<const P2 *>(par + org + (long)b * m + a);
-        *reinterpret_cast<P2 *>(A + (size_t)b * BR + a) = v;
-        if (from_x) *reinterpret_cast<P2 *>(yk + org + (long)b * m + a) = v;
-    }
+    for (Walk2 w(tid, BR2); w.hi < BC; w.next()) cp_async_pair<T>(A + w.hi * BR + 2 * w.lo, par + w.hi * m + 2 * w.lo);
+    cp_async_wait_all();
     __syncthreads();
+    if (from_x) {                                         // y[:,:,1] = x   DWT.jl:176
+        for (Walk2 w(tid, BR2); w.hi < BC; w.next())
+            *reinterpret_cast<P2 *>(yk + org + w.hi * m + 2 * w.lo) = *reinterpret_cast<const P2 *>(A + w.hi * BR + 2 * w.lo);
+    }
     for (int l = db; l < dend; ++l) {
-        const int mpl = (int)(m >> l), npl = (int)(n >> l), hr = mpl / 2, hc = npl / 2;
-        const FastDiv dhr(hr), dhc(hc);
-        // column pass A -> Tm, per node: scaling rows on top, detail rows below (shift resolved here)
-        for (int idx = tid; idx < BR2 * BC; idx += kT2) {
-            const int b = dBR2.div(idx), ig = idx - b * BR2;
-            const int jn = dhr.div(ig), il = ig - jn * hr, r0 = jn * mpl;
-            const T *src = A + (size_t)b * BR + r0;
-            T w[F];
-            if (mpl >= F) {                                // at most one wrap, pairs stay together
+        const int mpl = m >> l, npl = n >> l, hr = mpl / 2, hc = npl / 2;
+        // ---- column pass A -> Tm, per node: scaling rows on top, detail rows below (shift resolved here) ----
+        if (BR2 % 2 == 0) {                                // two pairs per thread: ig and ig + BR2/2 (consecutive lanes, consecutive pairs)
+            const FastDiv dq(hr);
+            for (Walk2 w(tid, BR2 / 2); w.hi < BC; w.next()) {
+                const int b = w.hi;
+                T lo[2], hi[2];
+                int il[2], r0[2];
 #pragma unroll
-                for (int q = 0; q < F / 2; ++q) {
-                    int rr = 2 * il + 2 * q; if (rr >= mpl) rr -= mpl;
-                    const P2 v = *reinterpret_cast<const P2 *>(src + rr);
-                    w[2 * q] = v.x; w[2 * q + 1] = v.y;
+                for (int t = 0; t < 2; ++t) {
+                    const int ig = w.lo + t * (BR2 / 2), jn = dq.div(ig);
+                    il[t] = ig - jn * hr; r0[t] = jn * mpl;
+                    T win[F];
+                    load_window_pairs<T, F>(win, A + b * BR + r0[t], 2 * il[t], mpl);
+                    dwt_dots<T, F>(win, tp, lo[t], hi[t]);
                 }
-            } else {
 #pragma unroll
-                for (int j = 0; j < F; ++j) w[j] = src[(2 * il + j) % mpl];
+                for (int t = 0; t < 2; ++t) {
+                    T *dst = Tm + b * BR + r0[t];
+                    dst[il[t]] = lo[t];
+                    int ih = il[t] + S; if (ih >= hr) ih %= hr;
+                    dst[hr + ih] = hi[t];
+                }
             }
-            T lo, hi;
-            dwt_dots<T, F>(w, tp, lo, hi);
-            T *dst = Tm + (size_t)b * BR + r0;
-            dst[il] = lo;
-            int ih = il + S; if (ih >= hr) ih = dhr.mod(ih);
-            dst[hr + ih] = hi;
+        } else {
+            const FastDiv dq(hr);
+            for (Walk2 w(tid, BR2); w.hi < BC; w.next()) {
+                const int b = w.hi, jn = dq.div(w.lo), il = w.lo - jn * hr, r0 = jn * mpl;
+                T win[F];
+                load_window_pairs<T, F>(win, A + b * BR + r0, 2 * il, mpl);
+                T lo, hi;
+                dwt_dots<T, F>(win, tp, lo, hi);
+                T *dst = Tm + b * BR + r0;
+                dst[il] = lo;
+                dst[hr + (il + S) % hr] = hi;
+            }
         }
         __syncthreads();
-        // row pass Tm -> A, per node: scaling columns left, detail columns right
-        for (int idx = tid; idx < BR * (BC / 2); idx += kT2) {
-            const int kg = dBR.div(idx), r = idx - kg * BR;
-            const int jn = dhc.div(kg), kl = kg - jn * hc, c0 = jn * npl;
-            const T *src = Tm + (size_t)c0 * BR + r;
-            T w[F];
-            if (npl >= F) {
-#pragma unroll
-                for (int j = 0; j < F; ++j) { int cc = 2 * kl + j; if (cc >= npl) cc -= npl; w[j] = src[(size_t)cc * BR]; }
-            } else {
-#pragma unroll
-                for (int j = 0; j < F; ++j) w[j] = src[(size_t)((2 * kl + j) % npl) * BR];
+        // ---- row pass Tm -> A, per node: scaling columns left, detail columns right ----
+        if (hc % 2 == 0) {
+            const FastDiv dq(hc / 2);
+            for (Walk2 w(tid, BR); w.hi < BC / 4; w.next()) {
+                const int r = w.lo, jn = dq.div(w.hi), kl = 2 * (w.hi - jn * (hc / 2)), c0 = jn * npl;
+                T win[F + 2];
+                load_window<T, F + 2>(win, Tm + c0 * BR + r, 2 * kl, npl, BR);
+                T lo0, hi0, lo1, hi1;
+                dwt_dots2<T, F>(win, tp, lo0, hi0, lo1, hi1);
+                T *dst = A + c0 * BR + r;
+                dst[kl * BR] = lo0; dst[(kl + 1) * BR] = lo1;
+                int kh = kl + S; if (kh >= hc) kh %= hc;
+                dst[(hc + kh) * BR] = hi0;
+                ++kh; if (kh >= hc) kh -= hc;
+                dst[(hc + kh) * BR] = hi1;
             }
-            T lo, hi;
-            dwt_dots<T, F>(w, tp, lo, hi);
-            T *dst = A + (size_t)c0 * BR + r;
-            dst[(size_t)kl * BR] = lo;
-            int kh = kl + S; if (kh >= hc) kh = dhc.mod(kh);
-            dst[(size_t)(hc + kh) * BR] = hi;
+        } else {
+            const FastDiv dq(hc);
+            for (Walk2 w(tid, BR); w.hi < BC / 2; w.next()) {
+                const int r = w.lo, jn = dq.div(w.hi), kl = w.hi - jn * hc, c0 = jn * npl;
+                T win[F];
+                load_window<T, F>(win, Tm + c0 * BR + r, 2 * kl, npl, BR);
+                T lo, hi;
+                dwt_dots<T, F>(win, tp, lo, hi);
+                T *dst = A + c0 * BR + r;
+                dst[kl * BR] = lo;
+                dst[(hc + (kl + S) % hc) * BR] = hi;
+            }
         }
         __syncthreads();
-        // level l+1 slice
+        // ---- level l+1 slice ----
         T *ynext = yk + (long)(l + 1) * img + org;
-        for (int idx = tid; idx < BR2 * BC; idx += kT2) {
-            const int b = dBR2.div(idx), a = 2 * (idx - b * BR2);
-            *reinterpret_cast<P2 *>(ynext + (long)b * m + a) = *reinterpret_cast<const P2 *>(A + (size_t)b * BR + a);
+        for (Walk2 w(tid, BR2); w.hi < BC; w.next()) {
+            const int b = w.hi, a = 2 * w.lo;
+            *reinterpret_cast<P2 *>(ynext + b * m + a) = *reinterpret_cast<const P2 *>(A + b * BR + a);
         }
         // the next column pass only reads A (complete after the barrier above) and writes Tm (free): no barrier needed here
     }
@@ -242,13 +356,13 @@ int wpd2d_run(T *y, const T *x, long m, long n, int L, long N, const Taps<T> &t,
         const long hr = (m >> d) / 2, hc = (n >> d) / 2;
         const int tr = largest_divisor_le(hr, cap), tc = largest_divisor_le(hc, cap);
         const int PR = 2 * tr + F - 2, PC = 2 * tc + F - 2;
-        const size_t smem = ((size_t)PR * PC + (size_t)2 * tr * PC) * sizeof(T);
+        const size_t smem = ((size_t)(PR + 2) * PC + (size_t)2 * tr * (PC + 2)) * sizeof(T);
         if (smem > dv.smem_optin) return wx_fail(WX_EUNSUPPORTED, "wpd 2-D tile does not fit shared memory");
         const long blocks = (hr / tr) * (hc / tc) * (1L << (2 * d)) * N;
         if (blocks >= (1L << 31)) return wx_fail(WX_EUNSUPPORTED, "wpd 2-D: too many tiles for one launch");
         auto kern = wpd2d_tile_k<T, F>;
         WX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<(unsigned)blocks, kT2, smem, s>>>(y, d == 0 ? x : nullptr, m, n, L, d, tr, tc, t);
+        kern<<<(unsigned)blocks, kT2, smem, s>>>(y, d == 0 ? x : nullptr, (int)m, (int)n, L, d, tr, tc, t);
         WX_LAUNCHED();
     }
     if (db < L) {
@@ -257,7 +371,7 @@ int wpd2d_run(T *y, const T *x, long m, long n, int L, long N, const Taps<T> &t,
         if (blocks >= (1L << 31)) return wx_fail(WX_EUNSUPPORTED, "wpd 2-D: too many blocks for one launch");
         auto kern = wpd2d_block_k<T, F>;
         WX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<(unsigned)blocks, kT2, smem, s>>>(y, db == 0 ? x : nullptr, m, n, L, db, L, t);
+        kern<<<(unsigned)blocks, kT2, smem, s>>>(y, db == 0 ? x : nullptr, (int)m, (int)n, L, db, L, t);
         WX_LAUNCHED();
     }
     return WX_OK;
@@ -271,7 +385,7 @@ int wx_wpd2d_fused(T *y, const T *x, long m, long n, int L, long N, const Taps<T
 {
     *handled = false;
     static const bool off = getenv("WX_B200_NO_FUSED_WPD2D") != nullptr;   // debugging / A-B measurements only
-    if (off || L < 1 || N < 1 || m >= (1L << 20) || n >= (1L << 20)) return WX_OK;
+    if (off || L < 1 || N < 1 || m * n >= (1L << 31)) return WX_OK;
     if (((((uintptr_t)y) | ((uintptr_t)x)) & 15) != 0) return WX_OK;
     if ((m >> (L - 1)) % 2 != 0 || (n >> (L - 1)) % 2 != 0) return WX_OK;
     int rc;
