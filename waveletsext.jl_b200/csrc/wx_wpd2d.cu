@@ -91,6 +91,9 @@ __device__ __forceinline__ void dwt_dots2(const T *w, const Taps<T> &tp, T &lo0,
     lo0 = a0; lo1 = a1; hi0 = b0; hi1 = b1;
 }
 
+// K consecutive output pairs from one window: win[0 .. 2K+F-3] = v[2i .. 2i+2K+F-3]; pair p uses win[2p .. 2p+F-1]
+constexpr int KROW = 8;
+
 // ---------------------------------------------------------------------------------------------------------
 // one level, tiles with halo.  Shared memory: P (PR+2 rows x PC) parent patch, Tm (2tr rows x PC+2) column-pass output;
 // the +2 padding lets the last thread of a row / column compute a (discarded) second pair without leaving the arrays.
@@ -102,7 +105,7 @@ __global__ void __launch_bounds__(kT2) wpd2d_tile_k(T *__restrict__ y, const T *
     using P2 = typename Pair<T>::type;
     constexpr int S = (F - 2) / 2;
     extern __shared__ __align__(16) unsigned char wx_2d_smem[];
-    const int PR = 2 * tr + F - 2, PC = 2 * tc + F - 2, LDP = PR + 2, R2 = 2 * tr;
+    const int PR = 2 * tr + F - 2, PC = 2 * tc + F - 2, LDP = PR + 2 * (tr & 1), R2 = 2 * tr;    // odd tiles: padded (see host)
     T *P = reinterpret_cast<T *>(wx_2d_smem);
     T *Tm = P + LDP * PC;
     const int tid = threadIdx.x;
@@ -141,7 +144,29 @@ __global__ void __launch_bounds__(kT2) wpd2d_tile_k(T *__restrict__ y, const T *
     }
     // ---- column pass: every column of the patch; a thread owns pairs il and il + ceil(tr/2) (lanes walk consecutive il:
     //      conflict-free 16-byte loads) ----
-    {
+    if (tr <= 32 && (32 % tr) == 0) {
+        // lanes walk il (conflict-free 16-byte loads), 32/tr columns per warp, warps stride over the columns, two columns in flight
+        const int lane = tid & 31, warp = tid >> 5, cpw = 32 / tr, il = lane % tr, bstep = (kT2 / 32) * cpw;
+        for (int b = warp * cpw + lane / tr; b < PC; b += 2 * bstep) {
+            const bool two = b + bstep < PC;
+            const T *s0 = P + b * LDP + 2 * il;
+            const T *s1 = two ? s0 + bstep * LDP : s0;
+            T w0[F], w1[F];
+#pragma unroll
+            for (int q = 0; q < F / 2; ++q) {
+                const P2 v = *reinterpret_cast<const P2 *>(s0 + 2 * q);
+                const P2 u = *reinterpret_cast<const P2 *>(s1 + 2 * q);
+                w0[2 * q] = v.x; w0[2 * q + 1] = v.y;
+                w1[2 * q] = u.x; w1[2 * q + 1] = u.y;
+            }
+            T lo0, hi0, lo1, hi1;
+            dwt_dots<T, F>(w0, tp, lo0, hi0);
+            dwt_dots<T, F>(w1, tp, lo1, hi1);
+            T *d0 = Tm + b * R2 + il;
+            d0[0] = lo0; d0[tr] = hi0;
+            if (two) { d0[bstep * R2] = lo1; d0[bstep * R2 + tr] = hi1; }
+        }
+    } else {
         const int trh = (tr + 1) / 2;
         for (Walk2 w(tid, trh); w.hi < PC; w.next()) {
             const int b = w.hi, il = w.lo;
@@ -165,8 +190,32 @@ __global__ void __launch_bounds__(kT2) wpd2d_tile_k(T *__restrict__ y, const T *
     }
     __syncthreads();
     // ---- row pass + store: (2tr rows) x (tc output pairs), two pairs per thread ----
-    {
-        T *ynext = yk + (long)(d + 1) * img + (long)nc0 * m + nr0;
+    T *ynext = yk + (long)(d + 1) * img + (long)nc0 * m + nr0;
+    if ((kT2 % R2) == 0 && (tc % KROW) == 0) {
+        // a thread owns one row r and KROW consecutive output columns: one window of 2*KROW+F-2 samples slides along the row
+        const int r = tid % R2;
+        int ci, qr;
+        if (r < tr) { ci = i0 + r; qr = 0; }
+        else { ci = i0 + (r - tr) + S; while (ci >= hr) ci -= hr; qr = hr; }
+        T *o = ynext + qr + ci;
+        for (int g = tid / R2; g < tc / KROW; g += kT2 / R2) {
+            const int kl0 = KROW * g;
+            T win[2 * KROW + F - 2];
+            const T *src = Tm + (2 * kl0) * R2 + r;
+#pragma unroll
+            for (int j = 0; j < 2 * KROW + F - 2; ++j) win[j] = src[j * R2];
+            int ch = k0 + kl0 + S; while (ch >= hc) ch -= hc;
+            T *olo = o + (k0 + kl0) * m;
+#pragma unroll
+            for (int p = 0; p < KROW; ++p) {
+                T lo, hi;
+                dwt_dots<T, F>(&win[2 * p], tp, lo, hi);
+                olo[p * m] = lo;                          // w1 / w3
+                o[(hc + ch) * m] = hi;                    // w2 / w4
+                ++ch; if (ch >= hc) ch -= hc;
+            }
+        }
+    } else {
         const int tcq = (tc + 1) / 2;
         for (Walk2 w(tid, R2); w.hi < tcq; w.next()) {
             const int kl = 2 * w.hi, r = w.lo;
@@ -259,7 +308,34 @@ __global__ void __launch_bounds__(kT2) wpd2d_block_k(T *__restrict__ y, const T 
     for (int l = db; l < dend; ++l) {
         const int mpl = m >> l, npl = n >> l, hr = mpl / 2, hc = npl / 2;
         // ---- column pass A -> Tm, per node: scaling rows on top, detail rows below (shift resolved here) ----
-        if (BR2 % 2 == 0) {                                // two pairs per thread: ig and ig + BR2/2 (consecutive lanes, consecutive pairs)
+        if (BR2 <= 32 && (32 % BR2) == 0 && mpl >= F) {
+            // lanes walk the pairs of one column (conflict-free 16-byte loads), warps stride over the columns, two in flight
+            const int lane = tid & 31, warp = tid >> 5, cpw = 32 / BR2, ig = lane % BR2, bstep = (kT2 / 32) * cpw;
+            const int jn = ig / hr, il = ig - jn * hr, r0 = jn * mpl;
+            int ih = il + S; if (ih >= hr) ih %= hr;
+            int e[F / 2];
+#pragma unroll
+            for (int q = 0; q < F / 2; ++q) { e[q] = 2 * il + 2 * q; if (e[q] >= mpl) e[q] -= mpl; }
+            for (int b = warp * cpw + lane / BR2; b < BC; b += 2 * bstep) {
+                const bool two = b + bstep < BC;
+                const T *s0 = A + b * BR + r0;
+                const T *s1 = two ? s0 + bstep * BR : s0;
+                T w0[F], w1[F];
+#pragma unroll
+                for (int q = 0; q < F / 2; ++q) {
+                    const P2 v = *reinterpret_cast<const P2 *>(s0 + e[q]);
+                    const P2 u = *reinterpret_cast<const P2 *>(s1 + e[q]);
+                    w0[2 * q] = v.x; w0[2 * q + 1] = v.y;
+                    w1[2 * q] = u.x; w1[2 * q + 1] = u.y;
+                }
+                T lo0, hi0, lo1, hi1;
+                dwt_dots<T, F>(w0, tp, lo0, hi0);
+                dwt_dots<T, F>(w1, tp, lo1, hi1);
+                T *d0 = Tm + b * BR + r0;
+                d0[il] = lo0; d0[hr + ih] = hi0;
+                if (two) { d0[bstep * BR + il] = lo1; d0[bstep * BR + hr + ih] = hi1; }
+            }
+        } else if (BR2 % 2 == 0) {                         // two pairs per thread: ig and ig + BR2/2 (consecutive lanes, consecutive pairs)
             const FastDiv dq(hr);
             for (Walk2 w(tid, BR2 / 2); w.hi < BC; w.next()) {
                 const int b = w.hi;
@@ -296,7 +372,27 @@ __global__ void __launch_bounds__(kT2) wpd2d_block_k(T *__restrict__ y, const T 
         }
         __syncthreads();
         // ---- row pass Tm -> A, per node: scaling columns left, detail columns right ----
-        if (hc % 2 == 0) {
+        if ((kT2 % BR) == 0 && (hc % KROW) == 0 && npl >= F) {
+            // a thread owns one row r and KROW consecutive output columns of one node: sliding window along the row
+            const int r = tid % BR;
+            for (int g = tid / BR; g < BC / (2 * KROW); g += kT2 / BR) {
+                const int kg0 = KROW * g, jn = kg0 / hc, kl0 = kg0 - jn * hc, c0 = jn * npl;
+                T win[2 * KROW + F - 2];
+                const T *src = Tm + c0 * BR + r;
+#pragma unroll
+                for (int j = 0; j < 2 * KROW + F - 2; ++j) { int cc = 2 * kl0 + j; if (cc >= npl) cc -= npl; win[j] = src[cc * BR]; }
+                int kh = kl0 + S; if (kh >= hc) kh %= hc;
+                T *dst = A + c0 * BR + r;
+#pragma unroll
+                for (int p = 0; p < KROW; ++p) {
+                    T lo, hi;
+                    dwt_dots<T, F>(&win[2 * p], tp, lo, hi);
+                    dst[(kl0 + p) * BR] = lo;
+                    dst[(hc + kh) * BR] = hi;
+                    ++kh; if (kh >= hc) kh -= hc;
+                }
+            }
+        } else if (hc % 2 == 0) {
             const FastDiv dq(hc / 2);
             for (Walk2 w(tid, BR); w.hi < BC / 4; w.next()) {
                 const int r = w.lo, jn = dq.div(w.hi), kl = 2 * (w.hi - jn * (hc / 2)), c0 = jn * npl;
@@ -356,7 +452,7 @@ int wpd2d_run(T *y, const T *x, long m, long n, int L, long N, const Taps<T> &t,
         const long hr = (m >> d) / 2, hc = (n >> d) / 2;
         const int tr = largest_divisor_le(hr, cap), tc = largest_divisor_le(hc, cap);
         const int PR = 2 * tr + F - 2, PC = 2 * tc + F - 2;
-        const size_t smem = ((size_t)(PR + 2) * PC + (size_t)2 * tr * (PC + 2)) * sizeof(T);
+        const size_t smem = ((size_t)(PR + 2 * (tr & 1)) * PC + (size_t)2 * tr * (PC + 2 * (tc & 1))) * sizeof(T);
         if (smem > dv.smem_optin) return wx_fail(WX_EUNSUPPORTED, "wpd 2-D tile does not fit shared memory");
         const long blocks = (hr / tr) * (hc / tc) * (1L << (2 * d)) * N;
         if (blocks >= (1L << 31)) return wx_fail(WX_EUNSUPPORTED, "wpd 2-D: too many tiles for one launch");
