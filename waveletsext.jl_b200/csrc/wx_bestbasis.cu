@@ -13,6 +13,7 @@
 #include "wx_steps.cuh"
 #include <vector>
 #include <cmath>
+#include <type_traits>
 
 namespace {
 
@@ -51,6 +52,63 @@ __global__ void __launch_bounds__(kT) moments_part_k(double *part, const T *X, c
     if (MODE == 1) { o[2 * szK] = mn + c; o[3 * szK] = mx + c; }
 }
 
+// vectorised variant: a thread owns V = 16/sizeof(T) consecutive positions (128-bit loads), U signals in flight per thread.
+// Per position the batch slice is accumulated in four interleaved partial sums (signal index mod 4), like the scalar kernel.
+template <typename T, int MODE>
+__global__ void __launch_bounds__(kT) moments_part_vec_k(double *part, const T *X, const double *shift, long szK, long N, long kchunk)
+{
+    constexpr int V = 16 / (int)sizeof(T), U = 8;
+    using VT = typename std::conditional<sizeof(T) == 8, double2, float4>::type;
+    const long e = ((long)blockIdx.x * kT + threadIdx.x) * V;
+    if (e >= szK) return;
+    const long k0 = (long)blockIdx.y * kchunk;
+    long k1 = k0 + kchunk; if (k1 > N) k1 = N;
+    double c[V], s[4][V], q[4][V], mn[V], mx[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        c[v] = (MODE == 1) ? shift[e + v] : 0.0;
+        mn[v] = INFINITY; mx[v] = -INFINITY;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) { s[a][v] = 0; q[a][v] = 0; }
+    }
+    const T *p = X + e;
+    long k = k0;
+    for (; k + U <= k1; k += U) {
+        VT r[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) r[u] = __ldcs(reinterpret_cast<const VT *>(p + (k + u) * szK));
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const T *rv = reinterpret_cast<const T *>(&r[u]);
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                const double a = (double)rv[v] - c[v];
+                s[u & 3][v] += a;
+                q[u & 3][v] = fma(a, a, q[u & 3][v]);
+                if (MODE == 1) { mn[v] = fmin(mn[v], a); mx[v] = fmax(mx[v], a); }
+            }
+        }
+    }
+    for (; k < k1; ++k) {
+        const VT r = __ldcs(reinterpret_cast<const VT *>(p + k * szK));
+        const T *rv = reinterpret_cast<const T *>(&r);
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            const double a = (double)rv[v] - c[v];
+            s[0][v] += a; q[0][v] = fma(a, a, q[0][v]);
+            if (MODE == 1) { mn[v] = fmin(mn[v], a); mx[v] = fmax(mx[v], a); }
+        }
+    }
+    const long ks = blockIdx.y, nq = (MODE == 1) ? 4 : 2;
+    double *o = part + (ks * nq) * szK + e;
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        o[v] = (s[0][v] + s[1][v]) + (s[2][v] + s[3][v]);
+        o[szK + v] = (q[0][v] + q[1][v]) + (q[2][v] + q[3][v]);
+        if (MODE == 1) { o[2 * szK + v] = mn[v] + c[v]; o[3 * szK + v] = mx[v] + c[v]; }
+    }
+}
+
 // stage 2: combine the ksplit partials in index order
 template <int MODE>
 __global__ void __launch_bounds__(kT) moments_final_k(double *o0, double *o1, double *o2, double *o3, const double *part, long szK, int ksplit)
@@ -86,12 +144,19 @@ int moments(double *o0, double *o1, double *o2, double *o3, const T *X, const do
     WX_REQUIRE(szK >= 1 && N >= 0, "bad sizes");
     WX_REQUIRE(o0 && o1 && (N == 0 || X), "null pointer");
     WxDev dv; int rc = wx_devinfo(dv); if (rc) return rc;
-    const int ksplit = N > 0 ? pick_ksplit(szK, N, dv.sms) : 1;
+    const bool vec = szK % (16 / (long)sizeof(T)) == 0 && (((uintptr_t)X) & 15) == 0;
+    const int ksplit = N > 0 ? pick_ksplit(vec ? szK / (16 / (long)sizeof(T)) : szK, N, dv.sms) : 1;
     const long kchunk = N > 0 ? (N + ksplit - 1) / ksplit : 1;
     const long nq = (MODE == 1) ? 4 : 2;
     double *part; rc = wx_scratch(&part, (size_t)ksplit * nq * szK, s); if (rc) return rc;
-    dim3 grid((unsigned)((szK + kT - 1) / kT), (unsigned)ksplit);
-    moments_part_k<T, MODE><<<grid, kT, 0, s>>>(part, X, shift, szK, N, kchunk);
+    constexpr long V = 16 / (long)sizeof(T);
+    if (szK % V == 0 && (((uintptr_t)X) & 15) == 0) {
+        dim3 grid((unsigned)((szK / V + kT - 1) / kT), (unsigned)ksplit);
+        moments_part_vec_k<T, MODE><<<grid, kT, 0, s>>>(part, X, shift, szK, N, kchunk);
+    } else {
+        dim3 grid((unsigned)((szK + kT - 1) / kT), (unsigned)ksplit);
+        moments_part_k<T, MODE><<<grid, kT, 0, s>>>(part, X, shift, szK, N, kchunk);
+    }
     WX_LAUNCHED();
     moments_final_k<MODE><<<gridf(szK), kT, 0, s>>>(o0, o1, o2, o3, part, szK, ksplit);
     WX_LAUNCHED();
@@ -227,6 +292,46 @@ __global__ void __launch_bounds__(kT) lsdb_hist_k(double *counts, const double *
     }
 }
 
+// shared-memory variant: a thread owns one position and keeps its npts bin counters in shared memory (column tid of a
+// (npts, kT) table: conflict free, no atomics needed), U signals in flight; the per-CTA counts are then added to the global
+// table with one atomicAdd per non-empty bin (integer-valued doubles: exact and order independent).
+template <typename T>
+__global__ void __launch_bounds__(kT) lsdb_hist_smem_k(double *counts, const double *stats, const T *X, long szK, long N, long kchunk, double Ntot,
+                                                        int npts)
+{
+    extern __shared__ unsigned int wx_cnt[];
+    constexpr int U = 8;
+    const int tid = threadIdx.x;
+    const long e = (long)blockIdx.x * kT + tid;
+    for (int i = 0; i < npts; ++i) wx_cnt[i * kT + tid] = 0;
+    if (e >= szK) return;                                  // a thread only ever touches its own column: no barrier needed
+    double a, delta;
+    lsdb_axis(stats, szK, e, Ntot, npts, a, delta);
+    const double dinv = 1.0 / delta;
+    const long k0 = (long)blockIdx.y * kchunk;
+    long k1 = k0 + kchunk; if (k1 > N) k1 = N;
+    const T *p = X + e;
+    long k = k0;
+    for (; k + U <= k1; k += U) {
+        T r[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) r[u] = __ldcs(p + (k + u) * szK);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long ki = (long)floor(((double)r[u] - a) * dinv + 1.5);      // AverageShiftedHistograms bin rule (1-based)
+            if (ki >= 1 && ki <= npts) wx_cnt[(int)(ki - 1) * kT + tid] += 1u;
+        }
+    }
+    for (; k < k1; ++k) {
+        const long ki = (long)floor(((double)p[k * szK] - a) * dinv + 1.5);
+        if (ki >= 1 && ki <= npts) wx_cnt[(int)(ki - 1) * kT + tid] += 1u;
+    }
+    for (int i = 0; i < npts; ++i) {
+        const unsigned c = wx_cnt[i * kT + tid];
+        if (c) atomicAdd(&counts[(long)i * szK + e], (double)c);
+    }
+}
+
 // ASH density on the grid from the (all-reduced) counts, triangular kernel, normalised by 1/(sum(y)*delta)
 __global__ void __launch_bounds__(kT) lsdb_density_k(double *dens, const double *counts, const double *stats, long szK, double Ntot, long npts, long mb)
 {
@@ -277,6 +382,49 @@ __global__ void __launch_bounds__(kT) lsdb_logpdf_part_k(double *part, const dou
     part[(long)blockIdx.y * szK + e] = acc;
 }
 
+// shared-memory variant: the density columns of the CTA's kL positions are staged in shared memory ((npts, kL) table)
+constexpr int kL = 128;
+template <typename T>
+__global__ void __launch_bounds__(kL) lsdb_logpdf_smem_k(double *part, const double *dens, const double *stats, const T *X, long szK, long N,
+                                                          long kchunk, double Ntot, int npts)
+{
+    extern __shared__ double wx_dens[];
+    constexpr int U = 4;
+    const int tid = threadIdx.x;
+    const long e = (long)blockIdx.x * kL + tid;
+    if (e >= szK) return;                                  // own column only: no barrier needed
+    for (int i = 0; i < npts; ++i) wx_dens[i * kL + tid] = dens[(long)i * szK + e];
+    double a, delta;
+    lsdb_axis(stats, szK, e, Ntot, npts, a, delta);
+    const double dinv = 1.0 / delta;
+    const long k0 = (long)blockIdx.y * kchunk;
+    long k1 = k0 + kchunk; if (k1 > N) k1 = N;
+    const T *p = X + e;
+    double acc = 0.0;
+    auto term = [&](double xv) {
+        long i = (long)floor((xv - a) * dinv) + 1;                   // searchsortedlast(rng, x), 1-based
+        while (i >= 1 && i <= npts && a + (double)(i - 1) * delta > xv) --i;
+        while (i + 1 <= npts && a + (double)i * delta <= xv) ++i;
+        double pdf = 0.0;
+        if (i >= 1 && i < npts) {
+            const double g0 = a + (double)(i - 1) * delta, g1 = a + (double)i * delta;
+            const double y0 = wx_dens[(int)(i - 1) * kL + tid], y1 = wx_dens[(int)i * kL + tid];
+            pdf = y0 + (y1 - y0) * (xv - g0) / (g1 - g0);
+        }
+        return log(pdf);
+    };
+    long k = k0;
+    for (; k + U <= k1; k += U) {
+        T r[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) r[u] = __ldcs(p + (k + u) * szK);
+#pragma unroll
+        for (int u = 0; u < U; ++u) acc += term((double)r[u]);
+    }
+    for (; k < k1; ++k) acc += term((double)p[k * szK]);
+    part[(long)blockIdx.y * szK + e] = acc;
+}
+
 __global__ void __launch_bounds__(kT) sum_parts_k(double *out, const double *part, long szK, int ksplit)
 {
     const long e = (long)blockIdx.x * kT + threadIdx.x;
@@ -298,7 +446,14 @@ int lsdb_pass2(double *counts, const double *stats, const T *X, long szK, long N
     const int ksplit = pick_ksplit(szK, Nlocal, dv.sms);
     const long kchunk = (Nlocal + ksplit - 1) / ksplit;
     dim3 grid((unsigned)((szK + kT - 1) / kT), (unsigned)ksplit);
-    lsdb_hist_k<T><<<grid, kT, 0, s>>>(counts, stats, X, szK, Nlocal, kchunk, (double)Ntotal, g.npts);
+    const size_t smem = (size_t)g.npts * kT * sizeof(unsigned int);
+    if (smem <= dv.smem_optin && kchunk < (1L << 32)) {
+        auto kern = lsdb_hist_smem_k<T>;
+        WX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, kT, smem, s>>>(counts, stats, X, szK, Nlocal, kchunk, (double)Ntotal, (int)g.npts);
+    } else {
+        lsdb_hist_k<T><<<grid, kT, 0, s>>>(counts, stats, X, szK, Nlocal, kchunk, (double)Ntotal, g.npts);
+    }
     WX_LAUNCHED();
     return WX_OK;
 }
@@ -318,8 +473,16 @@ int lsdb_pass3(double *logsum, const double *counts, const double *stats, const 
     rc = wx_scratch(&part, (size_t)ksplit * szK, s); if (rc) return rc;
     lsdb_density_k<<<gridf(szK), kT, 0, s>>>(dens, counts, stats, szK, (double)Ntotal, g.npts, g.mbins);
     WX_LAUNCHED();
-    dim3 grid((unsigned)((szK + kT - 1) / kT), (unsigned)ksplit);
-    lsdb_logpdf_part_k<T><<<grid, kT, 0, s>>>(part, dens, stats, X, szK, Nlocal, kchunk, (double)Ntotal, g.npts);
+    const size_t smem = (size_t)g.npts * kL * sizeof(double);
+    if (smem <= dv.smem_optin) {
+        dim3 grid((unsigned)((szK + kL - 1) / kL), (unsigned)ksplit);
+        auto kern = lsdb_logpdf_smem_k<T>;
+        WX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, kL, smem, s>>>(part, dens, stats, X, szK, Nlocal, kchunk, (double)Ntotal, (int)g.npts);
+    } else {
+        dim3 grid((unsigned)((szK + kT - 1) / kT), (unsigned)ksplit);
+        lsdb_logpdf_part_k<T><<<grid, kT, 0, s>>>(part, dens, stats, X, szK, Nlocal, kchunk, (double)Ntotal, g.npts);
+    }
     WX_LAUNCHED();
     sum_parts_k<<<gridf(szK), kT, 0, s>>>(logsum, part, szK, ksplit);
     WX_LAUNCHED();

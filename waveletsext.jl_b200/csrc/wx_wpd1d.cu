@@ -80,7 +80,8 @@ __global__ void __launch_bounds__(256) wpd1d_tma_k(const __grid_constant__ CUten
     constexpr int RE = 128 / (int)sizeof(T);          // elements per 128-byte row
     extern __shared__ unsigned char wx_smem_raw[];
     __shared__ __align__(8) unsigned long long bar;
-    T *buf0 = reinterpret_cast<T *>((reinterpret_cast<uintptr_t>(wx_smem_raw) + 1023) & ~(uintptr_t)1023);
+    // 1024-byte alignment for SWIZZLE_128B, as an offset from the array so that the accesses stay LDS/STS (not generic LD/ST)
+    T *buf0 = reinterpret_cast<T *>(wx_smem_raw + ((1024u - (wx_smem_u32(wx_smem_raw) & 1023u)) & 1023u));
     T *buf1 = buf0 + bufelems;
     const int n0 = (int)(n >> d0);
     const int tid = threadIdx.x, nthreads = blockDim.x;

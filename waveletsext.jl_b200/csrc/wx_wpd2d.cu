@@ -111,42 +111,49 @@ __global__ void __launch_bounds__(kT2) wpd2d_tile_k(T *__restrict__ y, const T *
     const int tid = threadIdx.x;
     const int mp = m >> d, np = n >> d, hr = mp / 2, hc = np / 2;
     const int tiles_r = hr / tr, tiles_c = hc / tc, nodes = 1 << d;
-    // block -> (tile row, node row, tile col, node col, image); neighbouring CTAs walk down the rows of the image
-    long bid = blockIdx.x;
-    const int ti = (int)(bid % tiles_r); bid /= tiles_r;
-    const int jr = (int)(bid % nodes); bid /= nodes;
-    const int tk = (int)(bid % tiles_c); bid /= tiles_c;
-    const int jc = (int)(bid % nodes); bid /= nodes;
-    const long k = bid;
+    // grid.x = image * (row tiles of all nodes), grid.y = column tiles of all nodes: neighbouring CTAs walk down the rows
+    const unsigned rowtiles = (unsigned)(tiles_r * nodes);
+    const unsigned k = blockIdx.x / rowtiles, rt = blockIdx.x - k * rowtiles;
+    const int jr = (int)(rt / (unsigned)tiles_r), ti = (int)(rt - (unsigned)jr * tiles_r);
+    const int jc = (int)(blockIdx.y / (unsigned)tiles_c), tk = (int)(blockIdx.y - (unsigned)jc * tiles_c);
     const long img = (long)m * n;
-    T *yk = y + k * img * (L + 1);
+    T *yk = y + (long)k * img * (L + 1);
     const bool from_x = (d == 0 && x != nullptr);
     const int nr0 = jr * mp, nc0 = jc * np;              // node origin in the image
     const int i0 = ti * tr, k0 = tk * tc;                // tile origin in child coordinates
-    const T *par = (from_x ? (x + k * img) : (yk + (long)d * img)) + (long)nc0 * m + nr0;
+    const T *par = (from_x ? (x + (long)k * img) : (yk + (long)d * img)) + (long)nc0 * m + nr0;
 
-    // ---- parent patch (periodic inside the node), two rows per asynchronous copy ----
+    // ---- parent patch (periodic inside the node), two rows per asynchronous copy; a warp per column ----
+    const int lane = tid & 31, warp = tid >> 5;
     {
         const int PR2 = PR / 2;
-        for (Walk2 w(tid, PR2); w.hi < PC; w.next()) {
-            const int b = w.hi, a = 2 * w.lo;
-            int rr = 2 * i0 + a; while (rr >= mp) rr -= mp;
+        int rr = 2 * i0 + 2 * lane; while (rr >= mp) rr -= mp;
+        for (int b = warp; b < PC; b += kT2 / 32) {
             int cc = 2 * k0 + b; while (cc >= np) cc -= np;
-            cp_async_pair<T>(P + b * LDP + a, par + cc * m + rr);
+            if (lane < PR2) cp_async_pair<T>(P + b * LDP + 2 * lane, par + cc * m + rr);
+        }
+        const int rem = PR2 - 32;                         // pairs 32.. of every column (halo rows of a 32-row tile)
+        if (rem > 0) {
+            for (int idx = tid; idx < rem * PC; idx += kT2) {
+                const int b = idx / rem, a = 2 * (32 + idx - b * rem);
+                int r2 = 2 * i0 + a; while (r2 >= mp) r2 -= mp;
+                int cc = 2 * k0 + b; while (cc >= np) cc -= np;
+                cp_async_pair<T>(P + b * LDP + a, par + cc * m + r2);
+            }
         }
         cp_async_wait_all();
     }
     __syncthreads();
-    if (from_x) {                                         // y[:,:,1] = x   DWT.jl:176 : the core of the patch
-        T *y0 = yk + (long)(nc0 + 2 * k0) * m + nr0 + 2 * i0;
-        for (Walk2 w(tid, tr); w.hi < 2 * tc; w.next())
-            *reinterpret_cast<P2 *>(y0 + w.hi * m + 2 * w.lo) = *reinterpret_cast<const P2 *>(P + w.hi * LDP + 2 * w.lo);
+    if (from_x && lane < tr) {                            // y[:,:,1] = x   DWT.jl:176 : the core of the patch (tr <= 32 pairs per column)
+        T *y0 = yk + (long)(nc0 + 2 * k0) * m + nr0 + 2 * i0 + 2 * lane;
+        for (int b = warp; b < 2 * tc; b += kT2 / 32)
+            *reinterpret_cast<P2 *>(y0 + b * m) = *reinterpret_cast<const P2 *>(P + b * LDP + 2 * lane);
     }
     // ---- column pass: every column of the patch; a thread owns pairs il and il + ceil(tr/2) (lanes walk consecutive il:
     //      conflict-free 16-byte loads) ----
     if (tr <= 32 && (32 % tr) == 0) {
         // lanes walk il (conflict-free 16-byte loads), 32/tr columns per warp, warps stride over the columns, two columns in flight
-        const int lane = tid & 31, warp = tid >> 5, cpw = 32 / tr, il = lane % tr, bstep = (kT2 / 32) * cpw;
+        const int cpw = 32 / tr, il = lane % tr, bstep = (kT2 / 32) * cpw;
         for (int b = warp * cpw + lane / tr; b < PC; b += 2 * bstep) {
             const bool two = b + bstep < PC;
             const T *s0 = P + b * LDP + 2 * il;
@@ -205,14 +212,16 @@ __global__ void __launch_bounds__(kT2) wpd2d_tile_k(T *__restrict__ y, const T *
 #pragma unroll
             for (int j = 0; j < 2 * KROW + F - 2; ++j) win[j] = src[j * R2];
             int ch = k0 + kl0 + S; while (ch >= hc) ch -= hc;
-            T *olo = o + (k0 + kl0) * m;
+            T *olo = o + (k0 + kl0) * m, *ohi = o + (hc + ch) * m;
+            const long back = (long)hc * m;
 #pragma unroll
             for (int p = 0; p < KROW; ++p) {
                 T lo, hi;
                 dwt_dots<T, F>(&win[2 * p], tp, lo, hi);
-                olo[p * m] = lo;                          // w1 / w3
-                o[(hc + ch) * m] = hi;                    // w2 / w4
-                ++ch; if (ch >= hc) ch -= hc;
+                *olo = lo;                                // w1 / w3
+                *ohi = hi;                                // w2 / w4
+                olo += m; ohi += m;
+                if (++ch >= hc) { ch -= hc; ohi -= back; }
             }
         }
     } else {
@@ -286,37 +295,41 @@ __global__ void __launch_bounds__(kT2) wpd2d_block_k(T *__restrict__ y, const T 
     T *A = reinterpret_cast<T *>(wx_2d_smem);            // (BR, BC) column-major: the block at the current level
     T *Tm = A + BR * BC;                                  // after the column pass
     const int tid = threadIdx.x;
-    const int nodes = 1 << db;
-    long bid = blockIdx.x;
-    const int jr = (int)(bid % nodes); bid /= nodes;
-    const int jc = (int)(bid % nodes); bid /= nodes;
-    const long k = bid;
+    // grid.x = image * nodes + node row, grid.y = node column
+    const unsigned k = blockIdx.x >> db;
+    const int jr = (int)(blockIdx.x & ((1u << db) - 1)), jc = (int)blockIdx.y;
     const long img = (long)m * n;
-    T *yk = y + k * img * (L + 1);
+    T *yk = y + (long)k * img * (L + 1);
     const bool from_x = (db == 0 && x != nullptr);
     const long org = (long)(jc * BC) * m + jr * BR;       // block origin in the image
-    const T *par = (from_x ? (x + k * img) : (yk + (long)db * img)) + org;
+    const T *par = (from_x ? (x + (long)k * img) : (yk + (long)db * img)) + org;
     const int BR2 = BR / 2;
+    const int lane = tid & 31, warp = tid >> 5;
+    // global <-> shared copies of the block: lanes walk the row pairs of a column when a column is at most one warp wide
+    const bool colwarp = BR2 <= 32 && (32 % BR2) == 0;
+    const int cpw = colwarp ? 32 / BR2 : 1, ca = 2 * (lane % BR2), cb0 = warp * cpw + lane / BR2, cbs = (kT2 / 32) * cpw;
 
-    for (Walk2 w(tid, BR2); w.hi < BC; w.next()) cp_async_pair<T>(A + w.hi * BR + 2 * w.lo, par + w.hi * m + 2 * w.lo);
+    if (colwarp) { for (int b = cb0; b < BC; b += cbs) cp_async_pair<T>(A + b * BR + ca, par + b * m + ca); }
+    else { for (Walk2 w(tid, BR2); w.hi < BC; w.next()) cp_async_pair<T>(A + w.hi * BR + 2 * w.lo, par + w.hi * m + 2 * w.lo); }
     cp_async_wait_all();
     __syncthreads();
     if (from_x) {                                         // y[:,:,1] = x   DWT.jl:176
-        for (Walk2 w(tid, BR2); w.hi < BC; w.next())
-            *reinterpret_cast<P2 *>(yk + org + w.hi * m + 2 * w.lo) = *reinterpret_cast<const P2 *>(A + w.hi * BR + 2 * w.lo);
+        T *y0 = yk + org;
+        if (colwarp) { for (int b = cb0; b < BC; b += cbs) *reinterpret_cast<P2 *>(y0 + b * m + ca) = *reinterpret_cast<const P2 *>(A + b * BR + ca); }
+        else { for (Walk2 w(tid, BR2); w.hi < BC; w.next()) *reinterpret_cast<P2 *>(y0 + w.hi * m + 2 * w.lo) = *reinterpret_cast<const P2 *>(A + w.hi * BR + 2 * w.lo); }
     }
     for (int l = db; l < dend; ++l) {
         const int mpl = m >> l, npl = n >> l, hr = mpl / 2, hc = npl / 2;
         // ---- column pass A -> Tm, per node: scaling rows on top, detail rows below (shift resolved here) ----
         if (BR2 <= 32 && (32 % BR2) == 0 && mpl >= F) {
             // lanes walk the pairs of one column (conflict-free 16-byte loads), warps stride over the columns, two in flight
-            const int lane = tid & 31, warp = tid >> 5, cpw = 32 / BR2, ig = lane % BR2, bstep = (kT2 / 32) * cpw;
+            const int ig = lane % BR2, bstep = cbs;
             const int jn = ig / hr, il = ig - jn * hr, r0 = jn * mpl;
             int ih = il + S; if (ih >= hr) ih %= hr;
             int e[F / 2];
 #pragma unroll
             for (int q = 0; q < F / 2; ++q) { e[q] = 2 * il + 2 * q; if (e[q] >= mpl) e[q] -= mpl; }
-            for (int b = warp * cpw + lane / BR2; b < BC; b += 2 * bstep) {
+            for (int b = cb0; b < BC; b += 2 * bstep) {
                 const bool two = b + bstep < BC;
                 const T *s0 = A + b * BR + r0;
                 const T *s1 = two ? s0 + bstep * BR : s0;
@@ -423,10 +436,8 @@ __global__ void __launch_bounds__(kT2) wpd2d_block_k(T *__restrict__ y, const T 
         __syncthreads();
         // ---- level l+1 slice ----
         T *ynext = yk + (long)(l + 1) * img + org;
-        for (Walk2 w(tid, BR2); w.hi < BC; w.next()) {
-            const int b = w.hi, a = 2 * w.lo;
-            *reinterpret_cast<P2 *>(ynext + b * m + a) = *reinterpret_cast<const P2 *>(A + b * BR + a);
-        }
+        if (colwarp) { for (int b = cb0; b < BC; b += cbs) *reinterpret_cast<P2 *>(ynext + b * m + ca) = *reinterpret_cast<const P2 *>(A + b * BR + ca); }
+        else { for (Walk2 w(tid, BR2); w.hi < BC; w.next()) *reinterpret_cast<P2 *>(ynext + w.hi * m + 2 * w.lo) = *reinterpret_cast<const P2 *>(A + w.hi * BR + 2 * w.lo); }
         // the next column pass only reads A (complete after the barrier above) and writes Tm (free): no barrier needed here
     }
 }
@@ -447,27 +458,27 @@ int wpd2d_run(T *y, const T *x, long m, long n, int L, long N, const Taps<T> &t,
     int db = 0;
     while (db < L && (size_t)2 * (m >> db) * (n >> db) * sizeof(T) > budget) ++db;
     static const char *env = getenv("WX_B200_WPD2D_TILE");      // measurement knob: tile edge of the halo kernel
-    const int cap = env ? atoi(env) : 32;
+    const int cap = (env && atoi(env) >= 1 && atoi(env) <= 32) ? atoi(env) : 32;     // the kernel maps one lane per row pair: tr <= 32
     for (int d = 0; d < db; ++d) {
         const long hr = (m >> d) / 2, hc = (n >> d) / 2;
         const int tr = largest_divisor_le(hr, cap), tc = largest_divisor_le(hc, cap);
         const int PR = 2 * tr + F - 2, PC = 2 * tc + F - 2;
         const size_t smem = ((size_t)(PR + 2 * (tr & 1)) * PC + (size_t)2 * tr * (PC + 2 * (tc & 1))) * sizeof(T);
         if (smem > dv.smem_optin) return wx_fail(WX_EUNSUPPORTED, "wpd 2-D tile does not fit shared memory");
-        const long blocks = (hr / tr) * (hc / tc) * (1L << (2 * d)) * N;
-        if (blocks >= (1L << 31)) return wx_fail(WX_EUNSUPPORTED, "wpd 2-D: too many tiles for one launch");
+        const long gx = (hr / tr) * (1L << d) * N, gy = (hc / tc) * (1L << d);
+        if (gx >= (1L << 31) || gy > 65535) return wx_fail(WX_EUNSUPPORTED, "wpd 2-D: too many tiles for one launch");
         auto kern = wpd2d_tile_k<T, F>;
         WX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<(unsigned)blocks, kT2, smem, s>>>(y, d == 0 ? x : nullptr, (int)m, (int)n, L, d, tr, tc, t);
+        kern<<<dim3((unsigned)gx, (unsigned)gy), kT2, smem, s>>>(y, d == 0 ? x : nullptr, (int)m, (int)n, L, d, tr, tc, t);
         WX_LAUNCHED();
     }
     if (db < L) {
         const size_t smem = (size_t)2 * (m >> db) * (n >> db) * sizeof(T);
-        const long blocks = (1L << (2 * db)) * N;
-        if (blocks >= (1L << 31)) return wx_fail(WX_EUNSUPPORTED, "wpd 2-D: too many blocks for one launch");
+        const long gx = (1L << db) * N, gy = 1L << db;
+        if (gx >= (1L << 31) || gy > 65535) return wx_fail(WX_EUNSUPPORTED, "wpd 2-D: too many blocks for one launch");
         auto kern = wpd2d_block_k<T, F>;
         WX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<(unsigned)blocks, kT2, smem, s>>>(y, db == 0 ? x : nullptr, (int)m, (int)n, L, db, L, t);
+        kern<<<dim3((unsigned)gx, (unsigned)gy), kT2, smem, s>>>(y, db == 0 ? x : nullptr, (int)m, (int)n, L, db, L, t);
         WX_LAUNCHED();
     }
     return WX_OK;
