@@ -382,47 +382,58 @@ __global__ void __launch_bounds__(kT) lsdb_logpdf_part_k(double *part, const dou
     part[(long)blockIdx.y * szK + e] = acc;
 }
 
-// shared-memory variant: the density columns of the CTA's kL positions are staged in shared memory ((npts, kL) table)
-constexpr int kL = 128;
+// shared-memory variant: the density columns of the CTA's kL positions are staged in shared memory ((npts, kL) table);
+// kH threads share a position (each takes a slice of the CTA's signals).  The interpolation weight uses 1/delta instead of
+// 1/(g1-g0) and the logarithm is taken of the product of U consecutive pdf values (log of a product = sum of logs;
+// a zero pdf still gives -Inf, and U pdf values of order 1e-3..1e3 cannot over/underflow a double).
+constexpr int kL = 128, kH = 2;
 template <typename T>
-__global__ void __launch_bounds__(kL) lsdb_logpdf_smem_k(double *part, const double *dens, const double *stats, const T *X, long szK, long N,
-                                                          long kchunk, double Ntot, int npts)
+__global__ void __launch_bounds__(kL * kH) lsdb_logpdf_smem_k(double *part, const double *dens, const double *stats, const T *X, long szK, long N,
+                                                               long kchunk, double Ntot, int npts)
 {
     extern __shared__ double wx_dens[];
     constexpr int U = 4;
-    const int tid = threadIdx.x;
-    const long e = (long)blockIdx.x * kL + tid;
-    if (e >= szK) return;                                  // own column only: no barrier needed
-    for (int i = 0; i < npts; ++i) wx_dens[i * kL + tid] = dens[(long)i * szK + e];
+    const int pos = threadIdx.x % kL, kh = threadIdx.x / kL;
+    const long e = (long)blockIdx.x * kL + pos;
+    const bool live = e < szK;
+    if (live) for (int i = kh; i < npts; i += kH) wx_dens[i * kL + pos] = dens[(long)i * szK + e];
+    __syncthreads();
+    if (!live) return;
     double a, delta;
     lsdb_axis(stats, szK, e, Ntot, npts, a, delta);
     const double dinv = 1.0 / delta;
-    const long k0 = (long)blockIdx.y * kchunk;
-    long k1 = k0 + kchunk; if (k1 > N) k1 = N;
+    const long c0 = (long)blockIdx.y * kchunk;
+    long c1 = c0 + kchunk; if (c1 > N) c1 = N;
+    const long sub = (c1 - c0 + kH - 1) / kH;
+    const long k0 = c0 + kh * sub;
+    long k1 = k0 + sub; if (k1 > c1) k1 = c1;
     const T *p = X + e;
-    double acc = 0.0;
-    auto term = [&](double xv) {
-        long i = (long)floor((xv - a) * dinv) + 1;                   // searchsortedlast(rng, x), 1-based
-        while (i >= 1 && i <= npts && a + (double)(i - 1) * delta > xv) --i;
-        while (i + 1 <= npts && a + (double)i * delta <= xv) ++i;
+    auto pdf_at = [&](double xv) {
+        const double t = (xv - a) * dinv;
+        long i = (long)floor(t) + 1;                                   // searchsortedlast(rng, x), 1-based
+        double g0 = fma((double)(i - 1), delta, a);
+        while (i >= 1 && i <= npts && g0 > xv) { --i; g0 = fma((double)(i - 1), delta, a); }
+        while (i + 1 <= npts && fma((double)i, delta, a) <= xv) { ++i; g0 = fma((double)(i - 1), delta, a); }
         double pdf = 0.0;
         if (i >= 1 && i < npts) {
-            const double g0 = a + (double)(i - 1) * delta, g1 = a + (double)i * delta;
-            const double y0 = wx_dens[(int)(i - 1) * kL + tid], y1 = wx_dens[(int)i * kL + tid];
-            pdf = y0 + (y1 - y0) * (xv - g0) / (g1 - g0);
+            const double y0 = wx_dens[(int)(i - 1) * kL + pos], y1 = wx_dens[(int)i * kL + pos];
+            pdf = fma((y1 - y0) * dinv, xv - g0, y0);
         }
-        return log(pdf);
+        return pdf;
     };
+    double acc = 0.0;
     long k = k0;
     for (; k + U <= k1; k += U) {
         T r[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) r[u] = __ldcs(p + (k + u) * szK);
+        double prod = 1.0;
 #pragma unroll
-        for (int u = 0; u < U; ++u) acc += term((double)r[u]);
+        for (int u = 0; u < U; ++u) prod *= pdf_at((double)r[u]);
+        acc += log(prod);
     }
-    for (; k < k1; ++k) acc += term((double)p[k * szK]);
-    part[(long)blockIdx.y * szK + e] = acc;
+    for (; k < k1; ++k) acc += log(pdf_at((double)p[k * szK]));
+    part[((long)blockIdx.y * kH + kh) * szK + e] = acc;
 }
 
 __global__ void __launch_bounds__(kT) sum_parts_k(double *out, const double *part, long szK, int ksplit)
@@ -470,21 +481,23 @@ int lsdb_pass3(double *logsum, const double *counts, const double *stats, const 
     const long kchunk = (Nlocal + ksplit - 1) / ksplit;
     double *dens, *part;
     rc = wx_scratch(&dens, (size_t)g.npts * szK, s); if (rc) return rc;
-    rc = wx_scratch(&part, (size_t)ksplit * szK, s); if (rc) return rc;
+    rc = wx_scratch(&part, (size_t)ksplit * kH * szK, s); if (rc) return rc;
     lsdb_density_k<<<gridf(szK), kT, 0, s>>>(dens, counts, stats, szK, (double)Ntotal, g.npts, g.mbins);
     WX_LAUNCHED();
     const size_t smem = (size_t)g.npts * kL * sizeof(double);
+    int nparts = ksplit;
     if (smem <= dv.smem_optin) {
         dim3 grid((unsigned)((szK + kL - 1) / kL), (unsigned)ksplit);
         auto kern = lsdb_logpdf_smem_k<T>;
         WX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, kL, smem, s>>>(part, dens, stats, X, szK, Nlocal, kchunk, (double)Ntotal, (int)g.npts);
+        kern<<<grid, kL * kH, smem, s>>>(part, dens, stats, X, szK, Nlocal, kchunk, (double)Ntotal, (int)g.npts);
+        nparts = ksplit * kH;
     } else {
         dim3 grid((unsigned)((szK + kT - 1) / kT), (unsigned)ksplit);
         lsdb_logpdf_part_k<T><<<grid, kT, 0, s>>>(part, dens, stats, X, szK, Nlocal, kchunk, (double)Ntotal, g.npts);
     }
     WX_LAUNCHED();
-    sum_parts_k<<<gridf(szK), kT, 0, s>>>(logsum, part, szK, ksplit);
+    sum_parts_k<<<gridf(szK), kT, 0, s>>>(logsum, part, szK, nparts);
     WX_LAUNCHED();
     int rc2 = wx_scratch_free(dens, s), rc3 = wx_scratch_free(part, s);
     return rc2 ? rc2 : rc3;

@@ -209,6 +209,7 @@ int rwpd_plan(T *xw, const T *x, long n, int L, int wpt, long N, const Taps<T> &
     const long ehalf = (long)((dv.smem_optin / 2 - 1024) / buf) - 2;
     if (efull < 1) return WX_OK;
     long elast = (ehalf >= 3 || ehalf >= dend) ? ehalf : efull;
+    if (elast > 6) elast = 6;                          // measured: deeper stacks lose more to occupancy than they save in re-reads
     static const char *env = getenv("WX_B200_RWPD_ELAST");        // measurement knob
     if (env && atol(env) >= 1 && atol(env) <= efull) elast = atol(env);
     if (elast > dend) elast = dend;
