@@ -145,13 +145,17 @@ int wx_jbb_moments_f32(double *sum, double *sumsq, const float *X, long szK, lon
 int wx_jbb_costs(double *costs_host, const double *sum, const double *sumsq, long Ntotal, long m, long n, int K, int redundant, int cost_kind, double p, int elt, void *stream);
 /* tree_costs(X, ::LSDB)  bestbasis/bestbasis_tree.jl:104-147 + DifferentialEntropyCost bestbasis/bestbasis_costs.jl:135-164,
  * three passes over the local batch with all-reducible per-position state in between:
- *  pass1: count,sum,sumsq-about-shift,min,max per position  -> stats(5, szK) device
+ *  pass1: stats(7, szK) device: row 0 = shift c (INPUT: first signal of the global batch), rows 1/2 = sum(x-c) hi/lo,
+ *         rows 3/4 = sum((x-c)^2) hi/lo (double-double pairs, exact to ~1e-32), row 5 = min, row 6 = max
  *  pass2: ASH bin counts on the grid derived from the reduced stats -> counts(npts, szK) device
- *  pass3: sum_k log pdf(x_k) per position -> logsum(szK) device
- *  costs: per-node costs from the reduced logsum. */
+ *  pass3: sum_k log pdf(x_k) per position -> logsum(2, szK) device (hi/lo)
+ *  costs: per-node costs from the reduced logsum (row hi).
+ * Across ranks: all-gather the hi/lo rows and combine them with wx_dd_sum (fixed order, exact), all-reduce min / max /
+ * counts; the costs are then independent of how the batch is sharded. */
 int wx_lsdb_pass1_f64(double *stats, const double *X, long szK, long Nlocal, void *stream);
 int wx_lsdb_pass1_f32(double *stats, const float *X, long szK, long Nlocal, void *stream);
 int wx_lsdb_grid(long Ntotal, long *nbins, long *mbins, long *npts);
+int wx_dd_sum(double *out, const double *parts, long count, int nparts, void *stream);
 int wx_lsdb_pass2_f64(double *counts, const double *stats, const double *X, long szK, long Nlocal, long Ntotal, void *stream);
 int wx_lsdb_pass2_f32(double *counts, const double *stats, const float *X, long szK, long Nlocal, long Ntotal, void *stream);
 int wx_lsdb_pass3_f64(double *logsum, const double *counts, const double *stats, const double *X, long szK, long Nlocal, long Ntotal, void *stream);

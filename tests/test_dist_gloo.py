@@ -55,6 +55,21 @@ def _worker(rank, world, port, q):
         assert np.array_equal(mn.numpy(), X.min(0)) and np.array_equal(mx.numpy(), X.max(0))
         first = wx.dist.broadcast_from_first(torch.from_numpy(X[lo].copy()))
         assert np.array_equal(first.numpy(), X[0])
+        # LSDB sums travel as double-double pairs, all-gathered and summed in rank order: the rounded total does not depend
+        # on the sharding.  Shard-local pairs here: (plain sum, 0) per half-shard, i.e. deliberately different roundings.
+        flat = Xl.reshape(Xl.shape[0], -1)
+        half = flat.shape[0] // 2
+        local = wx.dist.dd_sum_host(torch.stack([torch.stack([flat[:half].sum(0), torch.zeros(flat.shape[1], dtype=torch.float64)]),
+                                                 torch.stack([flat[half:].sum(0), torch.zeros(flat.shape[1], dtype=torch.float64)])]))
+        parts = wx.dist.allgather_parts(local)
+        assert parts.shape == (2, 2, flat.shape[1])
+        tot = wx.dist.dd_sum_host(parts)
+        import math
+        exact = np.array([math.fsum(X.reshape(N, -1)[:, j]) for j in range(flat.shape[1])])
+        assert np.abs(tot[0].numpy() - exact).max() <= 4e-16 * np.abs(exact).max() + 1e-15
+        g = [torch.empty_like(tot) for _ in range(world)]
+        dist.all_gather(g, tot)
+        assert torch.equal(g[0], g[1])                       # bitwise identical on every rank
         q.put((rank, "ok"))
     except Exception as e:      # pragma: no cover
         import traceback

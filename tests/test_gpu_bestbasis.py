@@ -112,6 +112,68 @@ def test_jbb_sharded_equals_single(wx, cuda):
     assert torch.equal(again, full)
 
 
+def _lsdb_by_shards(wx, cuda, Xw, cuts):
+    """the LSDB protocol across ranks, emulated on one GPU through the C ABI: per-shard pass1 (double-double sums), exact
+    combination in shard order (wx_dd_sum), min / max / counts reductions, per-shard pass2 / pass3"""
+    import ctypes as C
+    N, K, n = Xw.shape
+    szK = K * n
+    f64 = dict(dtype=torch.float64, device=cuda)
+    shards = [Xw[lo:hi].contiguous() for lo, hi in cuts]
+    shift = Xw[0].reshape(-1).clone()
+    stats = []
+    for sh in shards:
+        st = torch.empty((7, szK), **f64)
+        st[0] = shift
+        wx._dev.call("lsdb_pass1", sh, st.data_ptr(), sh.data_ptr(), szK, sh.shape[0], 0)
+        stats.append(st)
+    tot = stats[0].clone()
+    for rows in ((1, 3), (3, 5)):
+        parts = torch.stack([s_[rows[0]:rows[1]] for s_ in stats]).contiguous()
+        out = torch.empty((2, szK), **f64)
+        wx._lib.call("wx_dd_sum", out.data_ptr(), parts.data_ptr(), szK, len(stats), 0)
+        tot[rows[0]:rows[1]] = out
+        assert torch.equal(out, wx.dist.dd_sum_host(parts))          # the host mirror used by the gloo tests agrees bitwise
+    tot[5] = torch.stack([s_[5] for s_ in stats]).min(0).values
+    tot[6] = torch.stack([s_[6] for s_ in stats]).max(0).values
+    npts = C.c_long()
+    wx._lib.call("wx_lsdb_grid", N, None, None, C.byref(npts))
+    counts = torch.zeros((npts.value, szK), **f64)
+    for sh in shards:
+        c = torch.empty_like(counts)
+        wx._dev.call("lsdb_pass2", sh, c.data_ptr(), tot.data_ptr(), sh.data_ptr(), szK, sh.shape[0], N, 0)
+        counts += c
+    lparts = []
+    for sh in shards:
+        l = torch.empty((2, szK), **f64)
+        wx._dev.call("lsdb_pass3", sh, l.data_ptr(), counts.data_ptr(), tot.data_ptr(), sh.data_ptr(), szK, sh.shape[0], N, 0)
+        lparts.append(l)
+    lsum = torch.empty((2, szK), **f64)
+    wx._lib.call("wx_dd_sum", lsum.data_ptr(), torch.stack(lparts).contiguous().data_ptr(), szK, len(lparts), 0)
+    costs = np.empty((1 << K) - 1)
+    wx._lib.call("wx_lsdb_costs", costs.ctypes.data, lsum.data_ptr(), N, 0, n, K, 0, 0)
+    return tot, counts, costs
+
+
+def test_lsdb_does_not_depend_on_the_sharding(wx, cuda):
+    """Every sample is binned on a grid derived from the batch statistics, so the statistics must not move with the
+    sharding: sums (double-double), min, max and hence the ASH bin counts are BITWISE equal however the batch is cut; the
+    costs then agree to rounding of the final log sums and the trees are identical."""
+    wt = wx.wavelet("db4")
+    n, N = 64, 300
+    Xw = wx.wpdall(dev(signals(n, N, 21), cuda), wt)
+    c_api = wx.tree_costs(Xw, wx.LSDB())
+    tot1, counts1, costs1 = _lsdb_by_shards(wx, cuda, Xw, ((0, N),))
+    assert np.array_equal(costs1, c_api)
+    for cuts in (((0, 100), (100, 300)), ((0, 7), (7, 150), (150, 151), (151, 300))):
+        tot, counts, costs = _lsdb_by_shards(wx, cuda, Xw, cuts)
+        for row in (1, 3, 5, 6):
+            assert torch.equal(tot[row], tot1[row]), row
+        assert torch.equal(counts, counts1)
+        assert np.abs(costs - costs1).max() <= 1e-13 * np.abs(costs1).max()
+        assert np.array_equal(wx.bestbasis_treeselection(costs.copy(), n), wx.bestbasis_treeselection(costs1.copy(), n))
+
+
 def test_jbb_negative_variance_is_an_error(wx, cuda):
     """reference: sigma = VarX .^ 0.5 throws DomainError / @assert all(sigma .>= 0) (bestbasis_tree.jl:155-158)"""
     X = torch.full((4, 3, 8), 1e8, dtype=torch.float64, device=cuda)

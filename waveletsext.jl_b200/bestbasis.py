@@ -72,6 +72,18 @@ def _ncosts(m, K, redundant):
     return (4 ** K - 1) // 3 if m > 0 else (1 << K) - 1
 
 
+def _dd_allreduce(pair, group, st):
+    """in-place exact sum over ranks of a (2, count) double-double buffer (rows hi, lo)"""
+    if not (dist.is_dist(group) and dist.world_size(group) > 1):
+        return pair
+    parts = dist.allgather_parts(pair, group)
+    out = torch.empty_like(parts[0])
+    with torch.cuda.device(pair.device):
+        _lib.call("wx_dd_sum", D.ptr(out), D.ptr(parts), pair.shape[1], parts.shape[0], st)
+    pair.copy_(out)
+    return pair
+
+
 def tree_costs(X, method, group=None):
     """``tree_costs(X, method)`` bestbasis/bestbasis_tree.jl:104-207.  X is the LOCAL shard (N_local, K, ...) of the
     packet table; with an initialised process group the costs are those of the concatenated batch."""
@@ -96,21 +108,25 @@ def tree_costs(X, method, group=None):
                       C.c_double(float(method.cost.p)), elt, st)
     elif isinstance(method, LSDB):
         assert Ntot >= 2, "LSDB needs at least two signals"
-        stats = torch.empty((5, szK), dtype=torch.float64, device=X.device)
-        first = X[0].reshape(-1).to(torch.float64) if Nloc > 0 else torch.zeros(szK, dtype=torch.float64, device=X.device)
+        stats = torch.empty((7, szK), dtype=torch.float64, device=X.device)
+        # a COPY: the broadcast below writes into this buffer on every rank but the first (never into the caller's X)
+        first = X[0].reshape(-1).to(torch.float64, copy=True) if Nloc > 0 else torch.zeros(szK, dtype=torch.float64, device=X.device)
         stats[0] = dist.broadcast_from_first(first, group)       # common shift: first signal of the global batch
         D.call("lsdb_pass1", X, D.ptr(stats), D.ptr(X), szK, Nloc, st)
-        dist.allreduce_sum(stats[1:3], group)
-        dist.allreduce_min(stats[3], group)
-        dist.allreduce_max(stats[4], group)
+        # sums travel as double-double pairs and are combined in rank order: the grid every sample is binned on must not
+        # depend on the sharding (a 1-ulp change of a sum would move bin edges)
+        _dd_allreduce(stats[1:3], group, st)
+        _dd_allreduce(stats[3:5], group, st)
+        dist.allreduce_min(stats[5], group)
+        dist.allreduce_max(stats[6], group)
         nb, mb, npts = C.c_long(), C.c_long(), C.c_long()
         _lib.call("wx_lsdb_grid", Ntot, C.byref(nb), C.byref(mb), C.byref(npts))
         counts = torch.empty((npts.value, szK), dtype=torch.float64, device=X.device)
         D.call("lsdb_pass2", X, D.ptr(counts), D.ptr(stats), D.ptr(X), szK, Nloc, Ntot, st)
-        dist.allreduce_sum(counts, group)
-        logsum = torch.empty(szK, dtype=torch.float64, device=X.device)
+        dist.allreduce_sum(counts, group)                        # integer-valued: exact in any order
+        logsum = torch.empty((2, szK), dtype=torch.float64, device=X.device)
         D.call("lsdb_pass3", X, D.ptr(logsum), D.ptr(counts), D.ptr(stats), D.ptr(X), szK, Nloc, Ntot, st)
-        dist.allreduce_sum(logsum, group)
+        _dd_allreduce(logsum, group, st)
         with torch.cuda.device(X.device):
             _lib.call("wx_lsdb_costs", costs.ctypes.data, D.ptr(logsum), Ntot, m, n, K, int(method.redundant), st)
     else:

@@ -126,6 +126,108 @@ __global__ void __launch_bounds__(kT) moments_final_k(double *o0, double *o1, do
     if (MODE == 1) { o2[e] = mn; o3[e] = mx; }
 }
 
+// ---- double-double accumulation (error-free transformations) ------------------------------------------------
+// The LSDB grid (origin, step) of a position is a function of the batch statistics, and every sample is binned on it: a
+// 1-ulp change of a sum moves bin edges.  The sums that feed the grid (and the final sum of log pdf) are therefore kept
+// as unevaluated pairs hi + lo with |lo| <= ulp(hi)/2 (relative error ~1e-32), so their rounded value does not depend on
+// how the batch is cut into slices, CTAs or ranks.
+__device__ __forceinline__ void two_sum(double a, double b, double &s, double &e)
+{
+    s = a + b;
+    const double bb = s - a;
+    e = (a - (s - bb)) + (b - bb);
+}
+__device__ __forceinline__ void dd_acc(double &hi, double &lo, double x)
+{
+    double s, e;
+    two_sum(hi, x, s, e);
+    hi = s; lo += e;
+}
+__device__ __forceinline__ void dd_norm(double &hi, double &lo)
+{
+    const double s = hi + lo;
+    lo = lo - (s - hi); hi = s;
+}
+__device__ __forceinline__ void dd_add(double &hi, double &lo, double bh, double bl)
+{
+    double s, e;
+    two_sum(hi, bh, s, e);
+    e += lo + bl;
+    hi = s; lo = e;
+    dd_norm(hi, lo);
+}
+
+// LSDB pass 1: per position, over a slice of the batch: sum(x-c), sum((x-c)^2) as double-double, min, max.
+// part (ksplit, 6, szK): s_hi, s_lo, q_hi, q_lo, min, max.  V positions per thread (V > 1: 128-bit loads).
+template <typename T, int V>
+__global__ void __launch_bounds__(kT) lsdb_stats_part_k(double *part, const T *X, const double *shift, long szK, long N, long kchunk)
+{
+    constexpr int U = 8;
+    using VT = typename std::conditional<V == 1, T, typename std::conditional<sizeof(T) == 8, double2, float4>::type>::type;
+    const long e = ((long)blockIdx.x * kT + threadIdx.x) * V;
+    if (e >= szK) return;
+    const long k0 = (long)blockIdx.y * kchunk;
+    long k1 = k0 + kchunk; if (k1 > N) k1 = N;
+    double c[V], sh[V], sl[V], qh[V], ql[V], mn[V], mx[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) { c[v] = shift[e + v]; sh[v] = sl[v] = qh[v] = ql[v] = 0.0; mn[v] = INFINITY; mx[v] = -INFINITY; }
+    auto take = [&](const VT &r) {
+        const T *rv = reinterpret_cast<const T *>(&r);
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            const double a = (double)rv[v] - c[v];
+            dd_acc(sh[v], sl[v], a);
+            const double p = __dmul_rn(a, a);
+            ql[v] += fma(a, a, -p);                        // exact product = p + fma(a,a,-p)
+            dd_acc(qh[v], ql[v], p);
+            mn[v] = fmin(mn[v], a); mx[v] = fmax(mx[v], a);
+        }
+    };
+    const T *p = X + e;
+    long k = k0;
+    for (; k + U <= k1; k += U) {
+        VT r[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) r[u] = __ldcs(reinterpret_cast<const VT *>(p + (k + u) * szK));
+#pragma unroll
+        for (int u = 0; u < U; ++u) take(r[u]);
+    }
+    for (; k < k1; ++k) take(__ldcs(reinterpret_cast<const VT *>(p + k * szK)));
+    double *o = part + ((long)blockIdx.y * 6) * szK + e;
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        dd_norm(sh[v], sl[v]); dd_norm(qh[v], ql[v]);
+        o[v] = sh[v]; o[szK + v] = sl[v]; o[2 * szK + v] = qh[v]; o[3 * szK + v] = ql[v];
+        o[4 * szK + v] = mn[v] + c[v]; o[5 * szK + v] = mx[v] + c[v];
+    }
+}
+
+// combine the slices in index order (double-double): stats rows 1..6 = s_hi, s_lo, q_hi, q_lo, min, max
+__global__ void __launch_bounds__(kT) lsdb_stats_final_k(double *stats, const double *part, long szK, int ksplit)
+{
+    const long e = (long)blockIdx.x * kT + threadIdx.x;
+    if (e >= szK) return;
+    double sh = 0, sl = 0, qh = 0, ql = 0, mn = INFINITY, mx = -INFINITY;
+    for (int ks = 0; ks < ksplit; ++ks) {
+        const double *p = part + ((long)ks * 6) * szK + e;
+        dd_add(sh, sl, p[0], p[szK]);
+        dd_add(qh, ql, p[2 * szK], p[3 * szK]);
+        mn = fmin(mn, p[4 * szK]); mx = fmax(mx, p[5 * szK]);
+    }
+    stats[szK + e] = sh; stats[2 * szK + e] = sl; stats[3 * szK + e] = qh; stats[4 * szK + e] = ql;
+    stats[5 * szK + e] = mn; stats[6 * szK + e] = mx;
+}
+
+// parts (nparts, 2, cnt) of double-double numbers -> out (2, cnt), summed in index order
+__global__ void __launch_bounds__(kT) dd_sum_parts_k(double *out, const double *part, long cnt, int nparts)
+{
+    const long e = (long)blockIdx.x * kT + threadIdx.x;
+    if (e >= cnt) return;
+    double h = 0, l = 0;
+    for (int q = 0; q < nparts; ++q) dd_add(h, l, part[((long)q * 2) * cnt + e], part[((long)q * 2 + 1) * cnt + e]);
+    out[e] = h; out[cnt + e] = l;
+}
+
 static int pick_ksplit(long szK, long N, int sms)
 {
     long blocks_x = (szK + kT - 1) / kT;
@@ -264,10 +366,10 @@ static LsdbGrid lsdb_grid(long N)
 }
 
 // per-position grid origin a and step delta from the reduced statistics  (bestbasis_costs.jl:143-147)
-// stats rows: 0 shift c, 1 sum(x-c), 2 sum((x-c)^2), 3 min, 4 max
+// stats rows: 0 shift c, 1/2 sum(x-c) hi/lo, 3/4 sum((x-c)^2) hi/lo, 5 min, 6 max   (hi = the correctly rounded sum)
 __device__ __forceinline__ void lsdb_axis(const double *stats, long szK, long e, double Ntot, long npts, double &a, double &delta)
 {
-    const double s1 = stats[szK + e], s2 = stats[2 * szK + e], mn = stats[3 * szK + e], mx = stats[4 * szK + e];
+    const double s1 = stats[szK + e], s2 = stats[3 * szK + e], mn = stats[5 * szK + e], mx = stats[6 * szK + e];
     double var = (s2 - s1 * s1 / Ntot) / (Ntot - 1.0);               // Statistics.std (corrected)
     if (var < 0) var = 0;
     const double sg = sqrt(var);
@@ -365,7 +467,7 @@ __global__ void __launch_bounds__(kT) lsdb_logpdf_part_k(double *part, const dou
     const double dinv = 1.0 / delta;
     const long k0 = (long)blockIdx.y * kchunk;
     long k1 = k0 + kchunk; if (k1 > N) k1 = N;
-    double acc = 0.0;
+    double acc = 0.0, accl = 0.0;
     for (long k = k0; k < k1; ++k) {
         const double xv = (double)X[k * szK + e];
         long i = (long)floor((xv - a) * dinv) + 1;                   // searchsortedlast(rng, x), 1-based
@@ -377,9 +479,11 @@ __global__ void __launch_bounds__(kT) lsdb_logpdf_part_k(double *part, const dou
             const double y0 = dens[(i - 1) * szK + e], y1 = dens[i * szK + e];
             pdf = y0 + (y1 - y0) * (xv - g0) / (g1 - g0);
         }
-        acc += log(pdf);
+        dd_acc(acc, accl, log(pdf));
     }
-    part[(long)blockIdx.y * szK + e] = acc;
+    dd_norm(acc, accl);
+    double *o = part + ((long)blockIdx.y * 2) * szK + e;
+    o[0] = acc; o[szK] = accl;
 }
 
 // shared-memory variant: the density columns of the CTA's kL positions are staged in shared memory ((npts, kL) table);
@@ -421,7 +525,7 @@ __global__ void __launch_bounds__(kL * kH) lsdb_logpdf_smem_k(double *part, cons
         }
         return pdf;
     };
-    double acc = 0.0;
+    double acc = 0.0, accl = 0.0;
     long k = k0;
     for (; k + U <= k1; k += U) {
         T r[U];
@@ -430,10 +534,12 @@ __global__ void __launch_bounds__(kL * kH) lsdb_logpdf_smem_k(double *part, cons
         double prod = 1.0;
 #pragma unroll
         for (int u = 0; u < U; ++u) prod *= pdf_at((double)r[u]);
-        acc += log(prod);
+        dd_acc(acc, accl, log(prod));
     }
-    for (; k < k1; ++k) acc += log(pdf_at((double)p[k * szK]));
-    part[((long)blockIdx.y * kH + kh) * szK + e] = acc;
+    for (; k < k1; ++k) dd_acc(acc, accl, log(pdf_at((double)p[k * szK])));
+    dd_norm(acc, accl);
+    double *o = part + ((long)(blockIdx.y * kH + kh) * 2) * szK + e;
+    o[0] = acc; o[szK] = accl;
 }
 
 __global__ void __launch_bounds__(kT) sum_parts_k(double *out, const double *part, long szK, int ksplit)
@@ -443,6 +549,29 @@ __global__ void __launch_bounds__(kT) sum_parts_k(double *out, const double *par
     double s = 0.0;
     for (int ks = 0; ks < ksplit; ++ks) s += part[(long)ks * szK + e];
     out[e] = s;
+}
+
+template <typename T>
+int lsdb_pass1(double *stats, const T *X, long szK, long Nlocal, cudaStream_t s)
+{
+    WX_REQUIRE(stats && szK >= 1 && Nlocal >= 0 && (Nlocal == 0 || X), "bad arguments");
+    WxDev dv; int rc = wx_devinfo(dv); if (rc) return rc;
+    constexpr long V = 16 / (long)sizeof(T);
+    const bool vec = szK % V == 0 && (((uintptr_t)X) & 15) == 0;
+    const int ksplit = Nlocal > 0 ? pick_ksplit(vec ? szK / V : szK, Nlocal, dv.sms) : 1;
+    const long kchunk = Nlocal > 0 ? (Nlocal + ksplit - 1) / ksplit : 1;
+    double *part; rc = wx_scratch(&part, (size_t)ksplit * 6 * szK, s); if (rc) return rc;
+    if (vec) {
+        dim3 grid((unsigned)((szK / V + kT - 1) / kT), (unsigned)ksplit);
+        lsdb_stats_part_k<T, (int)V><<<grid, kT, 0, s>>>(part, X, stats, szK, Nlocal, kchunk);
+    } else {
+        dim3 grid((unsigned)((szK + kT - 1) / kT), (unsigned)ksplit);
+        lsdb_stats_part_k<T, 1><<<grid, kT, 0, s>>>(part, X, stats, szK, Nlocal, kchunk);
+    }
+    WX_LAUNCHED();
+    lsdb_stats_final_k<<<gridf(szK), kT, 0, s>>>(stats, part, szK, ksplit);
+    WX_LAUNCHED();
+    return wx_scratch_free(part, s);
 }
 
 template <typename T>
@@ -475,13 +604,13 @@ int lsdb_pass3(double *logsum, const double *counts, const double *stats, const 
     WX_REQUIRE(szK >= 1 && Nlocal >= 0 && Ntotal >= 2, "LSDB needs at least two signals");
     WX_REQUIRE(logsum && counts && stats && (Nlocal == 0 || X), "null pointer");
     const LsdbGrid g = lsdb_grid(Ntotal);
-    if (Nlocal == 0) { WX_CUDA(cudaMemsetAsync(logsum, 0, (size_t)szK * sizeof(double), s)); return WX_OK; }
+    if (Nlocal == 0) { WX_CUDA(cudaMemsetAsync(logsum, 0, (size_t)2 * szK * sizeof(double), s)); return WX_OK; }
     WxDev dv; int rc = wx_devinfo(dv); if (rc) return rc;
     const int ksplit = pick_ksplit(szK, Nlocal, dv.sms);
     const long kchunk = (Nlocal + ksplit - 1) / ksplit;
     double *dens, *part;
     rc = wx_scratch(&dens, (size_t)g.npts * szK, s); if (rc) return rc;
-    rc = wx_scratch(&part, (size_t)ksplit * kH * szK, s); if (rc) return rc;
+    rc = wx_scratch(&part, (size_t)ksplit * kH * 2 * szK, s); if (rc) return rc;
     lsdb_density_k<<<gridf(szK), kT, 0, s>>>(dens, counts, stats, szK, (double)Ntotal, g.npts, g.mbins);
     WX_LAUNCHED();
     const size_t smem = (size_t)g.npts * kL * sizeof(double);
@@ -497,7 +626,7 @@ int lsdb_pass3(double *logsum, const double *counts, const double *stats, const 
         lsdb_logpdf_part_k<T><<<grid, kT, 0, s>>>(part, dens, stats, X, szK, Nlocal, kchunk, (double)Ntotal, g.npts);
     }
     WX_LAUNCHED();
-    sum_parts_k<<<gridf(szK), kT, 0, s>>>(logsum, part, szK, nparts);
+    dd_sum_parts_k<<<gridf(szK), kT, 0, s>>>(logsum, part, szK, nparts);
     WX_LAUNCHED();
     int rc2 = wx_scratch_free(dens, s), rc3 = wx_scratch_free(part, s);
     return rc2 ? rc2 : rc3;
@@ -559,16 +688,19 @@ int wx_lsdb_grid(long Ntotal, long *nbins, long *mbins, long *npts)
     return WX_OK;
 }
 
-// stats(5, szK): row 0 = shift (INPUT, caller-filled, e.g. the first signal of the global batch), rows 1..4 = outputs
-int wx_lsdb_pass1_f64(double *stats, const double *X, long szK, long Nlocal, void *stream)
+// stats(7, szK): row 0 = shift (INPUT, caller-filled, e.g. the first signal of the global batch); rows 1..6 = outputs:
+// sum(x-c) hi/lo, sum((x-c)^2) hi/lo (double-double), min, max over the LOCAL batch.
+int wx_lsdb_pass1_f64(double *stats, const double *X, long szK, long Nlocal, void *stream) { return lsdb_pass1<double>(stats, X, szK, Nlocal, (cudaStream_t)stream); }
+int wx_lsdb_pass1_f32(double *stats, const float *X, long szK, long Nlocal, void *stream) { return lsdb_pass1<float>(stats, X, szK, Nlocal, (cudaStream_t)stream); }
+// parts (nparts, 2, count) double-double numbers (hi row, lo row) -> out (2, count), summed in index order: the cross-rank
+// combination of all-gathered LSDB statistics / log sums (exact to ~1e-32, hence independent of the sharding)
+int wx_dd_sum(double *out, const double *parts, long count, int nparts, void *stream)
 {
-    WX_REQUIRE(stats, "null pointer");
-    return moments<double, 1>(stats + szK, stats + 2 * szK, stats + 3 * szK, stats + 4 * szK, X, stats, szK, Nlocal, (cudaStream_t)stream);
-}
-int wx_lsdb_pass1_f32(double *stats, const float *X, long szK, long Nlocal, void *stream)
-{
-    WX_REQUIRE(stats, "null pointer");
-    return moments<float, 1>(stats + szK, stats + 2 * szK, stats + 3 * szK, stats + 4 * szK, X, stats, szK, Nlocal, (cudaStream_t)stream);
+    WX_REQUIRE(out && parts && count >= 0 && nparts >= 1, "bad arguments");
+    if (count == 0) return WX_OK;
+    dd_sum_parts_k<<<gridf(count), kT, 0, (cudaStream_t)stream>>>(out, parts, count, nparts);
+    WX_LAUNCHED();
+    return WX_OK;
 }
 int wx_lsdb_pass2_f64(double *counts, const double *stats, const double *X, long szK, long Nlocal, long Ntotal, void *s) { return lsdb_pass2<double>(counts, stats, X, szK, Nlocal, Ntotal, (cudaStream_t)s); }
 int wx_lsdb_pass2_f32(double *counts, const double *stats, const float *X, long szK, long Nlocal, long Ntotal, void *s) { return lsdb_pass2<float>(counts, stats, X, szK, Nlocal, Ntotal, (cudaStream_t)s); }

@@ -10,7 +10,7 @@ import torch
 import torch.distributed as dist
 
 __all__ = ["shard_range", "shard", "is_dist", "rank", "world_size", "allreduce_sum", "allreduce_min", "allreduce_max",
-           "total_count", "broadcast_from_first"]
+           "total_count", "broadcast_from_first", "allgather_parts", "dd_sum_host"]
 
 
 def is_dist(group=None) -> bool:
@@ -76,3 +76,33 @@ def broadcast_from_first(t: torch.Tensor, group=None) -> torch.Tensor:
         t = t.contiguous()
         dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
     return t
+
+
+def allgather_parts(pair: torch.Tensor, group=None) -> torch.Tensor:
+    """all-gather of a (2, count) double-double buffer (hi row, lo row) -> (world, 2, count), rank order.  The caller
+    sums the parts in that fixed order in double-double arithmetic (``wx_dd_sum`` on the device, ``dd_sum_host`` in the
+    CPU tests): the result is exact to ~1e-32, so it does not depend on how the batch was sharded."""
+    pair = pair.contiguous()
+    if not (is_dist(group) and world_size(group) > 1):
+        return pair.unsqueeze(0)
+    out = torch.empty((world_size(group),) + tuple(pair.shape), dtype=pair.dtype, device=pair.device)
+    if pair.is_cuda:
+        dist.all_gather_into_tensor(out, pair, group=group)
+    else:                                                  # gloo (CPU tests)
+        dist.all_gather(list(out.unbind(0)), pair, group=group)
+    return out
+
+
+def dd_sum_host(parts: torch.Tensor) -> torch.Tensor:
+    """(nparts, 2, count) -> (2, count): the double-double sum in index order with elementwise torch ops (each op is
+    correctly rounded; no fused multiply-add is involved).  Host mirror of ``wx_dd_sum`` for the gloo tests."""
+    hi = torch.zeros_like(parts[0, 0]); lo = torch.zeros_like(hi)
+    for q in range(parts.shape[0]):
+        bh, bl = parts[q, 0], parts[q, 1]
+        s = hi + bh
+        bb = s - hi
+        e = (hi - (s - bb)) + (bh - bb)
+        e = e + (lo + bl)
+        hi = s + e
+        lo = e - (hi - s)
+    return torch.stack([hi, lo])
