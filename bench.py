@@ -270,7 +270,7 @@ def main():
     except Exception:
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "kernel": "wpd1d_fused_k", "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": avg_launch_ms, "peak_source": peak_src}
+                "kernel": "wpd1d_tma_k", "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": avg_launch_ms, "peak_source": peak_src}
 
     cpu = None
     if not a.no_cpu and world == 1:
