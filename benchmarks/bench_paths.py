@@ -105,6 +105,58 @@ def main():
                 report(f"wpd2d_{tag}_{wname}", ms, nl, es * m * n2 * N * (L + 2), m * n2 * N, "GPixels_per_s")
                 del x, y
                 torch.cuda.empty_cache()
+    # general path (one launch per depth): the other output shapes and the inverses of the redundant families, 2-D by tree
+    if any(want(k) for k in ("general", "sdwt", "iswt", "tree2d", "swt2d")):
+        dt, es = torch.float64, 8
+        n, N, L = 2048, int(2048 * a.scale), 8
+        wt = wx.wavelet("db4")
+        x = torch.randn((N, n), dtype=dt, device=dev, generator=gen)
+        if want("general") or want("sdwt"):
+            for nm, fn in (("sdwtall", wx.sdwtall), ("acdwtall", wx.acdwtall)):
+                ms, nl = timeit(lambda: fn(x, wt, L), steps=3, warmup=1)
+                report(f"{nm}_f64", ms, nl, es * n * N * (L + 2), n * N, "GSamples_per_s")
+        if want("general") or want("iswt"):
+            xd = wx.sdwtall(x, wt, L)
+            for sm in (None, 5):
+                ms, nl = timeit(lambda: wx.isdwtall(xd, wt, sm), steps=3, warmup=1)
+                report(f"isdwtall_f64_{'avg' if sm is None else 'shift'}", ms, nl, es * n * N * (L + 2), n * N, "GSamples_per_s")
+            ms, nl = timeit(lambda: wx.iacdwtall(wx.acdwtall(x, wt, L)), steps=3, warmup=1)
+            del xd
+            xt = wx.swptall(x, wt, L)
+            for sm in (None, 5):
+                ms, nl = timeit(lambda: wx.iswptall(xt, wt, sm), steps=3, warmup=1)
+                err = float((wx.iswptall(xt, wt, sm) - x).abs().max() / x.abs().max())
+                report(f"iswptall_f64_{'avg' if sm is None else 'shift'}", ms, nl, es * n * N * ((1 << L) + 1), n * N, "GSamples_per_s", {"roundtrip_relerr": err})
+            xa = wx.acwptall(x, wt, L)
+            ms, nl = timeit(lambda: wx.iacwptall(xa), steps=3, warmup=1)
+            report("iacwptall_f64", ms, nl, es * n * N * ((1 << L) + 1), n * N, "GSamples_per_s")
+            del xt, xa
+            torch.cuda.empty_cache()
+        del x
+        if want("general") or want("tree2d"):
+            m = n2 = 512
+            N2, L2 = int(1024 * a.scale), 5
+            xi = torch.randn((N2, n2, m), dtype=dt, device=dev, generator=gen)
+            tree = wx.maketree(m, n2, L2, "full")
+            ms, nl = timeit(lambda: wx.wptall(xi, wt, tree), steps=3, warmup=1)
+            report("wptall2d_f64", ms, nl, 2 * es * m * n2 * N2, m * n2 * N2, "GPixels_per_s")
+            yi = wx.wptall(xi, wt, tree)
+            ms, nl = timeit(lambda: wx.iwptall(yi, wt, tree), steps=3, warmup=1)
+            err = float((wx.iwptall(yi, wt, tree) - xi).abs().max() / xi.abs().max())
+            report("iwptall2d_f64", ms, nl, 2 * es * m * n2 * N2, m * n2 * N2, "GPixels_per_s", {"roundtrip_relerr": err})
+            del xi, yi
+            torch.cuda.empty_cache()
+        if want("general") or want("swt2d"):
+            m = n2 = 256
+            N2, L2 = int(64 * a.scale) or 1, 3
+            xi = torch.randn((N2, n2, m), dtype=dt, device=dev, generator=gen)
+            nsl = (4 ** (L2 + 1) - 1) // 3
+            ms, nl = timeit(lambda: wx.swpdall(xi, wt, L2), steps=3, warmup=1)
+            report("swpdall2d_f64", ms, nl, es * m * n2 * N2 * (nsl + 1), m * n2 * N2, "GPixels_per_s")
+            ms, nl = timeit(lambda: wx.acwpdall(xi, wt, L2), steps=3, warmup=1)
+            report("acwpdall2d_f64", ms, nl, es * m * n2 * N2 * (nsl + 1), m * n2 * N2, "GPixels_per_s")
+            del xi
+            torch.cuda.empty_cache()
     # config 5: JBB / LSDB best basis + getbasiscoefall + iwptall on 131072 signals x 1024 per GPU (1M over 8 GPUs)
     n, N, L = 1024, int(131072 * a.scale), 10
     if want("jbb") or want("lsdb") or want("basis_iwpt"):
