@@ -170,6 +170,80 @@ __global__ void __launch_bounds__(256) rwpd_dfs_k(T *__restrict__ xw, const T *_
     if (tid == 0) wx_bulk_wait_all();
 }
 
+// sdwt! / acdwt! (SWT.jl:120-129, ACWT.jl:120-131): the scaling branch only.  xw(n, L+1, N): column L-d = detail of depth d+1,
+// column 0 = scaling of depth L.  One signal per CTA iteration: the scaling node ping-pongs between two buffers, each
+// detail leaves through a bulk store from one of two detail buffers; after `dend` levels the scaling node is stored in
+// column L-dend (= column 0 when dend == L; otherwise the per-depth path continues from there).
+template <typename T, int F, int AC>
+__global__ void __launch_bounds__(256) rdwt_chain_k(T *__restrict__ xw, const T *__restrict__ x, int n, int L, int dend, long N, Taps<T> tp)
+{
+    extern __shared__ __align__(128) unsigned char wx_rw_smem[];
+    __shared__ __align__(8) unsigned long long bar;
+    T *sc[2] = {reinterpret_cast<T *>(wx_rw_smem), reinterpret_cast<T *>(wx_rw_smem) + n};
+    T *dt[2] = {sc[1] + n, sc[1] + 2 * (size_t)n};
+    const unsigned nbytes = (unsigned)n * (unsigned)sizeof(T);
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    if (tid == 0) {
+        wx_mbar_init(&bar, 1);
+        wx_fence_mbar_init();
+    }
+    __syncthreads();
+    unsigned parity = 0;
+    for (long k = blockIdx.x; k < N; k += gridDim.x) {
+        T *xk = xw + k * (long)(L + 1) * n;
+        if (tid == 0) {
+            wx_bulk_wait_read0();
+            wx_mbar_expect_tx(&bar, nbytes);
+            wx_bulk_load_1d(sc[0], x + k * n, nbytes, &bar);
+        }
+        wx_mbar_wait(&bar, parity);
+        parity ^= 1;
+        int cur = 0;
+        for (int d = 0; d < dend; ++d) {
+            rw_pass2<T, F, AC>(sc[cur], sc[cur ^ 1], dt[d & 1], n, d, tp, tid, nthr);
+            wx_fence_proxy_async();
+            if (tid == 0) wx_bulk_wait_read0();
+            __syncthreads();
+            if (tid == 0) {
+                wx_bulk_store_1d(xk + (long)(L - d) * n, dt[d & 1], nbytes);
+                wx_bulk_commit();
+            }
+            cur ^= 1;
+        }
+        if (tid == 0) {
+            wx_bulk_store_1d(xk + (long)(L - dend) * n, sc[cur], nbytes);
+            wx_bulk_commit();
+        }
+    }
+    if (tid == 0) wx_bulk_wait_all();
+}
+
+template <typename T, int F, int AC>
+int rdwt_chain_plan(T *xw, const T *x, long n, int L, long N, const Taps<T> &t, cudaStream_t s, int *done)
+{
+    using C = RwCfg<T, F>;
+    WxDev dv; int rc = wx_devinfo(dv); if (rc) return rc;
+    const int lgn = wx_ilog2l(n);
+    if (lgn < C::LGK) return WX_OK;
+    int dend = lgn - C::LGK + 1;
+    if (dend > L) dend = L;
+    const size_t smem = (size_t)4 * n * sizeof(T);
+    if (smem > dv.smem_optin) return WX_OK;
+    int threads = (int)(((n >> C::LGK) + 31) / 32 * 32);
+    if (threads > 256) threads = 256;
+    auto kern = rdwt_chain_k<T, F, AC>;
+    WX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    WX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
+    if (occ < 1) return WX_OK;
+    long blocks = (long)dv.sms * occ;
+    if (blocks > N) blocks = N;
+    kern<<<(unsigned)blocks, threads, smem, s>>>(xw, x, (int)n, L, dend, N, t);
+    WX_LAUNCHED();
+    *done = dend;
+    return WX_OK;
+}
+
 template <typename T, int F, int AC>
 int rwpd_launch(T *xw, const T *x, long n, long ncols, int dstart, int dend, int L, int wpt, long N, const Taps<T> &t, cudaStream_t s)
 {
@@ -250,3 +324,102 @@ int wx_rwpd1d_fused(int ac, int wpt, T *xw, const T *x, long n, int L, long N, c
 }
 template int wx_rwpd1d_fused<double>(int, int, double *, const double *, long, int, long, const Taps<double> &, cudaStream_t, int *);
 template int wx_rwpd1d_fused<float>(int, int, float *, const float *, long, int, long, const Taps<float> &, cudaStream_t, int *);
+
+// sdwt / acdwt (scaling chain): runs the leading `*done` levels; the scaling node of depth *done is left in column L-*done.
+template <typename T>
+int wx_rdwt1d_fused(int ac, T *xw, const T *x, long n, int L, long N, const Taps<T> &t, cudaStream_t s, int *done)
+{
+    *done = 0;
+    if (L < 1 || N < 1 || !wx_ispow2(n) || n >= (1L << 30) || L > 30) return WX_OK;
+    if ((n * sizeof(T)) % 16 != 0 || ((((uintptr_t)xw) | ((uintptr_t)x)) & 15) != 0) return WX_OK;
+    static const bool off = getenv("WX_B200_NO_FUSED_RWPD") != nullptr;
+    if (off) return WX_OK;
+#define WX_RC_CASE(FF, AA) case FF: return rdwt_chain_plan<T, FF, AA>(xw, x, n, L, N, t, s, done);
+    if (ac) {
+        switch (t.F) { WX_RC_CASE(3, 1) WX_RC_CASE(7, 1) WX_RC_CASE(11, 1) WX_RC_CASE(15, 1) WX_RC_CASE(19, 1) WX_RC_CASE(23, 1) WX_RC_CASE(31, 1) WX_RC_CASE(39, 1) }
+    } else {
+        switch (t.F) { WX_RC_CASE(2, 0) WX_RC_CASE(4, 0) WX_RC_CASE(6, 0) WX_RC_CASE(8, 0) WX_RC_CASE(10, 0) WX_RC_CASE(12, 0) WX_RC_CASE(16, 0) WX_RC_CASE(20, 0) }
+    }
+#undef WX_RC_CASE
+    return WX_OK;
+}
+template int wx_rdwt1d_fused<double>(int, double *, const double *, long, int, long, const Taps<double> &, cudaStream_t, int *);
+template int wx_rdwt1d_fused<float>(int, float *, const float *, long, int, long, const Taps<float> &, cudaStream_t, int *);
+
+// ---- autocorrelation inverses are plain sums: iacdwt_step!(v, w1, w2) = (w1 + w2) / sqrt(2)  acwt/acwt_one_level.jl:217-224 ----
+namespace {
+
+// iacwpt! / iacwpd!(xw, L) (ACWT.jl:594-607, 954-969): x = pairwise tree sum of the 2^L depth-L columns starting at column c0,
+// in the reference's order ((w_{2b} + w_{2b+1}) / sqrt2 at every level).  One thread per (position, signal): a binary-counter
+// reduction, eight columns at a time in registers.
+template <typename T>
+__global__ void __launch_bounds__(256) iac_tree_sum_k(T *__restrict__ x, const T *__restrict__ xw, long n, long ncols, long c0, int L, long N)
+{
+    const long gid = (long)blockIdx.x * 256 + threadIdx.x;
+    if (gid >= n * N) return;
+    const long k = gid / n, i = gid - k * n;
+    const T *p = xw + (k * ncols + c0) * n + i;
+    const T r2 = (T)1.4142135623730951;
+    T stack[32];
+    const long nleaf = 1L << L;
+    if (L < 3) {
+        for (long c = 0; c < nleaf; ++c) {
+            T v = p[c * n];
+            int lvl = 0;
+            while ((c >> lvl) & 1) { v = (stack[lvl] + v) / r2; ++lvl; }
+            stack[lvl] = v;
+        }
+        x[gid] = stack[L];
+        return;
+    }
+    for (long c8 = 0; c8 < (nleaf >> 3); ++c8) {
+        T v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = __ldcs(p + (c8 * 8 + j) * n);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = (v[2 * j] + v[2 * j + 1]) / r2;
+        v[0] = (v[0] + v[1]) / r2; v[1] = (v[2] + v[3]) / r2;
+        T a = (v[0] + v[1]) / r2;
+        int lvl = 0;
+        while ((c8 >> lvl) & 1) { a = (stack[lvl] + a) / r2; ++lvl; }
+        stack[lvl] = a;
+    }
+    x[gid] = stack[L - 3];
+}
+
+// iacdwt! (ACWT.jl:292-303): x = col 0; for d = L-1..0: x = (x + col L-d) / sqrt2
+template <typename T>
+__global__ void __launch_bounds__(256) iac_chain_sum_k(T *__restrict__ x, const T *__restrict__ xw, long n, int L, long N)
+{
+    const long gid = (long)blockIdx.x * 256 + threadIdx.x;
+    if (gid >= n * N) return;
+    const long k = gid / n, i = gid - k * n;
+    const T *p = xw + k * (long)(L + 1) * n + i;
+    const T r2 = (T)1.4142135623730951;
+    T a = p[0];
+    for (int c = 1; c <= L; ++c) a = (a + __ldcs(p + (long)c * n)) / r2;
+    x[gid] = a;
+}
+
+}  // namespace
+
+template <typename T>
+int wx_iac_tree_sum(T *x, const T *xw, long n, long ncols, long c0, int L, long N, cudaStream_t s)
+{
+    if (n * N == 0) return WX_OK;
+    iac_tree_sum_k<T><<<(unsigned)((n * N + 255) / 256), 256, 0, s>>>(x, xw, n, ncols, c0, L, N);
+    WX_LAUNCHED();
+    return WX_OK;
+}
+template <typename T>
+int wx_iac_chain_sum(T *x, const T *xw, long n, int L, long N, cudaStream_t s)
+{
+    if (n * N == 0) return WX_OK;
+    iac_chain_sum_k<T><<<(unsigned)((n * N + 255) / 256), 256, 0, s>>>(x, xw, n, L, N);
+    WX_LAUNCHED();
+    return WX_OK;
+}
+template int wx_iac_tree_sum<double>(double *, const double *, long, long, long, int, long, cudaStream_t);
+template int wx_iac_tree_sum<float>(float *, const float *, long, long, long, int, long, cudaStream_t);
+template int wx_iac_chain_sum<double>(double *, const double *, long, int, long, cudaStream_t);
+template int wx_iac_chain_sum<float>(float *, const float *, long, int, long, cudaStream_t);

@@ -11,6 +11,10 @@
 
 template <typename T>
 int wx_rwpd1d_fused(int ac, int wpt, T *xw, const T *x, long n, int L, long N, const Taps<T> &t, cudaStream_t s, int *done);
+template <typename T>
+int wx_rdwt1d_fused(int ac, T *xw, const T *x, long n, int L, long N, const Taps<T> &t, cudaStream_t s, int *done);
+template <typename T> int wx_iac_tree_sum(T *x, const T *xw, long n, long ncols, long c0, int L, long N, cudaStream_t s);
+template <typename T> int wx_iac_chain_sum(T *x, const T *xw, long n, int L, long N, cudaStream_t s);
 
 namespace {
 
@@ -107,10 +111,15 @@ int rwt_fwd_1d(int ac, int mode, T *xw, const T *x, long n, int L, long N, const
     }
     // sdwt! SWT.jl:120-129 : xw(n, L+1, N); column L = x; depth d: parent = copy(col L-d) -> cols L-d-1 (scaling), L-d (detail)
     const long str = n * (L + 1);
-    rc = wx_launch_copy<T>(View<T>{xw + (long)L * n, 1, str, 0, 0}, View<const T>{x, 1, n, 0, 0}, n, Batch{N, 1, 1, false}, s);
-    if (rc) return rc;
+    int done = 0;                                            // leading levels produced by the fused chain kernel
+    rc = wx_rdwt1d_fused<T>(ac, xw, x, n, L, N, t, s, &done);
+    if (rc || done == L) return rc;
+    if (done == 0) {
+        rc = wx_launch_copy<T>(View<T>{xw + (long)L * n, 1, str, 0, 0}, View<const T>{x, 1, n, 0, 0}, n, Batch{N, 1, 1, false}, s);
+        if (rc) return rc;
+    }
     T *tmp; rc = wx_scratch(&tmp, (size_t)n * N, s); if (rc) return rc;
-    for (int d = 0; d < L && !rc; ++d) {
+    for (int d = done; d < L && !rc; ++d) {
         T *par = xw + (long)(L - d) * n;
         rc = wx_launch_copy<T>(View<T>{tmp, 1, n, 0, 0}, View<const T>{par, 1, str, 0, 0}, n, Batch{N, 1, 1, false}, s);
         if (!rc) rc = wx_launch_rdwt_step<T>(ac, View<T>{par - n, 1, str, 0, 0}, View<T>{par, 1, str, 0, 0}, View<const T>{tmp, 1, n, 0, 0}, n, d,
@@ -200,6 +209,8 @@ int irwt_1d(int imode, int mode, T *x, const T *xw, long n, long ncols, int L, l
     const long str = n * ncols;
     auto SV = [&](int d) { return imode == 1 ? sd[(size_t)d] : 0L; };
     auto SW = [&](int d) { return imode == 1 ? sd[(size_t)d + 1] : 0L; };
+    if (imode == 2 && mode == WX_MODE_DWT) return wx_iac_chain_sum<T>(x, xw, n, L, N, s);        // plain sums: one pass over the table
+    if (imode == 2 && mode == WX_MODE_WPT && L < 32) return wx_iac_tree_sum<T>(x, xw, n, ncols, 0, L, N, s);
     if (mode == WX_MODE_DWT) {
         // isdwt! SWT.jl:270-282, 311-328 ; iacdwt! ACWT.jl:292-303 : x = col 0; for d = L-1..0: x = step(copy(x), col L-d)
         T *tmp; rc = wx_scratch(&tmp, (size_t)n * N, s); if (rc) return rc;
@@ -242,6 +253,12 @@ int irwt_1d(int imode, int mode, T *x, const T *xw, long n, long ncols, int L, l
     const int Lx = wx_ilog2l(ncols + 1) - 1;                 // ncols = 2^(Lx+1)-1
     long lastsplit = 0;
     for (long i = ntree; i >= 1; --i) if (tree[i - 1]) { lastsplit = i; break; }
+    if (imode == 2 && lastsplit > 0) {                       // autocorrelation + complete tree of depth Lt: pairwise sum of the depth-Lt columns
+        const int Lt = wx_ilog2l(lastsplit) + 1;
+        bool full = lastsplit == (1L << Lt) - 1 && Lt < 32 && (1L << (Lt + 1)) - 1 <= ncols;
+        for (long i = 1; full && i <= lastsplit; ++i) full = tree[i - 1] != 0;
+        if (full) return wx_iac_tree_sum<T>(x, xw, n, ncols, (1L << Lt) - 1, Lt, N, s);
+    }
     if (lastsplit == 0) {                                    // root is a leaf: x = column 0
         return wx_launch_copy<T>(View<T>{x, 1, n, 0, 0}, View<const T>{xw, 1, str, 0, 0}, n, Batch{N, 1, 1, false}, s);
     }

@@ -8,36 +8,91 @@ namespace {
 
 constexpr int kThreads = 256;
 
+// Division of a 32-bit index by a launch constant without the integer divide sequence (round-up multiply-high, exact for
+// every 32-bit dividend); powers of two are shifts.
+struct Div32 {
+    unsigned d, m, s;
+    bool p2;
+};
+static inline Div32 make_div32(long dd)
+{
+    Div32 r;
+    r.d = (unsigned)dd; r.p2 = (dd & (dd - 1)) == 0; r.m = 0; r.s = 0;
+    if (r.p2) { while ((1L << r.s) < dd) ++r.s; return r; }
+    unsigned l = 0;
+    while ((1UL << l) < (unsigned long)dd) ++l;                       // l = ceil(log2 d)
+    r.m = (unsigned)((((1UL << l) - (unsigned long)dd) << 32) / (unsigned long)dd + 1);
+    r.s = l - 1;
+    return r;
+}
+__device__ __forceinline__ unsigned div32(unsigned x, const Div32 &v)
+{
+    if (v.p2) return x >> v.s;
+    const unsigned t = __umulhi(v.m, x);
+    return (t + ((x - t) >> 1)) >> v.s;
+}
+
+// flattened launch index -> (element i, batch coordinates); 32-bit fast path when the launch has < 2^32 threads
+struct Geo {
+    Batch b;
+    long nout;
+    bool small;
+    Div32 dn, d0, d1;
+};
+static inline Geo make_geo(long nout, const Batch &b)
+{
+    Geo g; g.b = b; g.nout = nout;
+    const long tot = nout * b.B0 * b.B1 * b.B2;
+    g.small = tot < (1L << 32) && nout < (1L << 31) && b.B0 < (1L << 31) && b.B1 < (1L << 31);
+    g.dn = make_div32(nout > 0 ? nout : 1); g.d0 = make_div32(b.B0 > 0 ? b.B0 : 1); g.d1 = make_div32(b.B1 > 0 ? b.B1 : 1);
+    return g;
+}
+
 template <typename T>
 __device__ __forceinline__ long voff(const View<T> &v, long b0, long b1, long b2)
 {
     return b0 * v.s0 + b1 * v.s1 + b2 * v.s2;
 }
 
-__device__ __forceinline__ bool decomp(long idx, long nout, const Batch &b, long &i, long &b0, long &b1, long &b2)
+__device__ __forceinline__ bool decomp(const Geo &g, long &i, long &b0, long &b1, long &b2)
 {
-    long tot = nout * b.B0 * b.B1 * b.B2;
+    if (g.small) {
+        const unsigned long tot = (unsigned long)g.nout * g.b.B0 * g.b.B1 * g.b.B2;
+        const unsigned long gid = (unsigned long)blockIdx.x * kThreads + threadIdx.x;
+        if (gid >= tot) return false;
+        unsigned idx = (unsigned)gid, q;
+        if (g.b.batch_fast) { q = div32(idx, g.d0); b0 = idx - q * g.d0.d; idx = q; q = div32(idx, g.dn); i = idx - q * g.dn.d; idx = q; }
+        else                { q = div32(idx, g.dn); i = idx - q * g.dn.d; idx = q; q = div32(idx, g.d0); b0 = idx - q * g.d0.d; idx = q; }
+        q = div32(idx, g.d1); b1 = idx - q * g.d1.d; b2 = q;
+        return true;
+    }
+    long idx = (long)blockIdx.x * kThreads + threadIdx.x;
+    const long tot = g.nout * g.b.B0 * g.b.B1 * g.b.B2;
     if (idx >= tot) return false;
-    if (b.batch_fast) { b0 = idx % b.B0; idx /= b.B0; i = idx % nout; idx /= nout; }
-    else              { i = idx % nout; idx /= nout; b0 = idx % b.B0; idx /= b.B0; }
-    b1 = idx % b.B1; b2 = idx / b.B1;
+    if (g.b.batch_fast) { b0 = idx % g.b.B0; idx /= g.b.B0; i = idx % g.nout; idx /= g.nout; }
+    else                { i = idx % g.nout; idx /= g.nout; b0 = idx % g.b.B0; idx /= g.b.B0; }
+    b1 = idx % g.b.B1; b2 = idx / g.b.B1;
     return true;
 }
 
 static inline unsigned grid_for(long total) { return (unsigned)((total + kThreads - 1) / kThreads); }
 
+// FF > 0: filter length known at compile time (taps become immediate constant-bank operands, loops unroll); FF = 0: tp.F
+#define WX_F (FF > 0 ? FF : tp.F)
+
 // a1 dwt_step!  dwt/dwt_one_level.jl:94-105
-template <typename T>
-__global__ void __launch_bounds__(kThreads) dwt_step_k(View<T> w1, View<T> w2, View<const T> v, long n, Batch b, Taps<T> tp)
+template <typename T, int FF>
+__global__ void __launch_bounds__(kThreads) dwt_step_k(View<T> w1, View<T> w2, View<const T> v, long n, Geo geo, Taps<T> tp)
 {
     long i, b0, b1, b2;
-    if (!decomp((long)blockIdx.x * kThreads + threadIdx.x, n / 2, b, i, b0, b1, b2)) return;
+    if (!decomp(geo, i, b0, b1, b2)) return;
     const T *pv = v.p + voff(v, b0, b1, b2);
-    const int F = tp.F;
+    const int F = WX_F;
     long k1 = 2 * i, k2 = 2 * i + 1;
     if (k2 >= n) k2 -= n;
     T a1 = tp.g[F - 1] * pv[k1 * v.es];
     T a2 = tp.h[0] * pv[k2 * v.es];
+#pragma unroll
     for (int j = 1; j < F; ++j) {
         k1 += 1; if (k1 >= n) k1 -= n;
         k2 -= 1; if (k2 < 0) k2 += n;
@@ -49,14 +104,14 @@ __global__ void __launch_bounds__(kThreads) dwt_step_k(View<T> w1, View<T> w2, V
 }
 
 // a2 idwt_step! dwt/dwt_one_level.jl:207-221
-template <typename T>
-__global__ void __launch_bounds__(kThreads) idwt_step_k(View<T> v, View<const T> w1, View<const T> w2, long n, Batch b, Taps<T> tp)
+template <typename T, int FF>
+__global__ void __launch_bounds__(kThreads) idwt_step_k(View<T> v, View<const T> w1, View<const T> w2, long n, Geo geo, Taps<T> tp)
 {
     long i0b, b0, b1, b2;
-    if (!decomp((long)blockIdx.x * kThreads + threadIdx.x, n, b, i0b, b0, b1, b2)) return;
+    if (!decomp(geo, i0b, b0, b1, b2)) return;
     const T *p1 = w1.p + voff(w1, b0, b1, b2);
     const T *p2 = w2.p + voff(w2, b0, b1, b2);
-    const int F = tp.F;
+    const int F = WX_F;
     const long n1 = n / 2;
     long i = i0b + 1;                              // Julia's 1-based i
     int j0 = (i & 1) ? 1 : 2;
@@ -64,7 +119,10 @@ __global__ void __launch_bounds__(kThreads) idwt_step_k(View<T> v, View<const T>
     int j2 = ((i + 1) & 1) ? 1 : 2;
     long k1 = (i + 1) >> 1, k2 = k1;
     T acc = fma(tp.g[j1 - 1], p1[(k1 - 1) * w1.es], tp.h[j2 - 1] * p2[(k2 - 1) * w2.es]);
-    for (int j = j0 + 2; j <= F; j += 2) {
+#pragma unroll
+    for (int jj = 1; jj < (F + 1) / 2; ++jj) {
+        const int j = j0 + 2 * jj;
+        if (j > F) break;
         j1 = F - j + 1;
         j2 = j + ((j & 1) ? 1 : -1);
         k1 -= 1; if (k1 <= 0) k1 += n1;
@@ -75,18 +133,19 @@ __global__ void __launch_bounds__(kThreads) idwt_step_k(View<T> v, View<const T>
 }
 
 // a9 sdwt_step! swt/swt_one_level.jl:114-125  /  a16 acdwt_step! acwt/acwt_one_level.jl:115-126
-template <typename T, int AC>
-__global__ void __launch_bounds__(kThreads) rdwt_step_k(View<T> w1, View<T> w2, View<const T> v, long n, long D, Batch b, Taps<T> tp)
+template <typename T, int AC, int FF>
+__global__ void __launch_bounds__(kThreads) rdwt_step_k(View<T> w1, View<T> w2, View<const T> v, long n, long D, Geo geo, Taps<T> tp)
 {
     long i, b0, b1, b2;
-    if (!decomp((long)blockIdx.x * kThreads + threadIdx.x, n, b, i, b0, b1, b2)) return;
+    if (!decomp(geo, i, b0, b1, b2)) return;
     const T *pv = v.p + voff(v, b0, b1, b2);
-    const int F = tp.F;
+    const int F = WX_F;
     const long Dm = D % n;
     if (AC == 0) {
         long k1 = wx_wrapl(i - D, n), k2 = i;
         T a1 = tp.g[F - 1] * pv[k1 * v.es];
         T a2 = tp.h[0] * pv[k2 * v.es];
+#pragma unroll
         for (int j = 1; j < F; ++j) {
             k1 += Dm; if (k1 >= n) k1 -= n;
             k2 -= Dm; if (k2 < 0) k2 += n;
@@ -100,6 +159,7 @@ __global__ void __launch_bounds__(kThreads) rdwt_step_k(View<T> w1, View<T> w2, 
         long io = wx_wrapl(i + (long)(F / 2 + 1) * D, n);              // output position
         T xv = pv[t * v.es];
         T a1 = tp.g[0] * xv, a2 = tp.h[0] * xv;
+#pragma unroll
         for (int k = 1; k < F; ++k) {
             t += Dm; if (t >= n) t -= n;
             xv = pv[t * v.es];
@@ -112,11 +172,11 @@ __global__ void __launch_bounds__(kThreads) rdwt_step_k(View<T> w1, View<T> w2, 
 }
 
 // one output of the shift-based inverse stationary step, swt/swt_one_level.jl:301-315 ; t is 1-based
-template <typename T>
+template <typename T, int FF>
 __device__ __forceinline__ T isdwt_elem(const T *p1, long e1, const T *p2, long e2, long n, int d, long sw, long t,
                                         const Taps<T> &tp, bool has_init, T init)
 {
-    const int F = tp.F;
+    const int F = WX_F;
     const long sc = 1L << (d + 1), ic = sw + 1;
     int i0 = (t & 1) ? 1 : 2;
     int i1 = F - i0 + 1;
@@ -125,7 +185,10 @@ __device__ __forceinline__ T isdwt_elem(const T *p1, long e1, const T *p2, long 
     T acc;
     if (has_init) acc = fma(tp.h[i2 - 1], p2[(k2 - 1) * e2], fma(tp.g[i1 - 1], p1[(k1 - 1) * e1], init));
     else          acc = fma(tp.g[i1 - 1], p1[(k1 - 1) * e1], tp.h[i2 - 1] * p2[(k2 - 1) * e2]);
-    for (int i = i0 + 2; i <= F; i += 2) {
+#pragma unroll
+    for (int ii = 1; ii < (F + 1) / 2; ++ii) {
+        const int i = i0 + 2 * ii;
+        if (i > F) break;
         i1 = F - i + 1;
         i2 = i + ((i & 1) ? 1 : -1);
         k1 -= sc; if (k1 <= 0) k1 = wx_wrapl(k1 - 1, n) + 1;
@@ -136,12 +199,12 @@ __device__ __forceinline__ T isdwt_elem(const T *p1, long e1, const T *p2, long 
 }
 
 // a10 isdwt_step! shift based: one thread per coset element
-template <typename T>
+template <typename T, int FF>
 __global__ void __launch_bounds__(kThreads) isdwt_shift_k(View<T> v, View<const T> w1, View<const T> w2, long n, int d, long sv, long sw,
-                                                           int add2out, long cnt, Batch b, Taps<T> tp)
+                                                           int add2out, Geo geo, Taps<T> tp)
 {
     long t0, b0, b1, b2;
-    if (!decomp((long)blockIdx.x * kThreads + threadIdx.x, cnt, b, t0, b0, b1, b2)) return;
+    if (!decomp(geo, t0, b0, b1, b2)) return;
     const T *p1 = w1.p + voff(w1, b0, b1, b2);
     const T *p2 = w2.p + voff(w2, b0, b1, b2);
     T *pv = v.p + voff(v, b0, b1, b2);
@@ -149,44 +212,57 @@ __global__ void __launch_bounds__(kThreads) isdwt_shift_k(View<T> v, View<const 
     long t = t0 + 1, m = sv + 1 + t0 * D;                              // 1-based
     long j = (sw == sv) ? wx_wrapl(m - D - 1, n) : wx_wrapl(m - 1, n); // 0-based write position
     T init = add2out ? pv[j * v.es] : (T)0;
-    pv[j * v.es] = isdwt_elem(p1, w1.es, p2, w2.es, n, d, sw, t, tp, add2out != 0, init);
+    pv[j * v.es] = isdwt_elem<T, FF>(p1, w1.es, p2, w2.es, n, d, sw, t, tp, add2out != 0, init);
 }
 
 // a10 isdwt_step! average based: one thread per output position (requires n % 2^(d+1) == 0)
-template <typename T>
-__global__ void __launch_bounds__(kThreads) isdwt_avg_k(View<T> v, View<const T> w1, View<const T> w2, long n, int d, Batch b, Taps<T> tp)
+template <typename T, int FF>
+__global__ void __launch_bounds__(kThreads) isdwt_avg_k(View<T> v, View<const T> w1, View<const T> w2, long n, int d, Geo geo, Taps<T> tp)
 {
     long pos, b0, b1, b2;
-    if (!decomp((long)blockIdx.x * kThreads + threadIdx.x, n, b, pos, b0, b1, b2)) return;
+    if (!decomp(geo, pos, b0, b1, b2)) return;
     const T *p1 = w1.p + voff(w1, b0, b1, b2);
     const T *p2 = w2.p + voff(w2, b0, b1, b2);
     const long D = 1L << d;
-    const long sv = pos % D;
+    const long sv = pos & (D - 1);
     long m1 = pos + 1 + D; if (m1 > n) m1 -= n;          // first call (sw = sv) writes position m-D
-    long t1 = (m1 - 1 - sv) / D + 1;
-    long t2 = (pos - sv) / D + 1;                        // second call (sw = sv+D) adds at position m
-    T a = isdwt_elem(p1, w1.es, p2, w2.es, n, d, sv, t1, tp, false, (T)0);
-    a = isdwt_elem(p1, w1.es, p2, w2.es, n, d, sv + D, t2, tp, true, a);
+    long t1 = ((m1 - 1 - sv) >> d) + 1;
+    long t2 = ((pos - sv) >> d) + 1;                     // second call (sw = sv+D) adds at position m
+    T a = isdwt_elem<T, FF>(p1, w1.es, p2, w2.es, n, d, sv, t1, tp, false, (T)0);
+    a = isdwt_elem<T, FF>(p1, w1.es, p2, w2.es, n, d, sv + D, t2, tp, true, a);
     v.p[voff(v, b0, b1, b2) + pos * v.es] = a / (T)2;
 }
 
 // a17 iacdwt_step! acwt/acwt_one_level.jl:221-223
 template <typename T>
-__global__ void __launch_bounds__(kThreads) iacdwt_step_k(View<T> v, View<const T> w1, View<const T> w2, long n, Batch b)
+__global__ void __launch_bounds__(kThreads) iacdwt_step_k(View<T> v, View<const T> w1, View<const T> w2, long n, Geo geo)
 {
     long i, b0, b1, b2;
-    if (!decomp((long)blockIdx.x * kThreads + threadIdx.x, n, b, i, b0, b1, b2)) return;
+    if (!decomp(geo, i, b0, b1, b2)) return;
     T a = w1.p[voff(w1, b0, b1, b2) + i * w1.es] + w2.p[voff(w2, b0, b1, b2) + i * w2.es];
     v.p[voff(v, b0, b1, b2) + i * v.es] = a / (T)1.4142135623730951;
 }
 
 template <typename T>
-__global__ void __launch_bounds__(kThreads) copy_k(View<T> dst, View<const T> src, long n, Batch b)
+__global__ void __launch_bounds__(kThreads) copy_k(View<T> dst, View<const T> src, long n, Geo geo)
 {
     long i, b0, b1, b2;
-    if (!decomp((long)blockIdx.x * kThreads + threadIdx.x, n, b, i, b0, b1, b2)) return;
+    if (!decomp(geo, i, b0, b1, b2)) return;
     dst.p[voff(dst, b0, b1, b2) + i * dst.es] = src.p[voff(src, b0, b1, b2) + i * src.es];
 }
+
+// instantiate KERNEL<..., FF> for the filter lengths of the shipped wavelets (orthogonal F and autocorrelation 2F-1), else FF = 0
+#define WX_DISPATCH_F(Fv, CALL)                                                                                           \
+    switch (Fv) {                                                                                                         \
+        case 2: { constexpr int FF = 2; CALL; } break;   case 3: { constexpr int FF = 3; CALL; } break;                   \
+        case 4: { constexpr int FF = 4; CALL; } break;   case 6: { constexpr int FF = 6; CALL; } break;                   \
+        case 7: { constexpr int FF = 7; CALL; } break;   case 8: { constexpr int FF = 8; CALL; } break;                   \
+        case 10: { constexpr int FF = 10; CALL; } break; case 11: { constexpr int FF = 11; CALL; } break;                 \
+        case 12: { constexpr int FF = 12; CALL; } break; case 15: { constexpr int FF = 15; CALL; } break;                 \
+        case 16: { constexpr int FF = 16; CALL; } break; case 23: { constexpr int FF = 23; CALL; } break;                 \
+        case 31: { constexpr int FF = 31; CALL; } break;                                                                  \
+        default: { constexpr int FF = 0; CALL; } break;                                                                   \
+    }
 
 static inline long btot(const Batch &b) { return b.B0 * b.B1 * b.B2; }
 
@@ -198,7 +274,8 @@ int wx_launch_dwt_step(View<T> w1, View<T> w2, View<const T> v, long n, Batch b,
     WX_REQUIRE(n >= 2 && n % 2 == 0, "dwt_step: parent length %ld must be even and >= 2", n);
     long total = (n / 2) * btot(b);
     if (total == 0) return WX_OK;
-    dwt_step_k<T><<<grid_for(total), kThreads, 0, s>>>(w1, w2, v, n, b, t);
+    const Geo geo = make_geo(n / 2, b);
+    WX_DISPATCH_F(t.F, (dwt_step_k<T, FF><<<grid_for(total), kThreads, 0, s>>>(w1, w2, v, n, geo, t)))
     WX_LAUNCHED();
     return WX_OK;
 }
@@ -209,7 +286,8 @@ int wx_launch_idwt_step(View<T> v, View<const T> w1, View<const T> w2, long n, B
     WX_REQUIRE(n >= 2 && n % 2 == 0, "idwt_step: parent length %ld must be even and >= 2", n);
     long total = n * btot(b);
     if (total == 0) return WX_OK;
-    idwt_step_k<T><<<grid_for(total), kThreads, 0, s>>>(v, w1, w2, n, b, t);
+    const Geo geo = make_geo(n, b);
+    WX_DISPATCH_F(t.F, (idwt_step_k<T, FF><<<grid_for(total), kThreads, 0, s>>>(v, w1, w2, n, geo, t)))
     WX_LAUNCHED();
     return WX_OK;
 }
@@ -220,8 +298,9 @@ int wx_launch_rdwt_step(int ac, View<T> w1, View<T> w2, View<const T> v, long n,
     WX_REQUIRE(n >= 1 && d >= 0 && d < 62, "rdwt_step: bad n=%ld or d=%d", n, d);
     long total = n * btot(b);
     if (total == 0) return WX_OK;
-    if (ac) rdwt_step_k<T, 1><<<grid_for(total), kThreads, 0, s>>>(w1, w2, v, n, 1L << d, b, t);
-    else    rdwt_step_k<T, 0><<<grid_for(total), kThreads, 0, s>>>(w1, w2, v, n, 1L << d, b, t);
+    const Geo geo = make_geo(n, b);
+    if (ac) { WX_DISPATCH_F(t.F, (rdwt_step_k<T, 1, FF><<<grid_for(total), kThreads, 0, s>>>(w1, w2, v, n, 1L << d, geo, t))) }
+    else    { WX_DISPATCH_F(t.F, (rdwt_step_k<T, 0, FF><<<grid_for(total), kThreads, 0, s>>>(w1, w2, v, n, 1L << d, geo, t))) }
     WX_LAUNCHED();
     return WX_OK;
 }
@@ -238,7 +317,8 @@ int wx_launch_isdwt_shift(View<T> v, View<const T> w1, View<const T> w2, long n,
     long cnt = (n - 1 - sv) / (1L << d) + 1;
     long total = cnt * btot(b);
     if (total <= 0) return WX_OK;
-    isdwt_shift_k<T><<<grid_for(total), kThreads, 0, s>>>(v, w1, w2, n, d, sv, sw, add2out, cnt, b, t);
+    const Geo geo = make_geo(cnt, b);
+    WX_DISPATCH_F(t.F, (isdwt_shift_k<T, FF><<<grid_for(total), kThreads, 0, s>>>(v, w1, w2, n, d, sv, sw, add2out, geo, t)))
     WX_LAUNCHED();
     return WX_OK;
 }
@@ -250,7 +330,8 @@ int wx_launch_isdwt_avg(View<T> v, View<const T> w1, View<const T> w2, long n, i
     WX_REQUIRE(n % (1L << (d + 1)) == 0, "isdwt_step: n=%ld must be a multiple of 2^(d+1)", n);
     long total = n * btot(b);
     if (total == 0) return WX_OK;
-    isdwt_avg_k<T><<<grid_for(total), kThreads, 0, s>>>(v, w1, w2, n, d, b, t);
+    const Geo geo = make_geo(n, b);
+    WX_DISPATCH_F(t.F, (isdwt_avg_k<T, FF><<<grid_for(total), kThreads, 0, s>>>(v, w1, w2, n, d, geo, t)))
     WX_LAUNCHED();
     return WX_OK;
 }
@@ -260,7 +341,7 @@ int wx_launch_iacdwt_step(View<T> v, View<const T> w1, View<const T> w2, long n,
 {
     long total = n * btot(b);
     if (total == 0) return WX_OK;
-    iacdwt_step_k<T><<<grid_for(total), kThreads, 0, s>>>(v, w1, w2, n, b);
+    iacdwt_step_k<T><<<grid_for(total), kThreads, 0, s>>>(v, w1, w2, n, make_geo(n, b));
     WX_LAUNCHED();
     return WX_OK;
 }
@@ -270,7 +351,7 @@ int wx_launch_copy(View<T> dst, View<const T> src, long n, Batch b, cudaStream_t
 {
     long total = n * btot(b);
     if (total == 0) return WX_OK;
-    copy_k<T><<<grid_for(total), kThreads, 0, s>>>(dst, src, n, b);
+    copy_k<T><<<grid_for(total), kThreads, 0, s>>>(dst, src, n, make_geo(n, b));
     WX_LAUNCHED();
     return WX_OK;
 }
