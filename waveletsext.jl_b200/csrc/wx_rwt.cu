@@ -15,6 +15,10 @@ template <typename T>
 int wx_rdwt1d_fused(int ac, T *xw, const T *x, long n, int L, long N, const Taps<T> &t, cudaStream_t s, int *done);
 template <typename T> int wx_iac_tree_sum(T *x, const T *xw, long n, long ncols, long c0, int L, long N, cudaStream_t s);
 template <typename T> int wx_iac_chain_sum(T *x, const T *xw, long n, int L, long N, cudaStream_t s);
+// fused average-based stationary inverses (wx_irwpd_fused.cu)
+template <typename T> int wx_irwpd_avg_fused(T *x, const T *xw, long in_sig, long in_col0, long n, int Lt, long N, const Taps<T> &t, cudaStream_t s, bool *handled);
+template <typename T> int wx_irdwt_chain_depth(const T *x, const T *xw, long n, int L, long N, const Taps<T> &t, int *dhi);
+template <typename T> int wx_irdwt_chain_run(T *x, const T *xw, long n, int L, int dhi, long N, const Taps<T> &t, cudaStream_t s);
 
 namespace {
 
@@ -213,15 +217,24 @@ int irwt_1d(int imode, int mode, T *x, const T *xw, long n, long ncols, int L, l
     if (imode == 2 && mode == WX_MODE_WPT && L < 32) return wx_iac_tree_sum<T>(x, xw, n, ncols, 0, L, N, s);
     if (mode == WX_MODE_DWT) {
         // isdwt! SWT.jl:270-282, 311-328 ; iacdwt! ACWT.jl:292-303 : x = col 0; for d = L-1..0: x = step(copy(x), col L-d)
+        int dhi = 0;                                         // levels d < dhi run in the fused chain kernel (average based only)
+        if (imode == 0) { rc = wx_irdwt_chain_depth<T>(x, xw, n, L, N, t, &dhi); if (rc) return rc; }
+        if (dhi == L) return wx_irdwt_chain_run<T>(x, xw, n, L, dhi, N, t, s);
         T *tmp; rc = wx_scratch(&tmp, (size_t)n * N, s); if (rc) return rc;
         rc = wx_launch_copy<T>(View<T>{x, 1, n, 0, 0}, View<const T>{xw, 1, str, 0, 0}, n, Batch{N, 1, 1, false}, s);
-        for (int d = L - 1; d >= 0 && !rc; --d) {
+        for (int d = L - 1; d >= dhi && !rc; --d) {
             WX_CUDA(cudaMemcpyAsync(tmp, x, (size_t)n * N * sizeof(T), cudaMemcpyDeviceToDevice, s));
             rc = istep1d<T>(imode, View<T>{x, 1, n, 0, 0}, View<const T>{tmp, 1, n, 0, 0}, View<const T>{xw + (long)(L - d) * n, 1, str, 0, 0}, n, d,
                             SV(d), SW(d), Batch{N, 1, 1, false}, t, s);
         }
+        if (!rc && dhi > 0) rc = wx_irdwt_chain_run<T>(x, xw, n, L, dhi, N, t, s);
         int rc2 = wx_scratch_free(tmp, s);
         return rc ? rc : rc2;
+    }
+    if (mode == WX_MODE_WPT && imode == 0) {
+        bool handled = false;
+        rc = wx_irwpd_avg_fused<T>(x, xw, str, 0, n, L, N, t, s, &handled);
+        if (rc || handled) return rc;
     }
     if (mode == WX_MODE_WPT) {
         // iswpt! SWT.jl:628-645, 700-715 ; iacwpt! ACWT.jl:594-607.  Depth-d nodes are kept compacted in a workspace
@@ -258,6 +271,16 @@ int irwt_1d(int imode, int mode, T *x, const T *xw, long n, long ncols, int L, l
         bool full = lastsplit == (1L << Lt) - 1 && Lt < 32 && (1L << (Lt + 1)) - 1 <= ncols;
         for (long i = 1; full && i <= lastsplit; ++i) full = tree[i - 1] != 0;
         if (full) return wx_iac_tree_sum<T>(x, xw, n, ncols, (1L << Lt) - 1, Lt, N, s);
+    }
+    if (imode == 0 && lastsplit > 0) {                       // average based + complete tree of depth Lt: fused tree reduction
+        const int Lt = wx_ilog2l(lastsplit) + 1;
+        bool full = lastsplit == (1L << Lt) - 1 && Lt < 31 && (1L << (Lt + 1)) - 1 <= ncols;
+        for (long i = 1; full && i <= lastsplit; ++i) full = tree[i - 1] != 0;
+        if (full) {
+            bool handled = false;
+            rc = wx_irwpd_avg_fused<T>(x, xw, str, (1L << Lt) - 1, n, Lt, N, t, s, &handled);
+            if (rc || handled) return rc;
+        }
     }
     if (lastsplit == 0) {                                    // root is a leaf: x = column 0
         return wx_launch_copy<T>(View<T>{x, 1, n, 0, 0}, View<const T>{xw, 1, str, 0, 0}, n, Batch{N, 1, 1, false}, s);
