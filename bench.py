@@ -223,7 +223,7 @@ def main():
     if not a.no_e2e:
         Ne = N
         per_sig = (L + 2) * n * esz
-        while Ne > 1024 and Ne * per_sig * world > 48e9:        # keep the pinned host footprint of all ranks under ~48 GB
+        while Ne > 1024 and Ne * per_sig * world > 96e9:        # keep the pinned host footprint of all ranks under ~96 GB
             Ne //= 2
         xh = yh = None
         while Ne >= 1024:
