@@ -47,12 +47,58 @@ def report(name, ms, launches, alg_bytes, units, unit_name, extra=None):
     print(json.dumps(out), flush=True)
 
 
+def cpu_rate(fn, units, budget_s=2.0):
+    """units per second of the CPU port: repeat fn() (which processes `units` samples / pixels) for about budget_s seconds"""
+    import time
+    fn()
+    t0 = time.perf_counter(); reps = 0
+    while True:
+        fn(); reps += 1
+        el = time.perf_counter() - t0
+        if el >= budget_s or reps >= 50:
+            break
+    return reps * units / el / 1e9
+
+
+def cpu_baselines():
+    """CPU port (oracle/, test infrastructure) timed on the host, one thread, bounded samples; one JSON line per path"""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as O
+    rng = np.random.default_rng(1)
+    q = wx.wavelet("db4").taps
+    g, h = O.makereverseqmfpair(q)
+    P, Q = O.make_acreverseqmfpair(q)
+    out = {}
+    x = rng.standard_normal((64, 4096))
+    out["wpdall_f64_db4"] = (cpu_rate(lambda: O.wpdall(x, q, 12, 1), x.size), "GSamples_per_s", "64 signals x 4096, L=12")
+    leaves = O.wpdall(x, q, 12, 1)[:, 12].copy()
+    tree = O.maketree1(4096, 12, "full")
+    out["iwptall_f64_db4"] = (cpu_rate(lambda: O.iwptall(leaves, q, tree, 1), x.size), "GSamples_per_s", "64 signals x 4096, full tree")
+    xs = rng.standard_normal((16, 2048))
+    out["swpdall_f64"] = (cpu_rate(lambda: O.rwpdall(0, xs, 8, h, g, 1), xs.size), "GSamples_per_s", "16 signals x 2048, L=8")
+    out["acwpdall_f64"] = (cpu_rate(lambda: O.rwpdall(1, xs, 8, Q, P, 1), xs.size), "GSamples_per_s", "16 signals x 2048, L=8")
+    img = rng.standard_normal((4, 512, 512))
+    out["wpd2d_f64_db4"] = (cpu_rate(lambda: O.wpdall(img, q, 5, 1), img.size), "GPixels_per_s", "4 images 512 x 512, L=5")
+    Xw = O.wpdall(rng.standard_normal((2048, 1024)), q, 10, 1)
+    out["jbb_tree_costs_f64"] = (cpu_rate(lambda: O.tree_costs_jbb(Xw), 2048 * 1024), "GSamples_per_s", "2048 signals x 1024 x 11 levels")
+    out["lsdb_tree_costs_f64"] = (cpu_rate(lambda: O.tree_costs_lsdb(Xw), 2048 * 1024), "GSamples_per_s", "2048 signals x 1024 x 11 levels")
+    for k, (v, unit, sample) in out.items():
+        print(json.dumps({"path": k, "cpu_port_1thread": {unit: round(v, 5), "sample": sample, "kind": "port (C restatement of the reference loops, "
+                                                                                                    "Julia unavailable)"}}), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default="")
     ap.add_argument("--scale", type=float, default=1.0, help="scale the batch sizes (1.0 = the per-GPU sizes of BASELINE.json)")
+    ap.add_argument("--cpu", action="store_true", help="also time the CPU port of the reference loops (oracle, 1 thread like the "
+                    "single-threaded reference) on a bounded sample of each workload")
     a = ap.parse_args()
     only = set(filter(None, a.only.split(",")))
+    if a.cpu:
+        cpu_baselines()
+        if a.only == "cpu":
+            return
     dev = torch.device("cuda:0")
     gen = torch.Generator(device=dev).manual_seed(7)
     want = lambda nm: (not only) or nm in only
@@ -159,7 +205,7 @@ def main():
             torch.cuda.empty_cache()
     # config 5: JBB / LSDB best basis + getbasiscoefall + iwptall on 131072 signals x 1024 per GPU (1M over 8 GPUs)
     n, N, L = 1024, int(131072 * a.scale), 10
-    if want("jbb") or want("lsdb") or want("basis_iwpt"):
+    if want("jbb") or want("lsdb") or want("basis_iwpt") or want("bb"):
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         wt = wx.wavelet("db4")
         t = torch.arange(n, device=dev, dtype=torch.float64) / n
@@ -177,6 +223,13 @@ def main():
         if want("lsdb"):
             ms, nl = timeit(lambda: wx.tree_costs(Xw, wx.LSDB()), steps=2, warmup=1)
             report("lsdb_tree_costs_f64", ms, nl, 3 * 8 * n * K * N, n * N, "GSamples_per_s")
+        if want("bb"):
+            ms, nl = timeit(lambda: wx.bestbasistreeall(Xw, wx.BB()), steps=3, warmup=1)
+            report("bestbasistreeall_bb_f64", ms, nl, 8 * n * K * N, n * N, "GSamples_per_s")
+            trees = wx.bestbasistreeall(Xw, wx.BB())
+            ms, nl = timeit(lambda: wx.getbasiscoefall(Xw, trees), steps=3, warmup=1)
+            report("getbasiscoefall_per_signal_trees_f64", ms, nl, 2 * 8 * n * N, n * N, "GSamples_per_s", {"mean_tree_nodes": float(trees.sum()) / N})
+            del trees
         if want("basis_iwpt"):
             if tree is None:
                 tree = wx.bestbasistree(Xw, wx.JBB())

@@ -161,6 +161,16 @@ int wx_lsdb_pass2_f32(double *counts, const double *stats, const float *X, long 
 int wx_lsdb_pass3_f64(double *logsum, const double *counts, const double *stats, const double *X, long szK, long Nlocal, long Ntotal, void *stream);
 int wx_lsdb_pass3_f32(double *logsum, const double *counts, const double *stats, const float *X, long szK, long Nlocal, long Ntotal, void *stream);
 int wx_lsdb_costs(double *costs_host, const double *logsum, long Ntotal, long m, long n, int K, int redundant, void *stream);
+/* tree_costs(X, ::BB)  bestbasis/bestbasis_tree.jl:210-256 + coefcost(::ShannonEntropyCost | ::LogEnergyEntropyCost)
+ * bestbasis/bestbasis_costs.jl:103-125, for every signal of a batch (bestbasistreeall BestBasis.jl:253-262):
+ * X(sz,K,N) -> costs(nnodes, N) device Float64 (nnodes as for JBB).  cost_kind 0 = Shannon, 1 = log energy.
+ * wx_bb_select: bestbasis_treeselection (:min) for the N cost vectors at once, trees(ntree, N) bytes on the DEVICE, costs updated
+ * in place.  wx_gather_basis_multi: getbasiscoefall with one tree per signal (Utils.jl:199-225), trees on the device. */
+int wx_bb_costs_f64(double *costs_dev, const double *X, long m, long n, int K, long N, int redundant, int cost_kind, void *stream);
+int wx_bb_costs_f32(double *costs_dev, const float *X, long m, long n, int K, long N, int redundant, int cost_kind, void *stream);
+int wx_bb_select(unsigned char *trees_dev, double *costs_dev, long nnodes, long m, long n, long N, int elt, void *stream);
+int wx_gather_basis_multi_f64(double *out, const double *Xw, long m, long n, int K, long N, const unsigned char *trees_dev, long ntree, void *stream);
+int wx_gather_basis_multi_f32(float *out, const float *Xw, long m, long n, int K, long N, const unsigned char *trees_dev, long ntree, void *stream);
 /* bestbasis_treeselection  BestBasis.jl:59-110 (host, O(n)); costs are modified in place like the reference.
  * m = 0: binary tree with n-1 entries; m > 0: quad tree. minmax 0 = :min, 1 = :max */
 int wx_tree_select(unsigned char *tree_out, double *costs_host, long ncosts, long m, long n, int minmax);

@@ -477,6 +477,21 @@ def tree_costs_lsdb(X, redundant=False):
     return costs
 
 
+def tree_costs_bb(X, redundant=False, cost="shannon"):
+    """tree_costs(X, ::BB) for ONE signal: X (K, n) or (K, n, m) -> costs (T)"""
+    X = np.ascontiguousarray(X)
+    kind = 0 if cost == "shannon" else 1
+    if X.ndim == 2:
+        K, n = X.shape
+        costs = np.empty(K if redundant else (1 << K) - 1, X.dtype)
+        _call(f"wxo_tree_costs_bb1_{_sfx(X.dtype)}", "PPllii", costs, X, n, K, int(redundant), kind)
+    else:
+        K, n, m = X.shape
+        costs = np.empty(K if redundant else (4 ** K - 1) // 3, X.dtype)
+        _call(f"wxo_tree_costs_bb2_{_sfx(X.dtype)}", "PPlllii", costs, X, m, n, K, int(redundant), kind)
+    return costs
+
+
 def diffentropy(x):
     x = np.ascontiguousarray(x)
     return _call(f"wxo_diffentropy_{_sfx(x.dtype)}", "Pll", x, 1, len(x), restype=C.c_double)

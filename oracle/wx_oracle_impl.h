@@ -911,6 +911,74 @@ WXO_API void SUF(tree_costs_lsdb2)(T *costs, const T *X, long nr, long nc, long 
     }
 }
 
+/* f-1 coefcost(x, ::ShannonEntropyCost / ::LogEnergyEntropyCost, nrm)  bestbasis/bestbasis_costs.jl:103-125
+ * kind 0: s = (x/nrm)^2, -s*log(s) (0 when s == 0); kind 1: -log(s) (0 when s == 0); nrm == 0 -> 0.  Summed in index
+ * order in the element type.  PARITY UNPINNED by the reference's tests (test/bestbasis.jl:13-21 only check isvalidtree);
+ * the arithmetic is fully visible in the reference and restated 1:1. */
+static T SUF(coefcost_bb)(const T *x, long r0, long c0, long rr, long cc, long ld, int kind, T nrm)
+{
+    T sum = (T)0;
+    if (nrm == sum) return sum;
+    for (long c = 0; c < cc; ++c)
+        for (long r = 0; r < rr; ++r) {
+            T q = x[(c0 + c) * ld + r0 + r] / nrm;
+            T s = q * q;
+            T v = (s == (T)0) ? (T)(-0.0) : (kind == 0 ? (T)(-s * (T)log((double)s)) : (T)(-(T)log((double)s)));
+            sum += v;
+        }
+    return sum;
+}
+static T SUF(norm2)(const T *x, long n)
+{
+    double a = 0.0;
+    for (long i = 0; i < n; ++i) a += (double)x[i] * (double)x[i];
+    return (T)sqrt(a);
+}
+
+/* f-1 tree_costs(X, ::BB) 1-D  bestbasis/bestbasis_tree.jl:210-233 ; X (n, K) one signal */
+WXO_API void SUF(tree_costs_bb1)(T *costs, const T *X, long n, long K, int redundant, int kind)
+{
+    T nrm = SUF(norm2)(X, n);                         /* norm(X[:,1]) */
+    if (redundant) {
+        for (long i = 1; i <= K; ++i) {
+            int j = wx_ilog2(i);
+            costs[i - 1] = (T)(SUF(coefcost_bb)(X + (i - 1) * n, 0, 0, n, 1, n, kind, nrm) / (T)(1L << j));
+        }
+    } else {
+        long i = 0;
+        for (long d = 0; d < K; ++d) {
+            long n0 = n >> d;
+            for (long node = 0; node < (1L << d); ++node)
+                costs[i++] = SUF(coefcost_bb)(X + d * n, node * n0, 0, n0, 1, n, kind, nrm);
+        }
+    }
+}
+
+/* f-1 tree_costs(X, ::BB) 2-D  bestbasis/bestbasis_tree.jl:234-256 ; X (nr, nc, K) one image.  The non-redundant branch
+ * calls coefcost WITHOUT nrm (:252), i.e. each node is normalised by its own norm -- restated as written. */
+WXO_API void SUF(tree_costs_bb2)(T *costs, const T *X, long nr, long nc, long K, int redundant, int kind)
+{
+    long sz = nr * nc;
+    T nrm = SUF(norm2)(X, sz);                        /* norm(X[:,:,1]) */
+    if (redundant) {
+        for (long i = 1; i <= K; ++i) {
+            int d = wx_quaddepth(i);
+            costs[i - 1] = (T)(SUF(coefcost_bb)(X + (i - 1) * sz, 0, 0, nr, nc, nr, kind, nrm) / (T)(1L << (2 * d)));
+        }
+    } else {
+        long ncost = ((1L << (2 * K)) - 1) / 3;
+        for (long i = 1; i <= ncost; ++i) {
+            int d = wx_quaddepth(i);
+            long r0, c0, rr, cc;
+            wx_quadrange(nr, nc, i, &r0, &c0, &rr, &cc);
+            double a = 0.0;
+            for (long c = 0; c < cc; ++c)
+                for (long r = 0; r < rr; ++r) { double v = (double)X[(long)d * sz + (c0 + c) * nr + r0 + r]; a += v * v; }
+            costs[i - 1] = SUF(coefcost_bb)(X + (long)d * sz, r0, c0, rr, cc, nr, kind, (T)sqrt(a));
+        }
+    }
+}
+
 /* a22 bestbasis_treeselection 1-D BestBasis.jl:59-83 (+ delete_subtree! :128-140).
  * costs (ncost) is modified in place like the reference; tree gets n-1 entries. minmax: 0 = :min, 1 = :max */
 WXO_API void SUF(tree_select1)(unsigned char *tree, T *costs, long ncost, long n, int minmax)

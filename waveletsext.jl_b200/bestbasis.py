@@ -18,8 +18,8 @@ from . import _lib
 from . import dist
 from .utils import gettreelength
 
-__all__ = ["LoglpCost", "NormCost", "DifferentialEntropyCost", "JBB", "LSDB", "tree_costs", "bestbasis_treeselection",
-           "bestbasistree", "delete_subtree_"]
+__all__ = ["LoglpCost", "NormCost", "DifferentialEntropyCost", "ShannonEntropyCost", "LogEnergyEntropyCost", "JBB", "LSDB", "BB",
+           "tree_costs", "bestbasis_treeselection", "bestbasistree", "bestbasistreeall", "delete_subtree_"]
 
 
 @dataclass(frozen=True)
@@ -37,6 +37,23 @@ class NormCost:
 @dataclass(frozen=True)
 class DifferentialEntropyCost:
     """bestbasis/bestbasis_costs.jl:66"""
+
+
+@dataclass(frozen=True)
+class ShannonEntropyCost:
+    """bestbasis/bestbasis_costs.jl:75"""
+
+
+@dataclass(frozen=True)
+class LogEnergyEntropyCost:
+    """bestbasis/bestbasis_costs.jl:85"""
+
+
+@dataclass(frozen=True)
+class BB:
+    """bestbasis/bestbasis_tree.jl:61-64 : standard (per-signal) best basis"""
+    cost: object = field(default_factory=ShannonEntropyCost)
+    redundant: bool = False
 
 
 @dataclass(frozen=True)
@@ -84,10 +101,49 @@ def _dd_allreduce(pair, group, st):
     return pair
 
 
-def tree_costs(X, method, group=None):
-    """``tree_costs(X, method)`` bestbasis/bestbasis_tree.jl:104-207.  X is the LOCAL shard (N_local, K, ...) of the
-    packet table; with an initialised process group the costs are those of the concatenated batch."""
+def _bb_kind(method):
+    if isinstance(method.cost, ShannonEntropyCost):
+        return 0
+    if isinstance(method.cost, LogEnergyEntropyCost):
+        return 1
+    raise TypeError("BB cost must be ShannonEntropyCost or LogEnergyEntropyCost")
+
+
+def _bb_costs_batch(X, method):
+    """X (N, K, ...) -> device costs (N, nnodes) Float64: tree_costs(Xi, ::BB) of every signal (bestbasis_tree.jl:210-256)"""
+    m, n, K, N, _ = _geom(X)
+    costs = torch.empty((N, _ncosts(m, K, method.redundant)), dtype=torch.float64, device=X.device)
+    D.call("bb_costs", X, D.ptr(costs), D.ptr(X), m, n, K, N, int(method.redundant), _bb_kind(method), D.stream(X))
+    return costs, m, n
+
+
+def bestbasistreeall(X, method=None):
+    """``bestbasistreeall(X, ::BB)`` BestBasis.jl:253-262: one best-basis tree per signal.  X (N, K, n[, m]) on the device ->
+    boolean device tensor (N, ntree) (the reference's BitMatrix (ntree, k) in this package's reversed-axes convention).
+    Costs and the bottom-up selection both run on the GPU; nothing depends on other signals, so shards need no exchange."""
+    method = BB() if method is None else method
+    assert isinstance(method, BB), "bestbasistreeall: method must be BB()"
     X = D.dev(X, "X")
+    assert 3 <= X.dim() <= 4, "AssertionError: 3 <= ndims(X) <= 4"
+    costs, m, n = _bb_costs_batch(X, method)
+    N, nn = costs.shape
+    ntree = gettreelength(m, n) if m > 0 else n - 1
+    trees = torch.zeros((N, max(ntree, 0)), dtype=torch.uint8, device=X.device)
+    with torch.cuda.device(X.device):
+        _lib.call("wx_bb_select", D.ptr(trees), D.ptr(costs), nn, m, n, N, X.element_size(), D.stream(X))
+    return trees.bool()
+
+
+def tree_costs(X, method, group=None):
+    """``tree_costs(X, method)`` bestbasis/bestbasis_tree.jl:104-256.  JBB / LSDB: X is the LOCAL shard (N_local, K, ...) of the
+    packet table; with an initialised process group the costs are those of the concatenated batch.  BB: X is ONE decomposed
+    signal (K, n[, m]) like in the reference."""
+    X = D.dev(X, "X")
+    if isinstance(method, BB):
+        assert 2 <= X.dim() <= 3, "AssertionError: 2 <= ndims(X) <= 3"
+        costs, _, _ = _bb_costs_batch(X.unsqueeze(0), method)
+        c = costs[0].cpu().numpy()
+        return c.astype(np.float32).astype(np.float64) if X.dtype == torch.float32 else c
     m, n, K, Nloc, szK = _geom(X)
     Ntot = dist.total_count(Nloc, X.device, group)
     elt = X.element_size()
@@ -169,6 +225,9 @@ def bestbasistree(X, method=None, group=None):
     """``bestbasistree(X, method)`` BestBasis.jl:185-217 for JBB / LSDB.  X: local shard (N_local, K, ...)."""
     method = JBB() if method is None else method
     X = D.dev(X, "X")
+    if isinstance(method, BB):                       # one signal (K, n[, m])   BestBasis.jl:206-213
+        assert 2 <= X.dim() <= 3, "AssertionError: 2 <= ndims(X) <= 3"
+        return bestbasistreeall(X.unsqueeze(0), method)[0].cpu().numpy()
     costs = tree_costs(X, method, group)
     if X.dim() == 3:
         return bestbasis_treeselection(costs, X.shape[2])

@@ -638,6 +638,181 @@ __global__ void __launch_bounds__(kT) scale_k(double *out, const double *in, lon
     if (e < n) out[e] = in[e] * f;
 }
 
+// ---- BB: per-signal best basis (bestbasis/bestbasis_tree.jl:210-256, bestbasis/bestbasis_costs.jl:103-125) ----------------
+// coefcost(x, ::ShannonEntropyCost | ::LogEnergyEntropyCost, nrm): s = (x/nrm)^2 ; -s log s | -log s ; 0 when s == 0
+__device__ __forceinline__ double bb_term(double x, double inv_nrm, int kind)
+{
+    const double q = x * inv_nrm, s = q * q;
+    if (s == 0.0) return 0.0;
+    return kind == 0 ? -s * log(s) : -log(s);
+}
+
+// sum over the G = blockDim-aligned power-of-two group of lanes that share a node (G <= 32: segmented xor shuffles;
+// G > 32: whole warps, combined through shared memory by the caller)
+__device__ __forceinline__ double group_sum(double v, int G)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) if (o < G) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// 1-D tables, one CTA per signal.  Level l of a non-redundant table (n, K) has 2^l nodes of n >> l coefficients; a redundant
+// table (n, K nodes) has one node of n coefficients per column, cost divided by 2^depth (:218-222).  Threads split each node
+// in G = max(1, 256 >> l) strided parts (coalesced loads), partial sums meet through shuffles / shared memory.
+template <typename T>
+__global__ void __launch_bounds__(kT) bb_costs_1d_k(double *costs, const T *X, long n, int K, long nn, int redundant, int kind)
+{
+    __shared__ double wsum[kT / 32];
+    __shared__ double s_inv;
+    const long k = blockIdx.x;
+    const T *Xk = X + k * n * K;
+    double *ck = costs + k * nn;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // nrm = norm(X[:,1])
+    double a = 0.0;
+    for (long e = tid; e < n; e += kT) { const double v = (double)Xk[e]; a = fma(v, v, a); }
+    a = group_sum(a, 32);
+    if (lane == 0) wsum[warp] = a;
+    __syncthreads();
+    if (tid == 0) {
+        double t = 0.0;
+        for (int w = 0; w < kT / 32; ++w) t += wsum[w];
+        double nrm = sqrt(t);
+        if (sizeof(T) == 4) nrm = (double)(float)nrm;
+        s_inv = nrm > 0.0 ? 1.0 / nrm : 0.0;                 // nrm == 0: every cost is 0 (bestbasis_costs.jl:119)
+    }
+    __syncthreads();
+    const double inv = s_inv;
+    for (int l = 0; l < K; ++l) {
+        const long nodes = redundant ? 1 : (1L << l), p = redundant ? n : (n >> l);
+        const T *lev = Xk + (long)l * n;
+        int lg = 0; while ((1L << lg) < nodes) ++lg;
+        const int G = (lg >= 8) ? 1 : (kT >> lg);             // threads per node
+        const double scale = redundant ? 1.0 / (double)(1L << ilog2d(l + 1)) : 1.0;
+        for (long j0 = 0; j0 < nodes; j0 += kT / G) {          // kT / G nodes per sweep
+            const long j = j0 + tid / G;
+            const int sub = tid % G;
+            double acc = 0.0;
+            if (j < nodes) {
+                const T *nd = lev + j * p;
+                for (long e = sub; e < p; e += G) acc += bb_term((double)nd[e], inv, kind);
+            }
+            if (G <= 32) {
+                acc = group_sum(acc, G);
+                if (sub == 0 && j < nodes) ck[redundant ? l : ((1L << l) - 1 + j)] = acc * scale;
+            } else {
+                acc = group_sum(acc, 32);
+                __syncthreads();
+                if (lane == 0) wsum[warp] = acc;
+                __syncthreads();
+                if (sub == 0 && j < nodes) {
+                    double t = 0.0;
+                    for (int w = 0; w < G / 32; ++w) t += wsum[warp + w];
+                    ck[redundant ? l : ((1L << l) - 1 + j)] = t * scale;
+                }
+            }
+        }
+    }
+}
+
+// any geometry (2-D quad trees, redundant 2-D): one warp per (signal, node) through node_elem.  pernode: the 2-D non-redundant
+// branch of the reference normalises every node by its own norm (bestbasis_tree.jl:252 passes no nrm) -- kept as written.
+template <typename T>
+__global__ void __launch_bounds__(kT) bb_costs_generic_k(double *costs, const T *X, NodeGeom g, long nn, long N, long szK, long sz0, int kind, int pernode)
+{
+    const long w = ((long)blockIdx.x * kT + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= nn * N) return;
+    const long k = w / nn, q = w - k * nn;
+    const T *Xk = X + k * szK;
+    long cnt; double scale;
+    node_elem(g, q, 0, cnt, scale);
+    double a = 0.0;
+    if (pernode) { for (long t = lane; t < cnt; t += 32) { long c2; double s2; const double v = (double)Xk[node_elem(g, q, t, c2, s2)]; a = fma(v, v, a); } }
+    else { for (long e = lane; e < sz0; e += 32) { const double v = (double)Xk[e]; a = fma(v, v, a); } }
+    a = group_sum(a, 32);
+    double nrm = sqrt(a);
+    if (sizeof(T) == 4) nrm = (double)(float)nrm;
+    const double inv = nrm > 0.0 ? 1.0 / nrm : 0.0;
+    double acc = 0.0;
+    for (long t = lane; t < cnt; t += 32) { long c2; double s2; acc += bb_term((double)Xk[node_elem(g, q, t, c2, s2)], inv, kind); }
+    acc = group_sum(acc, 32);
+    if (lane == 0) costs[k * nn + q] = acc * scale;
+}
+
+// bestbasis_treeselection (BestBasis.jl:59-110) for N signals at once, one warp per signal.  Bottom-up: a node keeps its split
+// iff the (already updated) children cost less; top-down: a node survives iff all its ancestors kept theirs -- the same tree
+// as the reference's delete_subtree! cascade.  costs (N, nn) are updated in place like the reference's.
+__global__ void __launch_bounds__(kT) bb_select_k(unsigned char *trees, double *costs, long nn, long ntree, int L, int ar, long N, int elt)
+{
+    const long k = ((long)blockIdx.x * kT + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (k >= N) return;
+    double *c = costs + k * nn;
+    unsigned char *t = trees + k * ntree;
+    for (long i = lane; i < ntree; i += 32) t[i] = 0;
+    __syncwarp();
+    for (int l = L - 1; l >= 0; --l) {
+        const long first = ar == 2 ? (1L << l) : ((1L << (2 * l)) - 1) / 3 + 1, cntl = ar == 2 ? (1L << l) : (1L << (2 * l));
+        for (long j = lane; j < cntl; j += 32) {
+            const long i = first + j;                                 // 1-based node
+            if (i > ntree) continue;
+            const long c0 = ar == 2 ? 2 * i : 4 * i - 2;
+            double cc = c[c0 - 1] + c[c0];
+            if (elt == 4) cc = (double)(float)cc;
+            if (ar == 4) { cc += c[c0 + 1]; if (elt == 4) cc = (double)(float)cc; cc += c[c0 + 2]; if (elt == 4) cc = (double)(float)cc; }
+            if (cc < c[i - 1]) { c[i - 1] = cc; t[i - 1] = 1; }
+        }
+        __syncwarp();
+    }
+    for (int l = 1; l < L; ++l) {
+        const long first = ar == 2 ? (1L << l) : ((1L << (2 * l)) - 1) / 3 + 1, cntl = ar == 2 ? (1L << l) : (1L << (2 * l));
+        for (long j = lane; j < cntl; j += 32) {
+            const long i = first + j;
+            if (i > ntree) continue;
+            const long par = ar == 2 ? (i >> 1) : ((i + 2) >> 2);
+            if (!t[par - 1]) t[i - 1] = 0;
+        }
+        __syncwarp();
+    }
+}
+
+// getbasiscoefall with one tree per signal (Utils.jl:199-225): walk the signal's tree from the root to the leaf that covers
+// the position and read that level.  trees (N, ntree) bytes on the device.
+template <typename T>
+__global__ void __launch_bounds__(kT) gather_multi_k(T *out, const T *Xw, long m, long n, int K, long N, const unsigned char *trees, long ntree)
+{
+    const long sz = (m > 0 ? m : 1) * n;
+    const long gid = (long)blockIdx.x * kT + threadIdx.x;
+    if (gid >= sz * N) return;
+    const long k = gid / sz, e = gid - k * sz;
+    const unsigned char *t = trees + k * ntree;
+    int d = 0;
+    if (m == 0) {
+        const int lgn = ilog2d(n);                                    // n is a power-of-two multiple at every split level
+        long idx = 1;
+        while (idx <= ntree && t[idx - 1] && d < K - 1) {
+            const long p = n >> (d + 1);                                  // child length
+            const long j = idx - (1L << d);                               // node index within the depth
+            idx = 2 * idx + ((e - j * 2 * p) >= p ? 1 : 0);
+            ++d;
+        }
+        (void)lgn;
+    } else {
+        const long r = e % m, c = e / m;
+        long idx = 1, r0 = 0, c0 = 0, nr = m, nc = n;
+        while (idx <= ntree && t[idx - 1] && d < K - 1) {
+            nr >>= 1; nc >>= 1;
+            const int rb = (r - r0) >= nr, cb = (c - c0) >= nc;
+            if (rb) r0 += nr;
+            if (cb) c0 += nc;
+            idx = 4 * idx - 2 + 2 * rb + cb;
+            ++d;
+        }
+    }
+    out[gid] = Xw[(k * K + d) * sz + e];
+}
+
 }  // namespace
 
 extern "C" {
@@ -766,4 +941,69 @@ int wx_tree_select(unsigned char *tree_out, double *costs, long ncosts, long m, 
     return WX_OK;
 }
 
+
 }  // extern "C"
+
+// tree_costs(X, ::BB) for every signal of a batch: X (sz, K, N) -> costs (nnodes, N) [device, Float64], nnodes as for JBB.
+template <typename T>
+static int bb_costs_impl(double *costs, const T *X, long m, long n, int K, long N, int redundant, int kind, cudaStream_t s)
+{
+    WX_REQUIRE(costs && n >= 1 && m >= 0 && K >= 1 && N >= 0 && (N == 0 || X), "bad arguments");
+    WX_REQUIRE(kind == 0 || kind == 1, "unknown BB cost kind %d", kind);
+    if (!redundant) WX_REQUIRE(m > 0 ? 2 * K < 62 : K < 62, "too many levels");
+    if (N == 0) return WX_OK;
+    const long nn = count_nodes(m, K, redundant);
+    if (m == 0) {
+        WX_REQUIRE(N < (1L << 31), "too many signals for one launch");
+        bb_costs_1d_k<T><<<(unsigned)N, kT, 0, s>>>(costs, X, n, K, nn, redundant, kind);
+    } else {
+        NodeGeom g{m, n, K, redundant};
+        const long sz = m * n;
+        bb_costs_generic_k<T><<<gridf(nn * N * 32), kT, 0, s>>>(costs, X, g, nn, N, sz * K, sz, kind, redundant ? 0 : 1);
+    }
+    WX_LAUNCHED();
+    return WX_OK;
+}
+extern "C" {
+
+int wx_bb_costs_f64(double *costs, const double *X, long m, long n, int K, long N, int redundant, int kind, void *s) { return bb_costs_impl<double>(costs, X, m, n, K, N, redundant, kind, (cudaStream_t)s); }
+int wx_bb_costs_f32(double *costs, const float *X, long m, long n, int K, long N, int redundant, int kind, void *s) { return bb_costs_impl<float>(costs, X, m, n, K, N, redundant, kind, (cudaStream_t)s); }
+
+// bestbasis_treeselection for N cost vectors at once: trees (ntree, N) bytes on the device, costs (nnodes, N) updated in place
+int wx_bb_select(unsigned char *trees, double *costs, long nnodes, long m, long n, long N, int elt, void *stream)
+{
+    WX_REQUIRE(trees && costs && nnodes >= 1 && n >= 1 && m >= 0 && N >= 0, "bad arguments");
+    WX_REQUIRE(elt == 4 || elt == 8, "elt must be 4 or 8");
+    if (N == 0) return WX_OK;
+    const int ar = m > 0 ? 4 : 2;
+    long ntree; int L;
+    if (m > 0) {
+        const int Lm = wx_maxlevels(m < n ? m : n);
+        ntree = ((1L << (2 * Lm)) - 1) / 3;
+        WX_REQUIRE(nnodes <= ((1L << (2 * (Lm + 1))) - 1) / 3, "AssertionError: k <= gettreelength(2n,2m)");
+        L = wx_quaddepthl(nnodes);
+    } else {
+        ntree = n - 1;
+        WX_REQUIRE(nnodes <= (1L << (wx_maxlevels(2 * n))) - 1, "AssertionError: k <= gettreelength(2n)");
+        L = wx_ilog2l(nnodes);
+    }
+    if (ntree <= 0) return WX_OK;
+    bb_select_k<<<gridf(N * 32), kT, 0, (cudaStream_t)stream>>>(trees, costs, nnodes, ntree, L, ar, N, elt);
+    WX_LAUNCHED();
+    return WX_OK;
+}
+
+}  // extern "C"
+
+// per-signal-tree gather (wx_trees.cu exports the C entry points)
+template <typename T>
+int wx_gather_multi(T *out, const T *Xw, long m, long n, int K, long N, const unsigned char *trees, long ntree, cudaStream_t s)
+{
+    const long sz = (m > 0 ? m : 1) * n;
+    if (sz * N == 0) return WX_OK;
+    gather_multi_k<T><<<gridf(sz * N), kT, 0, s>>>(out, Xw, m, n, K, N, trees, ntree);
+    WX_LAUNCHED();
+    return WX_OK;
+}
+template int wx_gather_multi<double>(double *, const double *, long, long, int, long, const unsigned char *, long, cudaStream_t);
+template int wx_gather_multi<float>(float *, const float *, long, long, int, long, const unsigned char *, long, cudaStream_t);

@@ -18,6 +18,9 @@ int wx_tree1d_fused(bool inverse, bool full, T *y, const T *x, long n, long N, i
 // fused 2-D packet decomposition (wx_wpd2d.cu)
 template <typename T> int wx_wpd2d_fused(T *y, const T *x, long m, long n, int L, long N, const Taps<T> &t, cudaStream_t s, bool *handled);
 
+template <typename T>
+int wx_gather_multi(T *out, const T *Xw, long m, long n, int K, long N, const unsigned char *trees, long ntree, cudaStream_t s);
+
 namespace {
 
 constexpr int kT = 256;
@@ -471,6 +474,16 @@ int wx_iwpt2d_f64(double *y, const double *xw, long m, long n, long N, const uns
 int wx_iwpt2d_f32(float *y, const float *xw, long m, long n, long N, const unsigned char *tree, long ntree, const double *h, const double *g, int F, void *s) { return tree2d<float>(true, y, xw, m, n, N, tree, ntree, h, g, F, s); }
 int wx_gather_basis_f64(double *out, const double *Xw, long m, long n, int K, long N, const unsigned char *tree, long ntree, void *s) { return gather_impl<double>(out, Xw, m, n, K, N, tree, ntree, s); }
 int wx_gather_basis_f32(float *out, const float *Xw, long m, long n, int K, long N, const unsigned char *tree, long ntree, void *s) { return gather_impl<float>(out, Xw, m, n, K, N, tree, ntree, s); }
+int wx_gather_basis_multi_f64(double *out, const double *Xw, long m, long n, int K, long N, const unsigned char *trees_dev, long ntree, void *s)
+{
+    WX_REQUIRE(out && Xw && trees_dev && n >= 1 && m >= 0 && K >= 1 && N >= 0 && ntree >= 0, "getbasiscoefall: bad arguments");
+    return wx_gather_multi<double>(out, Xw, m, n, K, N, trees_dev, ntree, (cudaStream_t)s);
+}
+int wx_gather_basis_multi_f32(float *out, const float *Xw, long m, long n, int K, long N, const unsigned char *trees_dev, long ntree, void *s)
+{
+    WX_REQUIRE(out && Xw && trees_dev && n >= 1 && m >= 0 && K >= 1 && N >= 0 && ntree >= 0, "getbasiscoefall: bad arguments");
+    return wx_gather_multi<float>(out, Xw, m, n, K, N, trees_dev, ntree, (cudaStream_t)s);
+}
 int wx_iwpd_f64(double *x, const double *Xw, long m, long n, int K, long N, const unsigned char *tree, long ntree, const double *h, const double *g, int F, void *s) { return iwpd_impl<double>(x, Xw, m, n, K, N, tree, ntree, h, g, F, s); }
 int wx_iwpd_f32(float *x, const float *Xw, long m, long n, int K, long N, const unsigned char *tree, long ntree, const double *h, const double *g, int F, void *s) { return iwpd_impl<float>(x, Xw, m, n, K, N, tree, ntree, h, g, F, s); }
 int wx_wpt1d_f64(double *y, const double *x, long n, long N, const unsigned char *tree, long ntree, const double *h, const double *g, int F, void *s) { return tree1d<double>(false, y, x, n, N, tree, ntree, h, g, F, s); }

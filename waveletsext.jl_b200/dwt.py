@@ -279,6 +279,17 @@ def getbasiscoefall(Xw, tree):
     shp = tuple(reversed(tuple(Xw.shape[2:])))
     N, K = Xw.shape[0], Xw.shape[1]
     assert K - 1 <= maxtransformlevels(shp), "AssertionError: k-1 <= maxtransformlevels(x)"
+    if isinstance(tree, torch.Tensor) and tree.dim() == 2:
+        # one tree per signal, (N, ntree) on the device (what bestbasistreeall returns): gathered by one kernel
+        assert tree.shape[0] == N, "AssertionError: m == m_t"
+        t8 = tree.to(device=Xw.device, dtype=torch.uint8).contiguous()
+        out = Xw.new_empty((N,) + tuple(Xw.shape[2:]))
+        if Xw.dim() == 3:
+            m, n = 0, Xw.shape[2]
+        else:
+            n, m = Xw.shape[2], Xw.shape[3]
+        D.call("gather_basis_multi", Xw, D.ptr(out), D.ptr(Xw), m, n, K, N, D.ptr(t8), t8.shape[1], D.stream(Xw))
+        return out
     tree = np.asarray(tree, dtype=bool)
     if tree.ndim == 2:
         assert tree.shape[1] == N, "AssertionError: m == m_t"
