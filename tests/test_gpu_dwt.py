@@ -310,3 +310,29 @@ def test_wpdall_host_pipeline(wx, O, cuda):
     assert np.array_equal(y, yd)
     ref = O.wpdall(x[:8], wt.taps, 9)
     assert relerr(y[:8], ref) <= 1e-12
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+def test_dwtall_idwtall(wx, O, cuda, dt):
+    """dwtall / idwtall (dwt/dwt_all.jl:39-110): the :dwt tree of the packet transform; batch == singles and the inverse
+    round trip are what the reference tests (test/transforms.jl:278-283); haar level 1 is pinned by test/wavemult.jl:26-30"""
+    haar = wx.wavelet("haar")
+    y = wx.dwtall(dev(np.array([[1, 2, -3, 4.0]], dtype=dt), cuda), haar, 1)
+    assert np.abs(y.cpu().numpy()[0].astype(np.float64) - np.array([2.1213, 0.7071, 0.7071, 4.9497])).max() < 6e-5
+    wt = wx.wavelet("db4")
+    h, g = pair(wx, wt)
+    x = np.random.default_rng(31).standard_normal((5, 256)).astype(dt)
+    for L in (None, 3, 0):
+        Lx = 8 if L is None else L
+        y = wx.dwtall(dev(x, cuda), wt) if L is None else wx.dwtall(dev(x, cuda), wt, L)
+        ref = np.stack([O.wpt(x[k], O.maketree1(256, Lx, "dwt"), h, g) for k in range(5)])
+        assert relerr(y.cpu().numpy(), ref) <= TOL[dt]
+        xr = wx.idwtall(y, wt) if L is None else wx.idwtall(y, wt, L)
+        assert relerr(xr.cpu().numpy(), x) <= (1e-10 if dt == np.float64 else 3e-4)
+    img = np.random.default_rng(32).standard_normal((3, 32, 16)).astype(dt)
+    y2 = wx.dwtall(dev(img, cuda), wt, 2)
+    ref2 = np.stack([O.wpt(img[k], O.maketree2(16, 32, 2, "dwt"), h, g) for k in range(3)])
+    assert relerr(y2.cpu().numpy(), ref2) <= TOL[dt]
+    assert relerr(wx.idwtall(y2, wt, 2).cpu().numpy(), img) <= (1e-10 if dt == np.float64 else 3e-4)
+    with pytest.raises(AssertionError):
+        wx.dwtall(dev(x, cuda), wt, 9)

@@ -14,7 +14,7 @@ from . import _dev as D
 from .filters import makereverseqmfpair
 from .utils import maketree, maxtransformlevels, isvalidtree, isdyadic
 
-__all__ = ["dwt_step", "dwt_step_", "idwt_step", "idwt_step_", "wpd", "wpd_", "iwpd", "iwpd_", "wpt", "wpt_",
+__all__ = ["dwtall", "idwtall", "dwt_step", "dwt_step_", "idwt_step", "idwt_step_", "wpd", "wpd_", "iwpd", "iwpd_", "wpt", "wpt_",
            "iwpt", "iwpt_", "wpdall", "iwpdall", "wptall", "iwptall", "getbasiscoef", "getbasiscoefall"]
 
 
@@ -270,6 +270,29 @@ def iwptall(xw, wt, arg=None):
 
 
 # ------------------------------------------------------------------ basis extraction
+def dwtall(x, wt, L=None):
+    """``dwtall(x, wt[, L])`` dwt/dwt_all.jl:39-54: the discrete wavelet transform of every signal.  The reference loops over
+    Wavelets.jl's ``dwt!``; on the device this is the tree transform along ``maketree(x, L, :dwt)`` (only the scaling node
+    is split again), run by the fused all-levels kernel.  Values are PARITY UNPINNED inside the reference (its tests only
+    check batch == single, test/transforms.jl:278-283)."""
+    x = D.dev(x, "x")
+    assert x.dim() > 1, "AssertionError: ndims(x) > 1"
+    shp = tuple(reversed(tuple(x.shape[1:])))
+    L = maxtransformlevels(shp) if L is None else int(L)
+    assert 0 <= L <= maxtransformlevels(shp), "AssertionError: 0 <= L <= maxtransformlevels(x)"
+    return _tree_batch("wpt", x, wt, maketree(*shp, L, "dwt"))
+
+
+def idwtall(xw, wt, L=None):
+    """``idwtall(xw, wt[, L])`` dwt/dwt_all.jl:95-110 (inverse of ``dwtall``)"""
+    xw = D.dev(xw, "xw")
+    assert xw.dim() > 1, "AssertionError: ndims(xw) > 1"
+    shp = tuple(reversed(tuple(xw.shape[1:])))
+    L = maxtransformlevels(shp) if L is None else int(L)
+    assert 0 <= L <= maxtransformlevels(shp), "AssertionError: 0 <= L <= maxtransformlevels(xw)"
+    return _tree_batch("iwpt", xw, wt, maketree(*shp, L, "dwt"))
+
+
 def getbasiscoefall(Xw, tree):
     """``getbasiscoefall(Xw, tree)`` Utils.jl:169-197 : Xw (N, K, n[, m]) -> (N, n[, m]).  ``tree`` may also be a
     (ntree, N) boolean matrix (one tree per signal, Utils.jl:199-225); those are gathered signal by signal."""
