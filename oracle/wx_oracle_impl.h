@@ -458,6 +458,9 @@ WXO_API void SUF(iwpd2)(T *xh, const T *Xw, long m, long n, int K, const unsigne
     size_t bytes = (size_t)m * n * sizeof(T);
     T *xt = (T *)malloc(bytes * (size_t)K), *temp = (T *)malloc(bytes);
     memcpy(xt, Xw, bytes * (size_t)K);
+    /* a root that is not split: the reference never writes x-hat in that case (DWT.jl:366-399 only stores inside the loop);
+     * defined here, and in the CUDA path, as the level-0 slice (what getbasiscoef returns for that tree) */
+    if (ntree < 1 || !tree[0]) memcpy(xh, Xw, bytes);
     for (long i = ntree; i >= 1; --i) {
         if (!tree[i - 1]) continue;
         int d = wx_quaddepth(i);

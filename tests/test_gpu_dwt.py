@@ -251,6 +251,26 @@ def test_wpd2d_large_images(wx, O, cuda, dt, name, m, n, L):
     ref = np.stack([O.wpd(x[k], h, g, L) for k in range(2)])
     assert relerr(y.cpu().numpy(), ref) <= TOL[dt]
     assert torch.equal(y[:, 0], dev(x, cuda))                                      # level 0 is a bit copy of x
+    # inverses through the fused 2-D kernels (whole-node kernel for the deep levels, halo tiles above): by level, by the
+    # dwt tree and by a random quad tree, against the oracle and as round trips; forward by tree == table + leaf gather
+    rt = 1e-10 if dt == np.float64 else 3e-4
+    assert relerr(wx.iwpdall(y, wt, L).cpu().numpy(), x) <= rt
+    rng = np.random.default_rng(L)
+    nt = wx.gettreelength(m, n)
+    rtree = np.zeros(nt, bool)
+    for i in range(1, nt + 1):
+        if wx.getdepth(i, "quad") >= L:
+            break
+        if (i == 1 or rtree[(i + 2) // 4 - 1]) and rng.random() < 0.8:
+            rtree[i - 1] = True
+    for tree in (wx.maketree(m, n, L, "dwt"), rtree, np.zeros(nt, bool)):
+        got = wx.iwpdall(y, wt, tree).cpu().numpy()
+        refi = np.stack([O.iwpd(ref[k], tree, h, g) for k in range(2)])
+        assert relerr(got, refi) <= TOL[dt] * 10
+        assert relerr(got, x) <= rt
+        yt = wx.wptall(dev(x, cuda), wt, tree)
+        assert relerr(yt.cpu().numpy(), np.stack([O.wpt(x[k], tree, h, g) for k in range(2)])) <= TOL[dt]
+        assert relerr(wx.iwptall(yt, wt, tree).cpu().numpy(), x) <= rt
 
 
 @pytest.mark.parametrize("dt", [np.float64, np.float32])

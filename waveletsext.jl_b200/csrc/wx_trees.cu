@@ -15,7 +15,10 @@ template <typename T>
 int wx_tree1d_fused(bool inverse, bool full, T *y, const T *x, long n, long N, int d0, int nlev, const unsigned char *dtree, long ntree,
                     const unsigned char *ddepth, int Kx, int vecgather, const Taps<T> &t, cudaStream_t s);
 
-// fused 2-D packet decomposition (wx_wpd2d.cu)
+// fused 2-D packet decomposition (wx_wpd2d.cu) and inverse by quad tree (wx_iwpt2d.cu)
+template <typename T>
+int wx_iwpt2d_fused(T *y, const T *xw, T *scratch, long m, long n, int nlev, long N, const unsigned char *dtree, long ntree, const Taps<T> &t,
+                    cudaStream_t s, bool *handled);
 template <typename T> int wx_wpd2d_fused(T *y, const T *x, long m, long n, int L, long N, const Taps<T> &t, cudaStream_t s, bool *handled);
 
 template <typename T>
@@ -331,6 +334,9 @@ int wpd2d_impl(T *y, const T *x, long m, long n, int L, long N, const double *h,
     return rc ? rc : rc2;
 }
 
+template <typename T>
+int gather_impl(T *out, const T *Xw, long m, long n, int K, long N, const unsigned char *tree, long ntree, void *stream);
+
 // wpt / iwpt 2-D by quad tree : x(m,n,N) -> y(m,n,N)   DWT.jl:500-548, 662-710
 template <typename T>
 int tree2d(bool inverse, T *y, const T *x, long m, long n, long N, const unsigned char *tree, long ntree, const double *h, const double *g, int F,
@@ -351,6 +357,40 @@ int tree2d(bool inverse, T *y, const T *x, long m, long n, long N, const unsigne
     }
     DevTree dt; rc = dt.upload(tree, ntree, s); if (rc) return rc;
     const long Nc = chunk_images(m, n, sizeof(T), N);
+    if (inverse && y != x) {
+        // fused inverse (wx_iwpt2d.cu): whole-node kernel for the deep levels, one halo-tile launch per coarse level
+        bool full = true;
+        { const long nfull = ((1L << (2 * nlev)) - 1) / 3; full = ntree >= nfull; for (long i = 0; full && i < nfull; ++i) full = tree[i] != 0; }
+        T *scr; rc = wx_scratch(&scr, (size_t)img * Nc, s); if (rc) return rc;
+        bool all = true;
+        for (long k0 = 0; k0 < N && !rc && all; k0 += Nc) {
+            const long nk = (N - k0 < Nc) ? N - k0 : Nc;
+            bool handled = false;
+            rc = wx_iwpt2d_fused<T>(y + k0 * img, x + k0 * img, scr, m, n, nlev, nk, full ? nullptr : dt.d, ntree, t, s, &handled);
+            if (!handled) all = false;                   // decided from the shape: the same for every chunk, nothing was launched
+        }
+        int rcf = wx_scratch_free(scr, s);
+        if (rc || rcf) return rc ? rc : rcf;
+        if (all) return WX_OK;
+    }
+    if (!inverse && y != x && m * n * (long)sizeof(T) * (nlev + 1) <= (1L << 31)) {
+        // forward by tree = packet table of the chunk (fused wpd kernels) + leaf gather (getbasiscoef)
+        long Nt = (long)(((size_t)3 << 30) / ((size_t)img * (nlev + 1) * sizeof(T)));
+        if (Nt < 1) Nt = 1;
+        if (Nt > N) Nt = N;
+        T *tab; rc = wx_scratch(&tab, (size_t)img * (nlev + 1) * Nt, s); if (rc) return rc;
+        bool all = true;
+        for (long k0 = 0; k0 < N && !rc && all; k0 += Nt) {
+            const long nk = (N - k0 < Nt) ? N - k0 : Nt;
+            bool handled = false;
+            rc = wx_wpd2d_fused<T>(tab, x + k0 * img, m, n, nlev, nk, t, s, &handled);
+            if (!rc && !handled) { all = false; break; }
+            if (!rc) rc = gather_impl<T>(y + k0 * img, tab, m, n, nlev + 1, nk, tree, ntree, stream);
+        }
+        int rcf = wx_scratch_free(tab, s);
+        if (rc || rcf) return rc ? rc : rcf;
+        if (all) return WX_OK;
+    }
     T *temp, *pp;
     rc = wx_scratch(&temp, (size_t)img * Nc, s); if (rc) return rc;
     rc = wx_scratch(&pp, (size_t)img * Nc, s); if (rc) return rc;

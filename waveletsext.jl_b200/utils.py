@@ -144,14 +144,11 @@ def isvalidtree(x, tree) -> bool:
         if gettreelength(shp[0], shp[1]) != nb:
             return False
         ar = 4
-    for i in range(1, nb + 1):
-        if tree[i - 1]:
-            continue
-        for c in range(ar):
-            ch = 2 * i + c if ar == 2 else 4 * i - 2 + c
-            if ch <= nb and tree[ch - 1]:
-                return False
-    return True
+    # a split node needs a split parent (children of i: 2i, 2i+1 / 4i-2 .. 4i+1)
+    on = np.flatnonzero(tree) + 1
+    on = on[on > 1]
+    par = on // 2 if ar == 2 else (on + 2) // 4
+    return bool(np.all(tree[par - 1]))
 
 
 def getleaf(tree, tree_type: str):
