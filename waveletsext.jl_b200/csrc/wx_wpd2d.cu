@@ -378,7 +378,7 @@ static int largest_divisor_le(long v, int cap)
 }
 
 template <typename T, int F>
-int wpd2d_run(T *y, const T *x, long m, long n, int L, long N, const Taps<T> &t, cudaStream_t s)
+int wpd2d_run_chunk(T *y, const T *x, long m, long n, int L, long N, const Taps<T> &t, cudaStream_t s)
 {
     WxDev dv; int rc = wx_devinfo(dv); if (rc) return rc;
     // depth from which a whole node fits the block kernel's two buffers (64 KB keeps three CTAs per SM)
@@ -408,6 +408,26 @@ int wpd2d_run(T *y, const T *x, long m, long n, int L, long N, const Taps<T> &t,
         WX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<dim3((unsigned)gx, (unsigned)gy), kT2, smem, s>>>(y, db == 0 ? x : nullptr, (int)m, (int)n, L, db, L, t);
         WX_LAUNCHED();
+    }
+    return WX_OK;
+}
+
+// Optional chunking of the batch (measurement knob WX_B200_WPD2D_CHUNK = images per chunk).  The idea -- keep the level a
+// launch writes resident in the 126 MB L2 for the launch that reads it -- was measured in round 1 and LOSES: with 8..64 images
+// per chunk the extra launches and partial waves cost more than the saved DRAM reads (19.1 ms -> 21.2..32.5 ms, db4 F64,
+// 4096 x 512^2), so the default is one launch per level for the whole batch.
+template <typename T, int F>
+int wpd2d_run(T *y, const T *x, long m, long n, int L, long N, const Taps<T> &t, cudaStream_t s)
+{
+    static const char *env = getenv("WX_B200_WPD2D_CHUNK");
+    long chunk = (env && atol(env) > 0) ? atol(env) : N;
+    if (chunk < 1) chunk = 1;
+    if (chunk > N) chunk = N;
+    const long img = m * n;
+    for (long k0 = 0; k0 < N; k0 += chunk) {
+        const long nk = (N - k0 < chunk) ? N - k0 : chunk;
+        int rc = wpd2d_run_chunk<T, F>(y + k0 * img * (L + 1), x + k0 * img, m, n, L, nk, t, s);
+        if (rc) return rc;
     }
     return WX_OK;
 }
