@@ -33,6 +33,29 @@ __device__ __forceinline__ void cp_async_pair(T *smem_dst, const T *gsrc)
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); }
 
+// division of a 32-bit index by a launch constant (host-built): shift for powers of two, else round-up multiply-high
+struct Div32 {
+    unsigned d, m, s;
+    int p2;
+};
+static inline Div32 make_div32(long dd)
+{
+    Div32 r;
+    r.d = (unsigned)dd; r.p2 = (dd & (dd - 1)) == 0; r.m = 0; r.s = 0;
+    if (r.p2) { while ((1L << r.s) < dd) ++r.s; return r; }
+    unsigned l = 0;
+    while ((1UL << l) < (unsigned long)dd) ++l;
+    r.m = (unsigned)((((1UL << l) - (unsigned long)dd) << 32) / (unsigned long)dd + 1);
+    r.s = l - 1;
+    return r;
+}
+__device__ __forceinline__ unsigned div32(unsigned x, const Div32 &v)
+{
+    if (v.p2) return x >> v.s;
+    const unsigned t = __umulhi(v.m, x);
+    return (t + ((x - t) >> 1)) >> v.s;
+}
+
 struct FastDiv {                    // division by a runtime constant that is usually a power of two
     int d, lg;
     __host__ __device__ FastDiv() : d(1), lg(0) {}

@@ -20,30 +20,39 @@
 namespace {
 
 // K consecutive output pairs from one window: win[0 .. 2K+F-3] = v[2i .. 2i+2K+F-3]; pair p uses win[2p .. 2p+F-1]
-constexpr int KROW = 8;
+constexpr int KROW = 8;       // row pass: output columns per thread (a window slides along the row)
+constexpr int KSEG = 4;       // column pass of the compile-time-shaped kernels: output pairs per thread (window slides down the column)
+
+// leading dimensions of the shared-memory arrays.  Column pass: lanes walk COLUMNS and read element pairs, conflict free when
+// (ld / 2) is odd; its outputs are single elements written by lanes that walk columns, conflict free when ld is odd.
+__host__ __device__ constexpr int wx_ld_pairs(int rows) { return ((rows / 2) % 2 == 0) ? rows + 2 : rows; }
+__host__ __device__ constexpr int wx_ld_odd(int rows) { return rows | 1; }
 
 // ---------------------------------------------------------------------------------------------------------
-// one level, tiles with halo.  Shared memory: P (PR+2 rows x PC) parent patch, Tm (2tr rows x PC+2) column-pass output;
-// the +2 padding lets the last thread of a row / column compute a (discarded) second pair without leaving the arrays.
+// one level, tiles with halo.  Shared memory: P (parent patch, PR rows x PC cols, column-major) and Tm (column-pass output,
+// 2tr rows x PC cols: rows [0,tr) scaling, [tr,2tr) detail).
+// TRC > 0: tile edge known at compile time (tr = tc = TRC): index arithmetic folds to shifts / immediates and the column pass
+// slides a register window down each column (KSEG pairs per thread, lanes across columns).
 // ---------------------------------------------------------------------------------------------------------
-template <typename T, int F>
-__global__ void __launch_bounds__(kT2) wpd2d_tile_k(T *__restrict__ y, const T *__restrict__ x, int m, int n, int L, int d, int tr, int tc,
-                                                   Taps<T> tp)
+template <typename T, int F, int TRC>
+__global__ void __launch_bounds__(kT2, 3) wpd2d_tile_k(T *__restrict__ y, const T *__restrict__ x, int m, int n, int L, int d, int tr_, int tc_,
+                                                      Div32 drowtiles, Div32 dtiles_r, Div32 dtiles_c, Taps<T> tp)
 {
+    const int tr = TRC > 0 ? TRC : tr_, tc = TRC > 0 ? TRC : tc_;
     using P2 = typename Pair<T>::type;
     constexpr int S = (F - 2) / 2;
     extern __shared__ __align__(16) unsigned char wx_2d_smem[];
-    const int PR = 2 * tr + F - 2, PC = 2 * tc + F - 2, LDP = PR + 2 * (tr & 1), R2 = 2 * tr;    // odd tiles: padded (see host)
+    const int PR = 2 * tr + F - 2, PC = 2 * tc + F - 2, R2 = 2 * tr;
+    const int LDP = TRC > 0 ? wx_ld_pairs(PR) : PR + 2 * (tr & 1);      // generic shape: odd tiles padded (see host)
+    const int LDT = TRC > 0 ? wx_ld_odd(R2) : R2;
     T *P = reinterpret_cast<T *>(wx_2d_smem);
     T *Tm = P + LDP * PC;
     const int tid = threadIdx.x;
     const int mp = m >> d, np = n >> d, hr = mp / 2, hc = np / 2;
-    const int tiles_r = hr / tr, tiles_c = hc / tc, nodes = 1 << d;
     // grid.x = image * (row tiles of all nodes), grid.y = column tiles of all nodes: neighbouring CTAs walk down the rows
-    const unsigned rowtiles = (unsigned)(tiles_r * nodes);
-    const unsigned k = blockIdx.x / rowtiles, rt = blockIdx.x - k * rowtiles;
-    const int jr = (int)(rt / (unsigned)tiles_r), ti = (int)(rt - (unsigned)jr * tiles_r);
-    const int jc = (int)(blockIdx.y / (unsigned)tiles_c), tk = (int)(blockIdx.y - (unsigned)jc * tiles_c);
+    const unsigned k = div32(blockIdx.x, drowtiles), rt = blockIdx.x - k * drowtiles.d;
+    const int jr = (int)div32(rt, dtiles_r), ti = (int)(rt - (unsigned)jr * dtiles_r.d);
+    const int jc = (int)div32(blockIdx.y, dtiles_c), tk = (int)(blockIdx.y - (unsigned)jc * dtiles_c.d);
     const long img = (long)m * n;
     T *yk = y + (long)k * img * (L + 1);
     const bool from_x = (d == 0 && x != nullptr);
@@ -77,9 +86,29 @@ __global__ void __launch_bounds__(kT2) wpd2d_tile_k(T *__restrict__ y, const T *
         for (int b = warp; b < 2 * tc; b += kT2 / 32)
             *reinterpret_cast<P2 *>(y0 + b * m) = *reinterpret_cast<const P2 *>(P + b * LDP + 2 * lane);
     }
-    // ---- column pass: every column of the patch; a thread owns pairs il and il + ceil(tr/2) (lanes walk consecutive il:
-    //      conflict-free 16-byte loads) ----
-    if (tr <= 32 && (32 % tr) == 0) {
+    // ---- column pass ----
+    if (TRC > 0 && TRC % KSEG == 0) {
+        // lanes walk the columns (pair loads, conflict free by the choice of LDP); a thread slides one window of
+        // 2*KSEG+F-2 samples down KSEG output pairs of its column
+        constexpr int PCc = 2 * TRC + F - 2, NSEG = (TRC > 0 ? TRC : KSEG) / KSEG, W = 2 * KSEG + F - 2;
+        for (int t = tid; t < PCc * NSEG; t += kT2) {
+            const int sg = t / PCc, b = t - sg * PCc, il0 = sg * KSEG;
+            const T *src = P + b * LDP + 2 * il0;
+            T win[W];
+#pragma unroll
+            for (int q = 0; q < W / 2; ++q) {
+                const P2 v = *reinterpret_cast<const P2 *>(src + 2 * q);
+                win[2 * q] = v.x; win[2 * q + 1] = v.y;
+            }
+            T *d0 = Tm + b * LDT + il0;
+#pragma unroll
+            for (int p = 0; p < KSEG; ++p) {
+                T lo, hi;
+                dwt_dots<T, F>(&win[2 * p], tp, lo, hi);
+                d0[p] = lo; d0[tr + p] = hi;
+            }
+        }
+    } else if (tr <= 32 && (32 % tr) == 0) {
         // lanes walk il (conflict-free 16-byte loads), 32/tr columns per warp, warps stride over the columns, two columns in flight
         const int cpw = 32 / tr, il = lane % tr, bstep = (kT2 / 32) * cpw;
         for (int b = warp * cpw + lane / tr; b < PC; b += 2 * bstep) {
@@ -97,9 +126,9 @@ __global__ void __launch_bounds__(kT2) wpd2d_tile_k(T *__restrict__ y, const T *
             T lo0, hi0, lo1, hi1;
             dwt_dots<T, F>(w0, tp, lo0, hi0);
             dwt_dots<T, F>(w1, tp, lo1, hi1);
-            T *d0 = Tm + b * R2 + il;
+            T *d0 = Tm + b * LDT + il;
             d0[0] = lo0; d0[tr] = hi0;
-            if (two) { d0[bstep * R2] = lo1; d0[bstep * R2 + tr] = hi1; }
+            if (two) { d0[bstep * LDT] = lo1; d0[bstep * LDT + tr] = hi1; }
         }
     } else {
         const int trh = (tr + 1) / 2;
@@ -118,13 +147,13 @@ __global__ void __launch_bounds__(kT2) wpd2d_tile_k(T *__restrict__ y, const T *
             T lo0, hi0, lo1, hi1;
             dwt_dots<T, F>(w0, tp, lo0, hi0);
             dwt_dots<T, F>(w1, tp, lo1, hi1);
-            T *dst = Tm + b * R2 + il;
+            T *dst = Tm + b * LDT + il;
             dst[0] = lo0; dst[tr] = hi0;
             if (two) { dst[trh] = lo1; dst[tr + trh] = hi1; }
         }
     }
     __syncthreads();
-    // ---- row pass + store: (2tr rows) x (tc output pairs), two pairs per thread ----
+    // ---- row pass + store: (2tr rows) x (tc output pairs) ----
     T *ynext = yk + (long)(d + 1) * img + (long)nc0 * m + nr0;
     if ((kT2 % R2) == 0 && (tc % KROW) == 0) {
         // a thread owns one row r and KROW consecutive output columns: one window of 2*KROW+F-2 samples slides along the row
@@ -136,9 +165,9 @@ __global__ void __launch_bounds__(kT2) wpd2d_tile_k(T *__restrict__ y, const T *
         for (int g = tid / R2; g < tc / KROW; g += kT2 / R2) {
             const int kl0 = KROW * g;
             T win[2 * KROW + F - 2];
-            const T *src = Tm + (2 * kl0) * R2 + r;
+            const T *src = Tm + (2 * kl0) * LDT + r;
 #pragma unroll
-            for (int j = 0; j < 2 * KROW + F - 2; ++j) win[j] = src[j * R2];
+            for (int j = 0; j < 2 * KROW + F - 2; ++j) win[j] = src[j * LDT];
             int ch = k0 + kl0 + S; while (ch >= hc) ch -= hc;
             T *olo = o + (k0 + kl0) * m, *ohi = o + (hc + ch) * m;
             const long back = (long)hc * m;
@@ -157,9 +186,9 @@ __global__ void __launch_bounds__(kT2) wpd2d_tile_k(T *__restrict__ y, const T *
         for (Walk2 w(tid, R2); w.hi < tcq; w.next()) {
             const int kl = 2 * w.hi, r = w.lo;
             T win[F + 2];
-            const T *src = Tm + (2 * kl) * R2 + r;
+            const T *src = Tm + (2 * kl) * LDT + r;
 #pragma unroll
-            for (int j = 0; j < F + 2; ++j) win[j] = src[j * R2];
+            for (int j = 0; j < F + 2; ++j) win[j] = src[j * LDT];
             T lo0, hi0, lo1, hi1;
             dwt_dots2<T, F>(win, tp, lo0, hi0, lo1, hi1);
             int ci, qr;
@@ -181,7 +210,7 @@ __global__ void __launch_bounds__(kT2) wpd2d_tile_k(T *__restrict__ y, const T *
 // ---------------------------------------------------------------------------------------------------------
 // all remaining levels of a node that fits shared memory
 // ---------------------------------------------------------------------------------------------------------
-// one window of NW values starting at element 2*il of a periodic vector of length len (stride st)
+// one window of NW values starting at element `start` of a periodic vector of length len (stride st)
 template <typename T, int NW>
 __device__ __forceinline__ void load_window(T *win, const T *src, int start, int len, int st)
 {
@@ -212,16 +241,18 @@ __device__ __forceinline__ void load_window_pairs(T *win, const T *src, int star
     }
 }
 
-template <typename T, int F>
-__global__ void __launch_bounds__(kT2) wpd2d_block_k(T *__restrict__ y, const T *__restrict__ x, int m, int n, int L, int db, int dend,
-                                                    Taps<T> tp)
+// BE > 0: square block of edge BE known at compile time (padded leading dimensions, sliding-window column pass)
+template <typename T, int F, int BE>
+__global__ void __launch_bounds__(kT2, 3) wpd2d_block_k(T *__restrict__ y, const T *__restrict__ x, int m, int n, int L, int db, int dend,
+                                                       Taps<T> tp)
 {
     using P2 = typename Pair<T>::type;
     constexpr int S = (F - 2) / 2;
     extern __shared__ __align__(16) unsigned char wx_2d_smem[];
-    const int BR = m >> db, BC = n >> db;
+    const int BR = BE > 0 ? BE : (m >> db), BC = BE > 0 ? BE : (n >> db);
+    const int LDA = BE > 0 ? wx_ld_pairs(BR) : BR, LDT = BE > 0 ? wx_ld_odd(BR) : BR;
     T *A = reinterpret_cast<T *>(wx_2d_smem);            // (BR, BC) column-major: the block at the current level
-    T *Tm = A + BR * BC;                                  // after the column pass
+    T *Tm = A + LDA * BC;                                 // after the column pass
     const int tid = threadIdx.x;
     // grid.x = image * nodes + node row, grid.y = node column
     const unsigned k = blockIdx.x >> db;
@@ -237,44 +268,37 @@ __global__ void __launch_bounds__(kT2) wpd2d_block_k(T *__restrict__ y, const T 
     const bool colwarp = BR2 <= 32 && (32 % BR2) == 0;
     const int cpw = colwarp ? 32 / BR2 : 1, ca = 2 * (lane % BR2), cb0 = warp * cpw + lane / BR2, cbs = (kT2 / 32) * cpw;
 
-    if (colwarp) { for (int b = cb0; b < BC; b += cbs) cp_async_pair<T>(A + b * BR + ca, par + b * m + ca); }
-    else { for (Walk2 w(tid, BR2); w.hi < BC; w.next()) cp_async_pair<T>(A + w.hi * BR + 2 * w.lo, par + w.hi * m + 2 * w.lo); }
+    if (colwarp) { for (int b = cb0; b < BC; b += cbs) cp_async_pair<T>(A + b * LDA + ca, par + b * m + ca); }
+    else { for (Walk2 w(tid, BR2); w.hi < BC; w.next()) cp_async_pair<T>(A + w.hi * LDA + 2 * w.lo, par + w.hi * m + 2 * w.lo); }
     cp_async_wait_all();
     __syncthreads();
     if (from_x) {                                         // y[:,:,1] = x   DWT.jl:176
         T *y0 = yk + org;
-        if (colwarp) { for (int b = cb0; b < BC; b += cbs) *reinterpret_cast<P2 *>(y0 + b * m + ca) = *reinterpret_cast<const P2 *>(A + b * BR + ca); }
-        else { for (Walk2 w(tid, BR2); w.hi < BC; w.next()) *reinterpret_cast<P2 *>(y0 + w.hi * m + 2 * w.lo) = *reinterpret_cast<const P2 *>(A + w.hi * BR + 2 * w.lo); }
+        if (colwarp) { for (int b = cb0; b < BC; b += cbs) *reinterpret_cast<P2 *>(y0 + b * m + ca) = *reinterpret_cast<const P2 *>(A + b * LDA + ca); }
+        else { for (Walk2 w(tid, BR2); w.hi < BC; w.next()) *reinterpret_cast<P2 *>(y0 + w.hi * m + 2 * w.lo) = *reinterpret_cast<const P2 *>(A + w.hi * LDA + 2 * w.lo); }
     }
     for (int l = db; l < dend; ++l) {
         const int mpl = m >> l, npl = n >> l, hr = mpl / 2, hc = npl / 2;
         // ---- column pass A -> Tm, per node: scaling rows on top, detail rows below (shift resolved here) ----
-        if (BR2 <= 32 && (32 % BR2) == 0 && mpl >= F) {
-            // lanes walk the pairs of one column (conflict-free 16-byte loads), warps stride over the columns, two in flight
-            const int ig = lane % BR2, bstep = cbs;
-            const int jn = ig / hr, il = ig - jn * hr, r0 = jn * mpl;
-            int ih = il + S; if (ih >= hr) ih %= hr;
-            int e[F / 2];
+        constexpr int WS = 2 * KSEG + F - 2;
+        if (BE > 0 && hr % KSEG == 0 && mpl >= WS) {
+            // lanes walk the columns; a thread slides one window down KSEG output pairs of one node
+            const FastDiv dq(hr);
+            for (int t = tid; t < (BR2 / KSEG) * BC; t += kT2) {
+                const int sg = t / BC, c = t - sg * BC, ig0 = sg * KSEG;
+                const int jn = dq.div(ig0), il0 = ig0 - jn * hr, r0 = jn * mpl;
+                T win[WS];
+                load_window_pairs<T, WS>(win, A + c * LDA + r0, 2 * il0, mpl);
+                T *dst = Tm + c * LDT + r0;
+                int ih = il0 + S; if (ih >= hr) ih %= hr;
 #pragma unroll
-            for (int q = 0; q < F / 2; ++q) { e[q] = 2 * il + 2 * q; if (e[q] >= mpl) e[q] -= mpl; }
-            for (int b = cb0; b < BC; b += 2 * bstep) {
-                const bool two = b + bstep < BC;
-                const T *s0 = A + b * BR + r0;
-                const T *s1 = two ? s0 + bstep * BR : s0;
-                T w0[F], w1[F];
-#pragma unroll
-                for (int q = 0; q < F / 2; ++q) {
-                    const P2 v = *reinterpret_cast<const P2 *>(s0 + e[q]);
-                    const P2 u = *reinterpret_cast<const P2 *>(s1 + e[q]);
-                    w0[2 * q] = v.x; w0[2 * q + 1] = v.y;
-                    w1[2 * q] = u.x; w1[2 * q + 1] = u.y;
+                for (int p = 0; p < KSEG; ++p) {
+                    T lo, hi;
+                    dwt_dots<T, F>(&win[2 * p], tp, lo, hi);
+                    dst[il0 + p] = lo;
+                    dst[hr + ih] = hi;
+                    if (++ih >= hr) ih -= hr;
                 }
-                T lo0, hi0, lo1, hi1;
-                dwt_dots<T, F>(w0, tp, lo0, hi0);
-                dwt_dots<T, F>(w1, tp, lo1, hi1);
-                T *d0 = Tm + b * BR + r0;
-                d0[il] = lo0; d0[hr + ih] = hi0;
-                if (two) { d0[bstep * BR + il] = lo1; d0[bstep * BR + hr + ih] = hi1; }
             }
         } else if (BR2 % 2 == 0) {                         // two pairs per thread: ig and ig + BR2/2 (consecutive lanes, consecutive pairs)
             const FastDiv dq(hr);
@@ -287,12 +311,12 @@ __global__ void __launch_bounds__(kT2) wpd2d_block_k(T *__restrict__ y, const T 
                     const int ig = w.lo + t * (BR2 / 2), jn = dq.div(ig);
                     il[t] = ig - jn * hr; r0[t] = jn * mpl;
                     T win[F];
-                    load_window_pairs<T, F>(win, A + b * BR + r0[t], 2 * il[t], mpl);
+                    load_window_pairs<T, F>(win, A + b * LDA + r0[t], 2 * il[t], mpl);
                     dwt_dots<T, F>(win, tp, lo[t], hi[t]);
                 }
 #pragma unroll
                 for (int t = 0; t < 2; ++t) {
-                    T *dst = Tm + b * BR + r0[t];
+                    T *dst = Tm + b * LDT + r0[t];
                     dst[il[t]] = lo[t];
                     int ih = il[t] + S; if (ih >= hr) ih %= hr;
                     dst[hr + ih] = hi[t];
@@ -303,10 +327,10 @@ __global__ void __launch_bounds__(kT2) wpd2d_block_k(T *__restrict__ y, const T 
             for (Walk2 w(tid, BR2); w.hi < BC; w.next()) {
                 const int b = w.hi, jn = dq.div(w.lo), il = w.lo - jn * hr, r0 = jn * mpl;
                 T win[F];
-                load_window_pairs<T, F>(win, A + b * BR + r0, 2 * il, mpl);
+                load_window_pairs<T, F>(win, A + b * LDA + r0, 2 * il, mpl);
                 T lo, hi;
                 dwt_dots<T, F>(win, tp, lo, hi);
-                T *dst = Tm + b * BR + r0;
+                T *dst = Tm + b * LDT + r0;
                 dst[il] = lo;
                 dst[hr + (il + S) % hr] = hi;
             }
@@ -319,17 +343,17 @@ __global__ void __launch_bounds__(kT2) wpd2d_block_k(T *__restrict__ y, const T 
             for (int g = tid / BR; g < BC / (2 * KROW); g += kT2 / BR) {
                 const int kg0 = KROW * g, jn = kg0 / hc, kl0 = kg0 - jn * hc, c0 = jn * npl;
                 T win[2 * KROW + F - 2];
-                const T *src = Tm + c0 * BR + r;
+                const T *src = Tm + c0 * LDT + r;
 #pragma unroll
-                for (int j = 0; j < 2 * KROW + F - 2; ++j) { int cc = 2 * kl0 + j; if (cc >= npl) cc -= npl; win[j] = src[cc * BR]; }
+                for (int j = 0; j < 2 * KROW + F - 2; ++j) { int cc = 2 * kl0 + j; if (cc >= npl) cc -= npl; win[j] = src[cc * LDT]; }
                 int kh = kl0 + S; if (kh >= hc) kh %= hc;
-                T *dst = A + c0 * BR + r;
+                T *dst = A + c0 * LDA + r;
 #pragma unroll
                 for (int p = 0; p < KROW; ++p) {
                     T lo, hi;
                     dwt_dots<T, F>(&win[2 * p], tp, lo, hi);
-                    dst[(kl0 + p) * BR] = lo;
-                    dst[(hc + kh) * BR] = hi;
+                    dst[(kl0 + p) * LDA] = lo;
+                    dst[(hc + kh) * LDA] = hi;
                     ++kh; if (kh >= hc) kh -= hc;
                 }
             }
@@ -338,34 +362,34 @@ __global__ void __launch_bounds__(kT2) wpd2d_block_k(T *__restrict__ y, const T 
             for (Walk2 w(tid, BR); w.hi < BC / 4; w.next()) {
                 const int r = w.lo, jn = dq.div(w.hi), kl = 2 * (w.hi - jn * (hc / 2)), c0 = jn * npl;
                 T win[F + 2];
-                load_window<T, F + 2>(win, Tm + c0 * BR + r, 2 * kl, npl, BR);
+                load_window<T, F + 2>(win, Tm + c0 * LDT + r, 2 * kl, npl, LDT);
                 T lo0, hi0, lo1, hi1;
                 dwt_dots2<T, F>(win, tp, lo0, hi0, lo1, hi1);
-                T *dst = A + c0 * BR + r;
-                dst[kl * BR] = lo0; dst[(kl + 1) * BR] = lo1;
+                T *dst = A + c0 * LDA + r;
+                dst[kl * LDA] = lo0; dst[(kl + 1) * LDA] = lo1;
                 int kh = kl + S; if (kh >= hc) kh %= hc;
-                dst[(hc + kh) * BR] = hi0;
+                dst[(hc + kh) * LDA] = hi0;
                 ++kh; if (kh >= hc) kh -= hc;
-                dst[(hc + kh) * BR] = hi1;
+                dst[(hc + kh) * LDA] = hi1;
             }
         } else {
             const FastDiv dq(hc);
             for (Walk2 w(tid, BR); w.hi < BC / 2; w.next()) {
                 const int r = w.lo, jn = dq.div(w.hi), kl = w.hi - jn * hc, c0 = jn * npl;
                 T win[F];
-                load_window<T, F>(win, Tm + c0 * BR + r, 2 * kl, npl, BR);
+                load_window<T, F>(win, Tm + c0 * LDT + r, 2 * kl, npl, LDT);
                 T lo, hi;
                 dwt_dots<T, F>(win, tp, lo, hi);
-                T *dst = A + c0 * BR + r;
-                dst[kl * BR] = lo;
-                dst[(hc + (kl + S) % hc) * BR] = hi;
+                T *dst = A + c0 * LDA + r;
+                dst[kl * LDA] = lo;
+                dst[(hc + (kl + S) % hc) * LDA] = hi;
             }
         }
         __syncthreads();
         // ---- level l+1 slice ----
         T *ynext = yk + (long)(l + 1) * img + org;
-        if (colwarp) { for (int b = cb0; b < BC; b += cbs) *reinterpret_cast<P2 *>(ynext + b * m + ca) = *reinterpret_cast<const P2 *>(A + b * BR + ca); }
-        else { for (Walk2 w(tid, BR2); w.hi < BC; w.next()) *reinterpret_cast<P2 *>(ynext + w.hi * m + 2 * w.lo) = *reinterpret_cast<const P2 *>(A + w.hi * BR + 2 * w.lo); }
+        if (colwarp) { for (int b = cb0; b < BC; b += cbs) *reinterpret_cast<P2 *>(ynext + b * m + ca) = *reinterpret_cast<const P2 *>(A + b * LDA + ca); }
+        else { for (Walk2 w(tid, BR2); w.hi < BC; w.next()) *reinterpret_cast<P2 *>(ynext + w.hi * m + 2 * w.lo) = *reinterpret_cast<const P2 *>(A + w.hi * LDA + 2 * w.lo); }
         // the next column pass only reads A (complete after the barrier above) and writes Tm (free): no barrier needed here
     }
 }
@@ -391,22 +415,38 @@ int wpd2d_run_chunk(T *y, const T *x, long m, long n, int L, long N, const Taps<
         const long hr = (m >> d) / 2, hc = (n >> d) / 2;
         const int tr = largest_divisor_le(hr, cap), tc = largest_divisor_le(hc, cap);
         const int PR = 2 * tr + F - 2, PC = 2 * tc + F - 2;
-        const size_t smem = ((size_t)(PR + 2 * (tr & 1)) * PC + (size_t)2 * tr * (PC + 2 * (tc & 1))) * sizeof(T);
+        const bool shaped = (tr == 32 && tc == 32);          // the compile-time-shaped instantiation (padded leading dimensions)
+        const size_t smem = shaped ? ((size_t)wx_ld_pairs(PR) * PC + (size_t)wx_ld_odd(2 * tr) * PC) * sizeof(T)
+                                   : ((size_t)(PR + 2 * (tr & 1)) * PC + (size_t)2 * tr * (PC + 2 * (tc & 1))) * sizeof(T);
         if (smem > dv.smem_optin) return wx_fail(WX_EUNSUPPORTED, "wpd 2-D tile does not fit shared memory");
         const long gx = (hr / tr) * (1L << d) * N, gy = (hc / tc) * (1L << d);
         if (gx >= (1L << 31) || gy > 65535) return wx_fail(WX_EUNSUPPORTED, "wpd 2-D: too many tiles for one launch");
-        auto kern = wpd2d_tile_k<T, F>;
-        WX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<dim3((unsigned)gx, (unsigned)gy), kT2, smem, s>>>(y, d == 0 ? x : nullptr, (int)m, (int)n, L, d, tr, tc, t);
+        const Div32 drt = make_div32((hr / tr) * (1L << d)), dtr = make_div32(hr / tr), dtc = make_div32(hc / tc);
+        if (tr == 32 && tc == 32) {
+            auto kern = wpd2d_tile_k<T, F, 32>;
+            WX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<dim3((unsigned)gx, (unsigned)gy), kT2, smem, s>>>(y, d == 0 ? x : nullptr, (int)m, (int)n, L, d, tr, tc, drt, dtr, dtc, t);
+        } else {
+            auto kern = wpd2d_tile_k<T, F, 0>;
+            WX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<dim3((unsigned)gx, (unsigned)gy), kT2, smem, s>>>(y, d == 0 ? x : nullptr, (int)m, (int)n, L, d, tr, tc, drt, dtr, dtc, t);
+        }
         WX_LAUNCHED();
     }
     if (db < L) {
-        const size_t smem = (size_t)2 * (m >> db) * (n >> db) * sizeof(T);
+        const bool shaped = (m >> db) == 64 && (n >> db) == 64;
+        const size_t smem = shaped ? (size_t)(wx_ld_pairs(64) + wx_ld_odd(64)) * 64 * sizeof(T) : (size_t)2 * (m >> db) * (n >> db) * sizeof(T);
         const long gx = (1L << db) * N, gy = 1L << db;
         if (gx >= (1L << 31) || gy > 65535) return wx_fail(WX_EUNSUPPORTED, "wpd 2-D: too many blocks for one launch");
-        auto kern = wpd2d_block_k<T, F>;
-        WX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<dim3((unsigned)gx, (unsigned)gy), kT2, smem, s>>>(y, db == 0 ? x : nullptr, (int)m, (int)n, L, db, L, t);
+        if ((m >> db) == 64 && (n >> db) == 64) {
+            auto kern = wpd2d_block_k<T, F, 64>;
+            WX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<dim3((unsigned)gx, (unsigned)gy), kT2, smem, s>>>(y, db == 0 ? x : nullptr, (int)m, (int)n, L, db, L, t);
+        } else {
+            auto kern = wpd2d_block_k<T, F, 0>;
+            WX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<dim3((unsigned)gx, (unsigned)gy), kT2, smem, s>>>(y, db == 0 ? x : nullptr, (int)m, (int)n, L, db, L, t);
+        }
         WX_LAUNCHED();
     }
     return WX_OK;
