@@ -205,3 +205,37 @@ def test_swpd_fullsize_properties(wx, cuda):
     xa = wx.acwpdall(x, wt, L)
     xr = wx.iacwpdall(xa, L)
     assert (xr - x).abs().max().item() <= 1e-10 * x.abs().max().item()
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+@pytest.mark.parametrize("name", ["db4", "sym8"])
+@pytest.mark.parametrize("n,L", [(4096, 6), (1024, 10), (256, 8), (8192, 3), (16384, 2)])
+def test_redundant_fused_stage_plans(wx, O, cuda, dt, name, n, L):
+    """shapes that exercise every plan of the fused redundant kernels: several stages (long stacks), a fused prefix followed
+    by the per-depth path (levels whose cosets are shorter than a thread's run), one and two CTAs per SM"""
+    wt = wx.wavelet(name)
+    h, g = pair(wx, wt)
+    P, Q = acpair(wx, wt)
+    x = np.random.default_rng(n + L).standard_normal((2, n)).astype(dt)
+    xd = dev(x, cuda)
+    rt = 1e-10 if dt == np.float64 else 5e-4
+    for k, fn, ref in (("swpd", wx.swpdall, lambda v: O.swpd(v, L, h, g)), ("sdwt", wx.sdwtall, lambda v: O.sdwt(v, L, h, g)),
+                       ("swpt", wx.swptall, lambda v: O.swpt(v, L, h, g)), ("acwpd", wx.acwpdall, lambda v: O.acwpd(v, L, P, Q)),
+                       ("acdwt", wx.acdwtall, lambda v: O.acdwt(v, L, P, Q)), ("acwpt", wx.acwptall, lambda v: O.acwpt(v, L, P, Q))):
+        out = fn(xd, wt, L)
+        want = np.stack([ref(x[i]) for i in range(2)])
+        assert out.shape == want.shape, k
+        assert relerr(out.cpu().numpy(), want) <= TOL[dt], k
+    # inverses (average based = the fused tree / chain reductions; shift based; autocorrelation sums) as round trips
+    assert relerr(wx.iswptall(wx.swptall(xd, wt, L), wt).cpu().numpy(), x) <= rt
+    assert relerr(wx.iswptall(wx.swptall(xd, wt, L), wt, 3 % (1 << L)).cpu().numpy(), x) <= rt
+    assert relerr(wx.isdwtall(wx.sdwtall(xd, wt, L), wt).cpu().numpy(), x) <= rt
+    assert relerr(wx.iswpdall(wx.swpdall(xd, wt, L), wt, L).cpu().numpy(), x) <= rt
+    assert relerr(wx.iswpdall(wx.swpdall(xd, wt, L), wt, min(2, L)).cpu().numpy(), x) <= rt
+    assert relerr(wx.iacwptall(wx.acwptall(xd, wt, L)).cpu().numpy(), x) <= rt
+    assert relerr(wx.iacdwtall(wx.acdwtall(xd, wt, L)).cpu().numpy(), x) <= rt
+    assert relerr(wx.iacwpdall(wx.acwpdall(xd, wt, L), L).cpu().numpy(), x) <= rt
+    # average-based inverses against the oracle (not only as round trips)
+    sw = wx.swptall(xd, wt, L)
+    want = np.stack([O.iswpt(sw[i].cpu().numpy(), h, g) for i in range(2)])
+    assert relerr(wx.iswptall(sw, wt).cpu().numpy(), want) <= TOL[dt] * 20
