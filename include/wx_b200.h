@@ -171,6 +171,14 @@ int wx_bb_costs_f32(double *costs_dev, const float *X, long m, long n, int K, lo
 int wx_bb_select(unsigned char *trees_dev, double *costs_dev, long nnodes, long m, long n, long N, int elt, void *stream);
 int wx_gather_basis_multi_f64(double *out, const double *Xw, long m, long n, int K, long N, const unsigned char *trees_dev, long ntree, void *stream);
 int wx_gather_basis_multi_f32(float *out, const float *Xw, long m, long n, int K, long N, const unsigned char *trees_dev, long ntree, void *stream);
+/* LDB (next row f-2): energy_map(Xw, y, ::TimeFrequency) ldb/ldb_energymap.jl:109-141 numerators (per class sum of squares over
+ * the local signals; labels = device int32 in [0, nc)), discriminant_measure ldb/ldb_measures.jl:139-183,302-325
+ * (kind 0 AsymmetricRelativeEntropy, 1 SymmetricRelativeEntropy, 2 LpDistance(p), 3 HellingerDistance) and the node sums of
+ * LDB.jl:217-237 (top_k >= node size).  Tree: wx_tree_select(..., minmax = 1). */
+int wx_energy_map_tf_f64(double *esum_dev, const double *X, const int *labels_dev, int nc, long szK, long Nlocal, void *stream);
+int wx_energy_map_tf_f32(double *esum_dev, const float *X, const int *labels_dev, int nc, long szK, long Nlocal, void *stream);
+int wx_ldb_discriminant(double *D_dev, const double *esum_dev, const double *inv_norm_dev, int nc, long szK, int kind, double p, int elt, void *stream);
+int wx_node_costs(double *costs_host, const double *term_dev, long m, long n, int K, int redundant, double mult, int elt, void *stream);
 /* bestbasis_treeselection  BestBasis.jl:59-110 (host, O(n)); costs are modified in place like the reference.
  * m = 0: binary tree with n-1 entries; m > 0: quad tree. minmax 0 = :min, 1 = :max */
 int wx_tree_select(unsigned char *tree_out, double *costs_host, long ncosts, long m, long n, int minmax);

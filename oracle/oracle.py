@@ -507,3 +507,57 @@ def tree_select(costs, n, m=None, minmax="min"):
         tree = np.zeros(treelength2(n, m), np.uint8)
         _call(f"wxo_tree_select2_{_sfx(costs.dtype)}", "PPllli", tree, costs, len(costs), n, m, mm)
     return tree.astype(bool)
+
+
+# ------------------------------------------------------------------ LDB (row f-2): numpy restatement, small per-position maps
+def energy_map_tf(Xw, y):
+    """energy_map(Xw, y, TimeFrequency()) ldb/ldb_energymap.jl:109-141.  Xw (N, K, n[, m]) -> Gamma (nc, K, n[, m]); classes in
+    order of first appearance (Julia unique)."""
+    Xw = np.asarray(Xw); y = list(y)
+    classes = list(dict.fromkeys(y))
+    out = np.empty((len(classes),) + Xw.shape[1:], Xw.dtype)
+    for i, c in enumerate(classes):
+        idx = [k for k, v in enumerate(y) if v == c]
+        xw = Xw[idx]
+        x = xw[:, 0]                                              # level 0 = the signals
+        norm_sum = np.sum(np.sum(x.reshape(len(idx), -1).astype(Xw.dtype) ** 2, axis=1))
+        out[i] = np.sum(xw ** 2, axis=0) / norm_sum
+    return out
+
+
+def discriminant_measure(G, kind="are", p=2.0):
+    """discriminant_measure(Gamma, dm) ldb/ldb_measures.jl:139-183 + pairwise measures :302-325 (time-frequency maps)"""
+    G = np.asarray(G)
+    nc = G.shape[0]
+    Dm = np.zeros(G.shape[1:], G.dtype)
+    def are(a, b):
+        with np.errstate(divide="ignore", invalid="ignore"):
+            v = a * np.log(a / b)
+        return np.where((a == 0) | (b == 0), 0, v)
+    for i in range(nc):
+        for j in range(i + 1, nc):
+            a, b = G[i], G[j]
+            if kind == "are":
+                Dm = Dm + are(a, b)
+            elif kind == "sre":
+                Dm = Dm + (are(a, b) + are(b, a))
+            elif kind == "lp":
+                Dm = Dm + (a - b) ** p
+            else:
+                Dm = Dm + (np.sqrt(a) - np.sqrt(b)) ** 2
+    return Dm.astype(G.dtype)
+
+
+def ldb_costs(DM):
+    """node costs of fitdec! with top_k >= node size (LDB.jl:217-237): sum of DM over the node.  DM (K, n) or (K, n, m)"""
+    DM = np.asarray(DM)
+    if DM.ndim == 2:
+        K, n = DM.shape
+        return np.array([DM[d, j * (n >> d):(j + 1) * (n >> d)].sum() for d in range(K) for j in range(1 << d)], DM.dtype)
+    K, nc_, nr = DM.shape
+    out = []
+    for i in range(1, (4 ** K - 1) // 3 + 1):
+        d = getdepth(i, "quad")
+        r0, c0, rr, cc = quadrange(nr, nc_, i)
+        out.append(DM[d, c0:c0 + cc, r0:r0 + rr].sum())
+    return np.array(out, DM.dtype)

@@ -287,3 +287,55 @@ def test_bb_redundant_and_2d(wx, O, cuda):
     coef = wx.getbasiscoefall(yw, wx.bestbasistreeall(yw, wx.BB()))
     t0 = wx.bestbasistree(yw[0], wx.BB())
     assert torch.equal(coef[0], wx.getbasiscoef(yw[0], t0))
+
+
+# ------------------------------------------------------------------ LDB tree search
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+def test_ldb_energy_map_measures_and_tree(wx, O, cuda, dt):
+    """energy_map(TimeFrequency) / discriminant_measure / node costs / treeselection(:max) (ldb_energymap.jl:109-141,
+    ldb_measures.jl:139-183, LDB.jl:209-240) against the numpy restatement; class labels of mixed types like the reference's"""
+    wt = wx.wavelet("db4")
+    n, N = 128, 90
+    rng = np.random.default_rng(17)
+    t = np.arange(n) / n
+    base = {"a": np.sin(6 * np.pi * t), "b": np.sign(np.sin(14 * np.pi * t)), 3: t * (1 - t) * 8}
+    y = [list(base)[k % 3] for k in rng.integers(0, 3, N)]
+    X = np.stack([base[c] + 0.3 * rng.standard_normal(n) for c in y]).astype(dt)
+    Xw = wx.wpdall(dev(X, cuda), wt)
+    Xh = Xw.cpu().numpy()
+    tol = 1e-12 if dt == np.float64 else 3e-5
+    G = wx.energy_map(Xw, y, wx.TimeFrequency())
+    Gref = O.energy_map_tf(Xh, y)
+    assert G.shape == Gref.shape and rel(G.cpu().numpy(), Gref) <= tol
+    assert abs(float(G[0, 0].sum()) - 1.0) <= (1e-12 if dt == np.float64 else 1e-5)            # level 0 of every class sums to 1
+    for dm, kind, p in ((wx.AsymmetricRelativeEntropy(), "are", 0), (wx.SymmetricRelativeEntropy(), "sre", 0), (wx.LpDistance(2), "lp", 2),
+                        (wx.HellingerDistance(), "hd", 0)):
+        Dm = wx.discriminant_measure(G, dm)
+        Dref = O.discriminant_measure(Gref.astype(np.float64), kind, p)
+        assert rel(Dm.cpu().numpy(), Dref) <= tol * 50, kind
+        G2, DM2, cost, tree = wx.ldb_tree(Xw, y, dm)
+        cref = O.ldb_costs(Dref)
+        assert rel(cost, cref) <= tol * 50, kind
+        assert wx.isvalidtree(X[0], tree)
+        if dt == np.float64:
+            assert np.array_equal(tree, O.tree_select(cref, n, minmax="max")), kind
+    # sharded: per-shard energy sums (same global class list on every shard) add up to the single-shot sums -- the all-reduce
+    e1, _, _, classes = wx.ldb._energy_sums(Xw, y)
+    parts = [wx.ldb._energy_sums(Xw[a:b].contiguous(), y[a:b], classes=classes)[0] for a, b in ((0, 40), (40, N))]
+    assert torch.allclose(parts[0] + parts[1], e1, rtol=1e-12, atol=0)
+
+
+def test_ldb_2d(wx, O, cuda):
+    wt = wx.wavelet("haar")
+    rng = np.random.default_rng(23)
+    y = [int(v) for v in rng.integers(0, 2, 30)]
+    img = np.stack([rng.standard_normal((16, 16)) * (1 + c * np.linspace(0, 2, 16)[None, :]) for c in y])
+    Xw = wx.wpdall(dev(img, cuda), wt, 3)
+    G, DM, cost, tree = wx.ldb_tree(Xw, y, wx.AsymmetricRelativeEntropy())
+    Gref = O.energy_map_tf(Xw.cpu().numpy(), y)
+    assert rel(G.cpu().numpy(), Gref) <= 1e-12
+    Dref = O.discriminant_measure(Gref, "are")
+    assert rel(DM.cpu().numpy(), Dref) <= 1e-10
+    cref = O.ldb_costs(Dref)
+    assert rel(cost, cref) <= 1e-10
+    assert np.array_equal(tree, O.tree_select(cref, 16, 16, minmax="max"))

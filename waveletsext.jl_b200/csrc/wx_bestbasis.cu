@@ -638,6 +638,104 @@ __global__ void __launch_bounds__(kT) scale_k(double *out, const double *in, lon
     if (e < n) out[e] = in[e] * f;
 }
 
+// ---- LDB time-frequency energy map (ldb/ldb_energymap.jl:109-141): per class, per position, sum of squares over the class ----
+// part (ksplit, NC, szK).  labels[k] in [0, nc) on the device; this launch accumulates classes c0 .. c0+NC-1.
+template <typename T, int NC>
+__global__ void __launch_bounds__(kT) energy_tf_part_k(double *part, const T *X, const int *labels, int c0, long szK, long N, long kchunk)
+{
+    constexpr int V = 16 / (int)sizeof(T), U = 4;
+    using VT = typename std::conditional<sizeof(T) == 8, double2, float4>::type;
+    const long e = ((long)blockIdx.x * kT + threadIdx.x) * V;
+    if (e >= szK) return;
+    const long k0 = (long)blockIdx.y * kchunk;
+    long k1 = k0 + kchunk; if (k1 > N) k1 = N;
+    double q[NC][V];
+#pragma unroll
+    for (int c = 0; c < NC; ++c)
+#pragma unroll
+        for (int v = 0; v < V; ++v) q[c][v] = 0.0;
+    const T *p = X + e;
+    long k = k0;
+    auto take = [&](const VT &r, int lab) {
+        const T *rv = reinterpret_cast<const T *>(&r);
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            const double a = (double)rv[v], a2 = a * a;
+#pragma unroll
+            for (int c = 0; c < NC; ++c) q[c][v] += (lab == c0 + c) ? a2 : 0.0;
+        }
+    };
+    for (; k + U <= k1; k += U) {
+        VT r[U]; int lab[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) { r[u] = __ldcs(reinterpret_cast<const VT *>(p + (k + u) * szK)); lab[u] = labels[k + u]; }
+#pragma unroll
+        for (int u = 0; u < U; ++u) take(r[u], lab[u]);
+    }
+    for (; k < k1; ++k) take(__ldcs(reinterpret_cast<const VT *>(p + k * szK)), labels[k]);
+    double *o = part + ((long)blockIdx.y * NC) * szK + e;
+#pragma unroll
+    for (int c = 0; c < NC; ++c)
+#pragma unroll
+        for (int v = 0; v < V; ++v) o[(long)c * szK + v] = q[c][v];
+}
+
+// scalar variant (any szK / alignment)
+template <typename T, int NC>
+__global__ void __launch_bounds__(kT) energy_tf_part_scalar_k(double *part, const T *X, const int *labels, int c0, long szK, long N, long kchunk)
+{
+    const long e = (long)blockIdx.x * kT + threadIdx.x;
+    if (e >= szK) return;
+    const long k0 = (long)blockIdx.y * kchunk;
+    long k1 = k0 + kchunk; if (k1 > N) k1 = N;
+    double q[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) q[c] = 0.0;
+    for (long k = k0; k < k1; ++k) {
+        const double a = (double)X[k * szK + e], a2 = a * a;
+        const int lab = labels[k];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) q[c] += (lab == c0 + c) ? a2 : 0.0;
+    }
+    for (int c = 0; c < NC; ++c) part[((long)blockIdx.y * NC + c) * szK + e] = q[c];
+}
+
+template <int NC>
+__global__ void __launch_bounds__(kT) energy_tf_final_k(double *esum, const double *part, long szK, int ksplit, int nvalid)
+{
+    const long e = (long)blockIdx.x * kT + threadIdx.x;
+    if (e >= szK) return;
+    for (int c = 0; c < nvalid; ++c) {
+        double s = 0.0;
+        for (int ks = 0; ks < ksplit; ++ks) s += part[((long)ks * NC + c) * szK + e];
+        esum[(long)c * szK + e] = s;
+    }
+}
+
+// discriminant_measure(Gamma, dm) ldb/ldb_measures.jl:139-183, 302-325: D[e] = sum over class pairs i<j of dm(p_i, p_j) with
+// p_c = esum[c][e] * inv_norm[c].  kind 0 asymmetric relative entropy, 1 symmetric, 2 Lp distance (p - q)^pw, 3 Hellinger.
+__global__ void __launch_bounds__(kT) ldb_dm_k(double *D, const double *esum, const double *inv_norm, int nc, long szK, int kind, double pw, int elt)
+{
+    const long e = (long)blockIdx.x * kT + threadIdx.x;
+    if (e >= szK) return;
+    double acc = 0.0;
+    for (int i = 0; i < nc; ++i) {
+        double p = esum[(long)i * szK + e] * inv_norm[i];
+        if (elt == 4) p = (double)(float)p;
+        for (int j = i + 1; j < nc; ++j) {
+            double q = esum[(long)j * szK + e] * inv_norm[j];
+            if (elt == 4) q = (double)(float)q;
+            double v;
+            if (kind == 0) v = (p == 0.0 || q == 0.0) ? 0.0 : p * log(p / q);
+            else if (kind == 1) v = (p == 0.0 || q == 0.0) ? 0.0 : p * log(p / q) + q * log(q / p);
+            else if (kind == 2) v = pow(p - q, pw);
+            else { const double t = sqrt(p) - sqrt(q); v = t * t; }
+            acc += v;
+        }
+    }
+    D[e] = acc;
+}
+
 // ---- BB: per-signal best basis (bestbasis/bestbasis_tree.jl:210-256, bestbasis/bestbasis_costs.jl:103-125) ----------------
 // coefcost(x, ::ShannonEntropyCost | ::LogEnergyEntropyCost, nrm): s = (x/nrm)^2 ; -s log s | -log s ; 0 when s == 0
 __device__ __forceinline__ double bb_term(double x, double inv_nrm, int kind)
@@ -968,6 +1066,55 @@ extern "C" {
 
 int wx_bb_costs_f64(double *costs, const double *X, long m, long n, int K, long N, int redundant, int kind, void *s) { return bb_costs_impl<double>(costs, X, m, n, K, N, redundant, kind, (cudaStream_t)s); }
 int wx_bb_costs_f32(double *costs, const float *X, long m, long n, int K, long N, int redundant, int kind, void *s) { return bb_costs_impl<float>(costs, X, m, n, K, N, redundant, kind, (cudaStream_t)s); }
+
+// energy_map(Xw, y, ::TimeFrequency) numerators: esum (nc, szK) device Float64 = per class, per position sum of squares over the
+// LOCAL signals of the class (labels: device int32 in [0, nc)).  The caller all-reduces esum, divides class c by
+// norm_sum_c = sum of esum[c] over the level-0 positions (ldb_energymap.jl:130-136).
+}  // extern "C"
+template <typename T>
+static int energy_tf_impl(double *esum, const T *X, const int *labels, int nc, long szK, long N, cudaStream_t s)
+{
+    WX_REQUIRE(esum && labels && nc >= 1 && szK >= 1 && N >= 0 && (N == 0 || X), "bad arguments");
+    if (N == 0) { WX_CUDA(cudaMemsetAsync(esum, 0, (size_t)nc * szK * sizeof(double), s)); return WX_OK; }
+    WxDev dv; int rc = wx_devinfo(dv); if (rc) return rc;
+    constexpr int NC = 4;
+    constexpr long V = 16 / (long)sizeof(T);
+    const bool vec = szK % V == 0 && (((uintptr_t)X) & 15) == 0;
+    const int ksplit = pick_ksplit(vec ? szK / V : szK, N, dv.sms);
+    const long kchunk = (N + ksplit - 1) / ksplit;
+    double *part; rc = wx_scratch(&part, (size_t)ksplit * NC * szK, s); if (rc) return rc;
+    for (int c0 = 0; c0 < nc; c0 += NC) {
+        if (vec) {
+            dim3 grid((unsigned)((szK / V + kT - 1) / kT), (unsigned)ksplit);
+            energy_tf_part_k<T, NC><<<grid, kT, 0, s>>>(part, X, labels, c0, szK, N, kchunk);
+        } else {
+            dim3 grid((unsigned)((szK + kT - 1) / kT), (unsigned)ksplit);
+            energy_tf_part_scalar_k<T, NC><<<grid, kT, 0, s>>>(part, X, labels, c0, szK, N, kchunk);
+        }
+        WX_LAUNCHED();
+        energy_tf_final_k<NC><<<gridf(szK), kT, 0, s>>>(esum + (long)c0 * szK, part, szK, ksplit, nc - c0 < NC ? nc - c0 : NC);
+        WX_LAUNCHED();
+    }
+    return wx_scratch_free(part, s);
+}
+extern "C" {
+int wx_energy_map_tf_f64(double *esum, const double *X, const int *labels_dev, int nc, long szK, long Nlocal, void *s) { return energy_tf_impl<double>(esum, X, labels_dev, nc, szK, Nlocal, (cudaStream_t)s); }
+int wx_energy_map_tf_f32(double *esum, const float *X, const int *labels_dev, int nc, long szK, long Nlocal, void *s) { return energy_tf_impl<float>(esum, X, labels_dev, nc, szK, Nlocal, (cudaStream_t)s); }
+// discriminant_measure on the (all-reduced) energy sums: D (szK) device; inv_norm (nc) device = 1 / norm_sum_c
+int wx_ldb_discriminant(double *D, const double *esum, const double *inv_norm_dev, int nc, long szK, int kind, double p, int elt, void *stream)
+{
+    WX_REQUIRE(D && esum && inv_norm_dev && nc >= 2 && szK >= 1, "bad arguments");
+    WX_REQUIRE(kind >= 0 && kind <= 3, "unknown discriminant measure %d", kind);
+    ldb_dm_k<<<gridf(szK), kT, 0, (cudaStream_t)stream>>>(D, esum, inv_norm_dev, nc, szK, kind, p, elt);
+    WX_LAUNCHED();
+    return WX_OK;
+}
+// per-node sums of a per-position term (the LDB node costs with top_k >= node size, LDB.jl:217-237): costs HOST
+int wx_node_costs(double *costs_host, const double *term, long m, long n, int K, int redundant, double mult, int elt, void *stream)
+{
+    WX_REQUIRE(costs_host && term && n >= 1 && m >= 0 && K >= 1, "bad arguments");
+    return node_costs_to_host(costs_host, term, m, n, K, redundant, mult, elt, (cudaStream_t)stream);
+}
 
 // bestbasis_treeselection for N cost vectors at once: trees (ntree, N) bytes on the device, costs (nnodes, N) updated in place
 int wx_bb_select(unsigned char *trees, double *costs, long nnodes, long m, long n, long N, int elt, void *stream)
