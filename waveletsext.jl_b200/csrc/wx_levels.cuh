@@ -351,6 +351,55 @@ __device__ __forceinline__ void iwpt_small_level(const T *__restrict__ src, T *_
     }
 }
 
+// one inverse level of the nodes of length P inside a register-resident run of G elements (compile-time wraps)
+template <typename T, int F, int P, int G>
+__device__ __forceinline__ void iwpt_regs_level(const T *v, T *o, const Taps<T> &tp)
+{
+    constexpr int H = P / 2, R = F / 2;
+#pragma unroll
+    for (int nd = 0; nd < G / P; ++nd) {
+        const T *w1 = &v[nd * P], *w2 = &v[nd * P + H];
+#pragma unroll
+        for (int t = 0; t < H; ++t) {
+            T e = tp.g[F - 1] * w1[t];
+            T od = tp.g[F - 2] * w1[t];
+            e = fma(tp.h[1], w2[t], e);
+            od = fma(tp.h[0], w2[t], od);
+#pragma unroll
+            for (int r = 1; r < R; ++r) {
+                e = fma(tp.g[F - 1 - 2 * r], w1[(t - r) & (H - 1)], e);
+                od = fma(tp.g[F - 2 - 2 * r], w1[(t - r) & (H - 1)], od);
+                e = fma(tp.h[2 * r + 1], w2[(t + r) & (H - 1)], e);
+                od = fma(tp.h[2 * r], w2[(t + r) & (H - 1)], od);
+            }
+            o[nd * P + 2 * t] = e;
+            o[nd * P + 2 * t + 1] = od;
+        }
+    }
+}
+
+// the four deepest levels of a complete tree in one pass: a thread owns 16 consecutive elements (= one node of length 16 and
+// everything below it), rebuilds the nodes of length 2, 4, 8 and 16 in registers and writes the run once -- three
+// shared-memory round trips and three barriers fewer than level by level.  n0 must be a multiple of 16.
+template <typename T, int F>
+__device__ __forceinline__ void iwpt_small_levels4(const T *__restrict__ src, T *__restrict__ dst, int n0, const Taps<T> &tp, int tid, int nthreads)
+{
+    using VT = typename WxVec<T>::type;
+    constexpr int V = WxVec<T>::N, G = 16;
+    for (int u = tid; u < n0 / G; u += nthreads) {
+        const int g0 = wx_swz_chunk((u * G) / V) * V;     // 16 elements = an aligned run of 8 (F64) / 4 (F32) chunks
+        T v[G], o[G];
+#pragma unroll
+        for (int c = 0; c < G / V; ++c) wx_unpack(&v[c * V], *reinterpret_cast<const VT *>(src + (g0 ^ (c * V))));
+        iwpt_regs_level<T, F, 2, G>(v, o, tp);
+        iwpt_regs_level<T, F, 4, G>(o, v, tp);
+        iwpt_regs_level<T, F, 8, G>(v, o, tp);
+        iwpt_regs_level<T, F, 16, G>(o, v, tp);
+#pragma unroll
+        for (int c = 0; c < G / V; ++c) *reinterpret_cast<VT *>(dst + (g0 ^ (c * V))) = wx_pack(&v[c * V]);
+    }
+}
+
 // any even node length, one output pair per thread
 template <typename T, int F, bool TREE>
 __device__ __forceinline__ void iwpt_generic_level(const T *__restrict__ src, T *__restrict__ dst, int n0, int p, const Taps<T> &tp, int tid,

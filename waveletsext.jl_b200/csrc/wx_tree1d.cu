@@ -49,7 +49,15 @@ __global__ void __launch_bounds__(256) tree1d_fused_k(T *__restrict__ y, const T
         __syncthreads();
         // ---- levels ---------------------------------------------------------------------------------
         T *a = buf0, *b = buf1;
-        for (int q = 0; q < nl; ++q) {
+        int q0 = 0;
+        if (INV && !TREE && nl >= 4 && (n0 >> (nl - 1)) == 2 && n0 % 16 == 0) {
+            // complete tree down to nodes of length 2: the four deepest levels in registers
+            iwpt_small_levels4<T, F>(a, b, n0, tp, tid, nthreads);
+            __syncthreads();
+            T *t = a; a = b; b = t;
+            q0 = 4;
+        }
+        for (int q = q0; q < nl; ++q) {
             const int l = INV ? nl - 1 - q : q;       // level relative to the staged node
             const int d = d0 + l;
             const long first = ((1L << d) - 1) + (j0 << l);               // 0-based heap position of the node's first depth-d descendant
