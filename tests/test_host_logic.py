@@ -137,3 +137,41 @@ def test_no_cpu_fallback(wx):
         wx.swpdall(torch.zeros((2, 8), dtype=torch.float64), wt, 2)
     with pytest.raises(TypeError):
         wx.wpdall(np.zeros((2, 8)), wt)
+
+
+def test_isvalidtree_matches_the_definition(wx):
+    """vectorised isvalidtree == the definition (no split node below an unsplit one), binary and quad, valid and invalid"""
+    import numpy as np
+    rng = np.random.default_rng(0)
+
+    def slow(tree, ar):
+        nb = len(tree)
+        for i in range(1, nb + 1):
+            if tree[i - 1]:
+                continue
+            for c in range(ar):
+                ch = 2 * i + c if ar == 2 else 4 * i - 2 + c
+                if ch <= nb and tree[ch - 1]:
+                    return False
+        return True
+
+    for _ in range(200):
+        t = rng.random(63) < 0.6
+        assert wx.isvalidtree(64, t) == slow(t, 2)
+        q = rng.random(21) < 0.6
+        assert wx.isvalidtree((8, 8), q) == slow(q, 4)
+    assert wx.isvalidtree(64, wx.maketree(64, 6, "full")) and wx.isvalidtree((8, 8), wx.maketree(8, 8, 3, "dwt"))
+    assert not wx.isvalidtree(64, np.ones(62, bool))                      # wrong length
+
+
+def test_ldb_class_numbering_and_bb_types(wx):
+    """host pieces of the f-1 / f-2 rows: class labels are numbered in order of first appearance (Julia unique) unless a global
+    class list is given (needed when the batch is sharded); BB option types mirror the reference's defaults"""
+    import numpy as np
+    import torch
+    lab, classes = wx.ldb._labels(["b", "a", "b", 3, "a"], torch.device("cpu"))
+    assert classes == ["b", "a", 3] and lab.tolist() == [0, 1, 0, 2, 1]
+    lab, classes = wx.ldb._labels(["a", 3], torch.device("cpu"), classes=["b", "a", 3])
+    assert lab.tolist() == [1, 2] and classes == ["b", "a", 3]
+    assert isinstance(wx.BB().cost, wx.ShannonEntropyCost) and wx.BB().redundant is False
+    assert wx.LpDistance().p == 2 and wx.JBB().cost.p == 2 and wx.NormCost().p == 1
