@@ -51,7 +51,7 @@ class HellingerDistance:
 def _labels(y, device, classes=None):
     """class index of every signal.  classes = None: Julia's unique(y), i.e. order of first appearance in THIS label list; when the
     batch is sharded over ranks pass the global class list so that every rank numbers the classes identically."""
-    ylist = np.asarray(y).tolist()
+    ylist = y.tolist() if isinstance(y, (np.ndarray, torch.Tensor)) else list(y)
     if classes is None:
         classes = list(dict.fromkeys(ylist))
     index = {v: i for i, v in enumerate(classes)}
