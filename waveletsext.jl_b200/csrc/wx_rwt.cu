@@ -8,6 +8,7 @@
 //            batch loops swt/swt_all.jl, acwt/acwt_all.jl.
 #include "wx_steps.cuh"
 #include <vector>
+#include <cstdlib>
 
 template <typename T>
 int wx_rwpd1d_fused(int ac, int wpt, T *xw, const T *x, long n, int L, long N, const Taps<T> &t, cudaStream_t s, int *done);
@@ -15,6 +16,10 @@ template <typename T>
 int wx_rdwt1d_fused(int ac, T *xw, const T *x, long n, int L, long N, const Taps<T> &t, cudaStream_t s, int *done);
 template <typename T> int wx_iac_tree_sum(T *x, const T *xw, long n, long ncols, long c0, int L, long N, cudaStream_t s);
 template <typename T> int wx_iac_chain_sum(T *x, const T *xw, long n, int L, long N, cudaStream_t s);
+// fused 2-D a-trous step (wx_rwt2d.cu)
+template <typename T>
+int wx_rdwt2d_fused(int ac, T *w1, long wns, long wis, long wq, const T *v, long vns, long vis, long m, long n, long nodes, long Nc, int d,
+                    const Taps<T> &t, cudaStream_t s, bool *handled);
 // fused average-based stationary inverses (wx_irwpd_fused.cu)
 template <typename T> int wx_irwpd_avg_fused(T *x, const T *xw, long in_sig, long in_col0, long n, int Lt, long N, const Taps<T> &t, cudaStream_t s, bool *handled);
 template <typename T> int wx_irdwt_chain_depth(const T *x, const T *xw, long n, int L, long N, const Taps<T> &t, int *dhi);
@@ -33,6 +38,21 @@ int fwd2d(int ac, T *w1, long wns, long wis, long wq /*slice distance between w1
           long nodes, long Nc, int d, const Taps<T> &t, cudaStream_t s)
 {
     const long img = m * n;
+    {   // fused tile kernel: one launch per depth.  When the children overwrite their parents (swpt! / sdwt! layouts) the
+        // parents are first copied to the scratch, like the reference's `copy(xw[:,:,j])` (SWT.jl:150,498).
+        const T *v_hi = v + (nodes - 1) * vns + img, *w_hi = w1 + (nodes - 1) * wns + 3 * wq + img;
+        const bool disjoint = (vis == wis || Nc == 1) && (v_hi <= w1 || w_hi <= v);
+        bool handled = false;
+        int rc0 = WX_OK;
+        static const bool off = getenv("WX_B200_NO_FUSED_RWT2D") != nullptr;
+        if (off) { /* per-pass path below */ }
+        else if (disjoint) rc0 = wx_rdwt2d_fused<T>(ac, w1, wns, wis, wq, v, vns, vis, m, n, nodes, Nc, d, t, s, &handled);
+        else {
+            rc0 = wx_launch_copy<T>(View<T>{temp, 1, img, img * nodes, 0}, View<const T>{v, 1, vns, vis, 0}, img, Batch{nodes, Nc, 1, false}, s);
+            if (!rc0) rc0 = wx_rdwt2d_fused<T>(ac, w1, wns, wis, wq, temp, img, img * nodes, m, n, nodes, Nc, d, t, s, &handled);
+        }
+        if (rc0 || handled) return rc0;
+    }
     // temp (m, n, 2, nodes, Nc)
     View<T> t1{temp, 1, m, 2 * img, 2 * img * nodes}, t2{temp + img, 1, m, 2 * img, 2 * img * nodes};
     int rc = wx_launch_rdwt_step<T>(ac, t1, t2, View<const T>{v, 1, m, vns, vis}, m, d, Batch{n, nodes, Nc, false}, t, s);
