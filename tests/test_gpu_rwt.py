@@ -167,6 +167,35 @@ def test_redundant_2d(wx, O, cuda, dt, ac):
             assert relerr(wx.isdwtall(outs["dwt"], wt, s).cpu().numpy(), want) <= TOL[dt] * 20
 
 
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+@pytest.mark.parametrize("ac", [False, True])
+@pytest.mark.parametrize("name,nr,nc,L", [("haar", 64, 32, 3), ("db4", 96, 64, 2), ("db2", 128, 128, 3), ("db4", 32, 160, 1)])
+def test_redundant_2d_tiles(wx, O, cuda, dt, ac, name, nr, nc, L):
+    """images larger than a tile: the fused 2-D a-trous step (halo patches, shifted detail outputs, periodic wrap at the image
+    border, parent copies for the in-place swpt / sdwt layouts) and the per-pass path beyond the halo threshold"""
+    wt = wx.wavelet(name)
+    x = np.random.default_rng(nr + nc + L).standard_normal((2, nc, nr)).astype(dt)
+    xd = dev(x, cuda)
+    if ac:
+        P, Q = acpair(wx, wt)
+        fw = {"dwt": (wx.acdwtall, lambda a: O.acdwt(a, L, P, Q)), "wpt": (wx.acwptall, lambda a: O.acwpt(a, L, P, Q)),
+              "wpd": (wx.acwpdall, lambda a: O.acwpd(a, L, P, Q))}
+    else:
+        h, g = pair(wx, wt)
+        fw = {"dwt": (wx.sdwtall, lambda a: O.sdwt(a, L, h, g)), "wpt": (wx.swptall, lambda a: O.swpt(a, L, h, g)),
+              "wpd": (wx.swpdall, lambda a: O.swpd(a, L, h, g))}
+    for k, (f, of) in fw.items():
+        out = f(xd, wt, L)
+        ref = np.stack([of(x[i]) for i in range(2)])
+        assert out.shape == ref.shape, k
+        assert relerr(out.cpu().numpy(), ref) <= TOL[dt], k
+    rt = 1e-10 if dt == np.float64 else 3e-4
+    if ac:
+        assert relerr(wx.iacwptall(wx.acwptall(xd, wt, L), wt).cpu().numpy(), x) <= rt
+    else:
+        assert relerr(wx.iswptall(wx.swptall(xd, wt, L), wt).cpu().numpy(), x) <= rt
+
+
 def test_swt_argument_errors(wx, cuda):
     """test/transforms.jl:340-341,352-353: isdwtall / iswptall with sm = 12 on L = 3 tables -> AssertionError"""
     wt = wx.wavelet("db4")
