@@ -9,7 +9,9 @@
 template <typename T, int F>
 struct WpdCfg {
     static constexpr int V = WxVec<T>::N;                              // elements per 16 B chunk
-    static constexpr int K = 2 * V;                                    // output pairs per window
+    // output pairs per window.  K = 4V (thread stride of one 128-byte row, fully conflict-free window loads) was measured in
+    // round 1: same speed within noise (the kernel is HBM-bound, 5.21 vs 5.13 ms) at 78 instead of 54 registers -- kept at 2V.
+    static constexpr int K = 2 * V;
     static constexpr int S = (((F - 2) / 2) + V - 1) / V * V;          // high-pass look-ahead (multiple of V)
     static constexpr int W = 2 * S + 2 * K;                            // window length (elements)
 };
@@ -211,6 +213,8 @@ __device__ __forceinline__ void wpd_level(const T *__restrict__ a, T *__restrict
         wpd_small_level<T, F, 4, GST, TREE>(a, b, grow, n0, last, tp, tid, nthreads, tmk);
     } else if (p == 8) {
         wpd_small_level<T, F, 8, GST, TREE>(a, b, grow, n0, last, tp, tid, nthreads, tmk);
+    } else if (p == 16 && V == 4) {
+        wpd_small_level<T, F, 16, GST, TREE>(a, b, grow, n0, last, tp, tid, nthreads, tmk);
     } else {
         wpd_generic_level<T, F, GST, TREE>(a, b, grow, n0, p, last, tp, tid, nthreads, tmk);
     }
