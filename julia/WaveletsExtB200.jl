@@ -187,4 +187,45 @@ end
 Wavelets.Threshold.bestbasistree(X::B200Array{T,3}, method::JBB; kw...) where T =
     bestbasis_treeselection(tree_costs(X, method; kw...), size(X, 1))
 
+# tree_costs(X, ::LSDB)   bestbasis/bestbasis_tree.jl:104-124.  Single GPU shown; across ranks all-gather rows 1-4 of `stats` and
+# the two rows of `logsum` and combine them with wx_dd_sum, all-reduce rows 5-6 (min / max) and `counts` (INTEGRATION.md section 4).
+function tree_costs(X::B200Array{T,3}, method::LSDB) where T
+    n, K, N = size(X)
+    szK = n * K
+    stats = B200Array{Float64,2}((szK, 7); dev=X.dev)
+    x0 = Vector{T}(undef, szK)                                  # row 0 of stats = the first signal of the (global) batch, as Float64
+    check(ccall((:wx_d2h, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Csize_t, Ptr{Cvoid}), x0, X.ptr, szK * sizeof(T), C_NULL))
+    check(ccall((:wx_stream_sync, LIB), Cint, (Ptr{Cvoid},), C_NULL))
+    check(ccall((:wx_h2d, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Csize_t, Ptr{Cvoid}), stats.ptr, Float64.(x0), szK * 8, C_NULL))
+    sfx_ = sfx(T)
+    check(ccall((Symbol("wx_lsdb_pass1_", sfx_), LIB), Cint, (Ptr{Cdouble}, Ptr{T}, Clong, Clong, Ptr{Cvoid}), stats.ptr, X.ptr, szK, N, C_NULL))
+    npts = Ref{Clong}(0)
+    check(ccall((:wx_lsdb_grid, LIB), Cint, (Clong, Ptr{Clong}, Ptr{Clong}, Ptr{Clong}), N, C_NULL, C_NULL, npts))
+    counts = B200Array{Float64,2}((szK, npts[]); dev=X.dev)
+    check(ccall((Symbol("wx_lsdb_pass2_", sfx_), LIB), Cint, (Ptr{Cdouble}, Ptr{Cdouble}, Ptr{T}, Clong, Clong, Clong, Ptr{Cvoid}),
+                counts.ptr, stats.ptr, X.ptr, szK, N, N, C_NULL))
+    logsum = B200Array{Float64,2}((szK, 2); dev=X.dev)
+    check(ccall((Symbol("wx_lsdb_pass3_", sfx_), LIB), Cint, (Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{T}, Clong, Clong, Clong, Ptr{Cvoid}),
+                logsum.ptr, counts.ptr, stats.ptr, X.ptr, szK, N, N, C_NULL))
+    costs = Vector{Float64}(undef, method.redundant ? K : (1 << K) - 1)
+    check(ccall((:wx_lsdb_costs, LIB), Cint, (Ptr{Cdouble}, Ptr{Cdouble}, Clong, Clong, Clong, Cint, Cint, Ptr{Cvoid}),
+                costs, logsum.ptr, N, 0, n, K, method.redundant, C_NULL))
+    return T.(costs)
+end
+
+# bestbasistreeall(X, ::BB)   BestBasis.jl:253-262 : per-signal costs and the bottom-up selection both on the device;
+# returns the BitMatrix (n-1, N) of the reference
+function bestbasistreeall(X::B200Array{T,3}, method::WaveletsExt.BestBasis.BB) where T
+    n, K, N = size(X)
+    nn = method.redundant ? K : (1 << K) - 1
+    costs = B200Array{Float64,2}((nn, N); dev=X.dev)
+    kind = method.cost isa WaveletsExt.BestBasis.ShannonEntropyCost ? 0 : 1
+    check(ccall((Symbol("wx_bb_costs_", sfx(T)), LIB), Cint, (Ptr{Cdouble}, Ptr{T}, Clong, Clong, Cint, Clong, Cint, Cint, Ptr{Cvoid}),
+                costs.ptr, X.ptr, 0, n, K, N, method.redundant, kind, C_NULL))
+    trees = B200Array{UInt8,2}((n - 1, N); dev=X.dev)
+    check(ccall((:wx_bb_select, LIB), Cint, (Ptr{UInt8}, Ptr{Cdouble}, Clong, Clong, Clong, Clong, Cint, Ptr{Cvoid}),
+                trees.ptr, costs.ptr, nn, 0, n, N, sizeof(T), C_NULL))
+    return BitMatrix(Array(trees) .!= 0)
+end
+
 end # module

@@ -21,41 +21,35 @@ constexpr int kT = 256;
 static inline unsigned gridf(long total) { return (unsigned)((total + kT - 1) / kT); }
 
 // ---- stage 1: per-position partial reductions over a slice of the batch ----------------------------------
-// grid.x covers positions (kT per block), grid.y = ksplit.  Partial results go to part[ks][q][e].
-template <typename T, int MODE>   // MODE 0: sum,sumsq   MODE 1: shifted sum, shifted sumsq, min, max
-__global__ void __launch_bounds__(kT) moments_part_k(double *part, const T *X, const double *shift, long szK, long N, long kchunk)
+// grid.x covers positions (kT per block), grid.y = ksplit.  Partial results (sum, sum of squares) go to part[ks][q][e].
+template <typename T>
+__global__ void __launch_bounds__(kT) moments_part_k(double *part, const T *X, long szK, long N, long kchunk)
 {
     const long e = (long)blockIdx.x * kT + threadIdx.x;
     if (e >= szK) return;
     const long k0 = (long)blockIdx.y * kchunk;
     long k1 = k0 + kchunk; if (k1 > N) k1 = N;
-    const double c = (MODE == 1) ? shift[e] : 0.0;
     double s0 = 0, s1 = 0, s2 = 0, s3 = 0, q0 = 0, q1 = 0, q2 = 0, q3 = 0;
-    double mn = INFINITY, mx = -INFINITY;
     long k = k0;
     const T *p = X + e;
     for (; k + 4 <= k1; k += 4) {
-        double a = (double)p[k * szK] - c, b = (double)p[(k + 1) * szK] - c, cc = (double)p[(k + 2) * szK] - c, d = (double)p[(k + 3) * szK] - c;
+        const double a = (double)p[k * szK], b = (double)p[(k + 1) * szK], cc = (double)p[(k + 2) * szK], d = (double)p[(k + 3) * szK];
         s0 += a; s1 += b; s2 += cc; s3 += d;
         q0 = fma(a, a, q0); q1 = fma(b, b, q1); q2 = fma(cc, cc, q2); q3 = fma(d, d, q3);
-        if (MODE == 1) { mn = fmin(mn, fmin(fmin(a, b), fmin(cc, d))); mx = fmax(mx, fmax(fmax(a, b), fmax(cc, d))); }
     }
     for (; k < k1; ++k) {
-        double a = (double)p[k * szK] - c;
+        const double a = (double)p[k * szK];
         s0 += a; q0 = fma(a, a, q0);
-        if (MODE == 1) { mn = fmin(mn, a); mx = fmax(mx, a); }
     }
-    const long ks = blockIdx.y, nq = (MODE == 1) ? 4 : 2;
-    double *o = part + (ks * nq) * szK + e;
+    double *o = part + ((long)blockIdx.y * 2) * szK + e;
     o[0] = (s0 + s1) + (s2 + s3);
     o[szK] = (q0 + q1) + (q2 + q3);
-    if (MODE == 1) { o[2 * szK] = mn + c; o[3 * szK] = mx + c; }
 }
 
 // vectorised variant: a thread owns V = 16/sizeof(T) consecutive positions (128-bit loads), U signals in flight per thread.
 // Per position the batch slice is accumulated in four interleaved partial sums (signal index mod 4), like the scalar kernel.
-template <typename T, int MODE>
-__global__ void __launch_bounds__(kT) moments_part_vec_k(double *part, const T *X, const double *shift, long szK, long N, long kchunk)
+template <typename T>
+__global__ void __launch_bounds__(kT) moments_part_vec_k(double *part, const T *X, long szK, long N, long kchunk)
 {
     constexpr int V = 16 / (int)sizeof(T), U = 8;
     using VT = typename std::conditional<sizeof(T) == 8, double2, float4>::type;
@@ -63,14 +57,11 @@ __global__ void __launch_bounds__(kT) moments_part_vec_k(double *part, const T *
     if (e >= szK) return;
     const long k0 = (long)blockIdx.y * kchunk;
     long k1 = k0 + kchunk; if (k1 > N) k1 = N;
-    double c[V], s[4][V], q[4][V], mn[V], mx[V];
+    double s[4][V], q[4][V];
 #pragma unroll
-    for (int v = 0; v < V; ++v) {
-        c[v] = (MODE == 1) ? shift[e + v] : 0.0;
-        mn[v] = INFINITY; mx[v] = -INFINITY;
+    for (int v = 0; v < V; ++v)
 #pragma unroll
         for (int a = 0; a < 4; ++a) { s[a][v] = 0; q[a][v] = 0; }
-    }
     const T *p = X + e;
     long k = k0;
     for (; k + U <= k1; k += U) {
@@ -82,10 +73,9 @@ __global__ void __launch_bounds__(kT) moments_part_vec_k(double *part, const T *
             const T *rv = reinterpret_cast<const T *>(&r[u]);
 #pragma unroll
             for (int v = 0; v < V; ++v) {
-                const double a = (double)rv[v] - c[v];
+                const double a = (double)rv[v];
                 s[u & 3][v] += a;
                 q[u & 3][v] = fma(a, a, q[u & 3][v]);
-                if (MODE == 1) { mn[v] = fmin(mn[v], a); mx[v] = fmax(mx[v], a); }
             }
         }
     }
@@ -94,36 +84,29 @@ __global__ void __launch_bounds__(kT) moments_part_vec_k(double *part, const T *
         const T *rv = reinterpret_cast<const T *>(&r);
 #pragma unroll
         for (int v = 0; v < V; ++v) {
-            const double a = (double)rv[v] - c[v];
+            const double a = (double)rv[v];
             s[0][v] += a; q[0][v] = fma(a, a, q[0][v]);
-            if (MODE == 1) { mn[v] = fmin(mn[v], a); mx[v] = fmax(mx[v], a); }
         }
     }
-    const long ks = blockIdx.y, nq = (MODE == 1) ? 4 : 2;
-    double *o = part + (ks * nq) * szK + e;
+    double *o = part + ((long)blockIdx.y * 2) * szK + e;
 #pragma unroll
     for (int v = 0; v < V; ++v) {
         o[v] = (s[0][v] + s[1][v]) + (s[2][v] + s[3][v]);
         o[szK + v] = (q[0][v] + q[1][v]) + (q[2][v] + q[3][v]);
-        if (MODE == 1) { o[2 * szK + v] = mn[v] + c[v]; o[3 * szK + v] = mx[v] + c[v]; }
     }
 }
 
 // stage 2: combine the ksplit partials in index order
-template <int MODE>
-__global__ void __launch_bounds__(kT) moments_final_k(double *o0, double *o1, double *o2, double *o3, const double *part, long szK, int ksplit)
+__global__ void __launch_bounds__(kT) moments_final_k(double *o0, double *o1, const double *part, long szK, int ksplit)
 {
     const long e = (long)blockIdx.x * kT + threadIdx.x;
     if (e >= szK) return;
-    const long nq = (MODE == 1) ? 4 : 2;
-    double s = 0, q = 0, mn = INFINITY, mx = -INFINITY;
+    double s = 0, q = 0;
     for (int ks = 0; ks < ksplit; ++ks) {
-        const double *p = part + ((long)ks * nq) * szK + e;
+        const double *p = part + ((long)ks * 2) * szK + e;
         s += p[0]; q += p[szK];
-        if (MODE == 1) { mn = fmin(mn, p[2 * szK]); mx = fmax(mx, p[3 * szK]); }
     }
     o0[e] = s; o1[e] = q;
-    if (MODE == 1) { o2[e] = mn; o3[e] = mx; }
 }
 
 // ---- double-double accumulation (error-free transformations) ------------------------------------------------
@@ -240,27 +223,26 @@ static int pick_ksplit(long szK, long N, int sms)
     return (int)ks;
 }
 
-template <typename T, int MODE>
-int moments(double *o0, double *o1, double *o2, double *o3, const T *X, const double *shift, long szK, long N, cudaStream_t s)
+template <typename T>
+int moments(double *o0, double *o1, const T *X, long szK, long N, cudaStream_t s)
 {
     WX_REQUIRE(szK >= 1 && N >= 0, "bad sizes");
     WX_REQUIRE(o0 && o1 && (N == 0 || X), "null pointer");
     WxDev dv; int rc = wx_devinfo(dv); if (rc) return rc;
-    const bool vec = szK % (16 / (long)sizeof(T)) == 0 && (((uintptr_t)X) & 15) == 0;
-    const int ksplit = N > 0 ? pick_ksplit(vec ? szK / (16 / (long)sizeof(T)) : szK, N, dv.sms) : 1;
-    const long kchunk = N > 0 ? (N + ksplit - 1) / ksplit : 1;
-    const long nq = (MODE == 1) ? 4 : 2;
-    double *part; rc = wx_scratch(&part, (size_t)ksplit * nq * szK, s); if (rc) return rc;
     constexpr long V = 16 / (long)sizeof(T);
-    if (szK % V == 0 && (((uintptr_t)X) & 15) == 0) {
+    const bool vec = szK % V == 0 && (((uintptr_t)X) & 15) == 0;
+    const int ksplit = N > 0 ? pick_ksplit(vec ? szK / V : szK, N, dv.sms) : 1;
+    const long kchunk = N > 0 ? (N + ksplit - 1) / ksplit : 1;
+    double *part; rc = wx_scratch(&part, (size_t)ksplit * 2 * szK, s); if (rc) return rc;
+    if (vec) {
         dim3 grid((unsigned)((szK / V + kT - 1) / kT), (unsigned)ksplit);
-        moments_part_vec_k<T, MODE><<<grid, kT, 0, s>>>(part, X, shift, szK, N, kchunk);
+        moments_part_vec_k<T><<<grid, kT, 0, s>>>(part, X, szK, N, kchunk);
     } else {
         dim3 grid((unsigned)((szK + kT - 1) / kT), (unsigned)ksplit);
-        moments_part_k<T, MODE><<<grid, kT, 0, s>>>(part, X, shift, szK, N, kchunk);
+        moments_part_k<T><<<grid, kT, 0, s>>>(part, X, szK, N, kchunk);
     }
     WX_LAUNCHED();
-    moments_final_k<MODE><<<gridf(szK), kT, 0, s>>>(o0, o1, o2, o3, part, szK, ksplit);
+    moments_final_k<<<gridf(szK), kT, 0, s>>>(o0, o1, part, szK, ksplit);
     WX_LAUNCHED();
     return wx_scratch_free(part, s);
 }
@@ -540,15 +522,6 @@ __global__ void __launch_bounds__(kL * kH) lsdb_logpdf_smem_k(double *part, cons
     dd_norm(acc, accl);
     double *o = part + ((long)(blockIdx.y * kH + kh) * 2) * szK + e;
     o[0] = acc; o[szK] = accl;
-}
-
-__global__ void __launch_bounds__(kT) sum_parts_k(double *out, const double *part, long szK, int ksplit)
-{
-    const long e = (long)blockIdx.x * kT + threadIdx.x;
-    if (e >= szK) return;
-    double s = 0.0;
-    for (int ks = 0; ks < ksplit; ++ks) s += part[(long)ks * szK + e];
-    out[e] = s;
 }
 
 template <typename T>
@@ -917,11 +890,11 @@ extern "C" {
 
 int wx_jbb_moments_f64(double *sum, double *sumsq, const double *X, long szK, long Nlocal, void *stream)
 {
-    return moments<double, 0>(sum, sumsq, nullptr, nullptr, X, nullptr, szK, Nlocal, (cudaStream_t)stream);
+    return moments<double>(sum, sumsq, X, szK, Nlocal, (cudaStream_t)stream);
 }
 int wx_jbb_moments_f32(double *sum, double *sumsq, const float *X, long szK, long Nlocal, void *stream)
 {
-    return moments<float, 0>(sum, sumsq, nullptr, nullptr, X, nullptr, szK, Nlocal, (cudaStream_t)stream);
+    return moments<float>(sum, sumsq, X, szK, Nlocal, (cudaStream_t)stream);
 }
 
 int wx_jbb_costs(double *costs_host, const double *sum, const double *sumsq, long Ntotal, long m, long n, int K, int redundant, int cost_kind,
