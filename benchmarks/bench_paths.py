@@ -203,6 +203,33 @@ def main():
             report("acwpdall2d_f64", ms, nl, es * m * n2 * N2 * (nsl + 1), m * n2 * N2, "GPixels_per_s")
             del xi
             torch.cuda.empty_cache()
+    # the paper's pipeline end to end from HOST buffers (paper/paper.md:100-118): x (pinned host) -> H2D -> wpdall -> bestbasistree(JBB)
+    # -> getbasiscoefall -> D2H of the best-basis coefficients.  The 13x larger packet table never crosses PCIe.
+    if want("pipeline_host"):
+        import time
+        n, N, L = 4096, int(65536 * a.scale), 12
+        wt = wx.wavelet("db4")
+        xh = torch.randn((N, n), dtype=torch.float64).pin_memory()
+        ch = torch.empty((N, n), dtype=torch.float64).pin_memory()
+        y = torch.empty((N, L + 1, n), dtype=torch.float64, device=dev)
+
+        def run():
+            xd = xh.to(dev, non_blocking=True)
+            wx.dwt._wpd_batch(xd, wt, L, y)
+            tree = wx.bestbasistree(y, wx.JBB())
+            ch.copy_(wx.getbasiscoefall(y, tree), non_blocking=True)
+            torch.cuda.synchronize()
+            return tree
+        run()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            tree = run()
+        el = (time.perf_counter() - t0) / 3
+        print(json.dumps({"path": "pipeline_host_wpd_jbb_basiscoef_f64", "ms": round(el * 1e3, 3), "GSamples_per_s": round(n * N / el / 1e9, 3),
+                          "h2d_bytes": 8 * n * N, "d2h_bytes": 8 * n * N, "tree_nodes": int(tree.sum()),
+                          "timer": "host wall clock, pinned host buffers, copies inside the timed region"}), flush=True)
+        del xh, ch, y
+        torch.cuda.empty_cache()
     # config 5: JBB / LSDB best basis + getbasiscoefall + iwptall on 131072 signals x 1024 per GPU (1M over 8 GPUs)
     n, N, L = 1024, int(131072 * a.scale), 10
     if want("jbb") or want("lsdb") or want("basis_iwpt") or want("bb"):
