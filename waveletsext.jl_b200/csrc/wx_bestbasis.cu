@@ -860,7 +860,6 @@ __global__ void __launch_bounds__(kT) gather_multi_k(T *out, const T *Xw, long m
     const unsigned char *t = trees + k * ntree;
     int d = 0;
     if (m == 0) {
-        const int lgn = ilog2d(n);                                    // n is a power-of-two multiple at every split level
         long idx = 1;
         while (idx <= ntree && t[idx - 1] && d < K - 1) {
             const long p = n >> (d + 1);                                  // child length
@@ -868,7 +867,6 @@ __global__ void __launch_bounds__(kT) gather_multi_k(T *out, const T *Xw, long m
             idx = 2 * idx + ((e - j * 2 * p) >= p ? 1 : 0);
             ++d;
         }
-        (void)lgn;
     } else {
         const long r = e % m, c = e / m;
         long idx = 1, r0 = 0, c0 = 0, nr = m, nc = n;

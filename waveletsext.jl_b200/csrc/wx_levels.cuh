@@ -295,7 +295,6 @@ __device__ __forceinline__ void iwpt_wide_level(const T *__restrict__ src, T *__
         T a[W], b[W];
 #pragma unroll
         for (int c = 0; c < W / V; ++c) {
-            constexpr int dummy = 0; (void)dummy;
             const int pa = GA * K - S + c * V;           // element position of this chunk relative to the first w1 group
             const int pb = c * V;
             wx_unpack(&a[c * V], *reinterpret_cast<const VT *>(src + (ga[pa / K] ^ (pa % K))));

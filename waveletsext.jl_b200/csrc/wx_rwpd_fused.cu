@@ -103,7 +103,7 @@ __device__ __forceinline__ long rw_col(int wpt, int L, int d, long idx) { return
 // idx << (L - dend) (swpt!'s in-place order, SWT.jl:454-470).
 template <typename T, int F, int AC>
 __global__ void __launch_bounds__(256) rwpd_dfs_k(T *__restrict__ xw, const T *__restrict__ x, int n, long ncols, int dstart, int dend, int L,
-                                                 int wpt, long items, Taps<T> tp)
+                                                 int wpt, int chain, long items, Taps<T> tp)
 {
     extern __shared__ __align__(128) unsigned char wx_rw_smem[];
     __shared__ __align__(8) unsigned long long bar;
@@ -124,17 +124,51 @@ __global__ void __launch_bounds__(256) rwpd_dfs_k(T *__restrict__ xw, const T *_
         const long k = item >> dstart;
         const long j0 = item & ((1L << dstart) - 1);
         T *xk = xw + k * ncols * n;
-        const T *src = (dstart == 0) ? (x + k * n) : (xk + rw_col(wpt, L, dstart, j0) * n);
-        if (tid == 0) {
-            wx_bulk_wait_read0();                                      // stores of the previous item have released smem
-            wx_mbar_expect_tx(&bar, nbytes);
-            wx_bulk_load_1d(bufs, src, nbytes, &bar);
-        }
-        wx_mbar_wait(&bar, parity);
-        parity ^= 1;
-        if (dstart == 0 && !wpt && tid == 0) {                         // xw[:,1] = x    SWT.jl:857
-            wx_bulk_store_1d(xk, bufs, nbytes);
-            wx_bulk_commit();
+        if (chain) {
+            // One launch for the whole tree: the item rebuilds its depth-dstart node from x by walking the dstart ancestors on
+            // its path (dstart single-child passes, ping-pong between the two leaf buffers, last one into bufs[0]).  An ancestor
+            // is stored by the item that is its leftmost descendant, column 0 (= x) by item 0 of the signal.
+            T *cur = lb0;
+            if (tid == 0) {
+                wx_bulk_wait_read0();
+                wx_mbar_expect_tx(&bar, nbytes);
+                wx_bulk_load_1d(cur, x + k * n, nbytes, &bar);
+            }
+            wx_mbar_wait(&bar, parity);
+            parity ^= 1;
+            if (j0 == 0 && !wpt && tid == 0) {                         // xw[:,1] = x    SWT.jl:857
+                wx_bulk_store_1d(xk, cur, nbytes);
+                wx_bulk_commit();
+            }
+            for (int d = 0; d < dstart; ++d) {
+                T *dst = (d == dstart - 1) ? bufs : (cur == lb0 ? lb1 : lb0);
+                const long anc = j0 >> (dstart - 1 - d);               // index of the path node of depth d+1
+                if (tid == 0) wx_bulk_wait_read0();                    // dst may still be feeding the store issued two passes ago
+                __syncthreads();
+                if (anc & 1) rw_pass1<T, F, AC, 1>(cur, dst, n, d, tp, tid, nthr);
+                else         rw_pass1<T, F, AC, 0>(cur, dst, n, d, tp, tid, nthr);
+                wx_fence_proxy_async();
+                __syncthreads();
+                const bool mine = (j0 & ((1L << (dstart - 1 - d)) - 1)) == 0;      // leftmost descendant of that node
+                if (tid == 0 && !wpt && mine) {
+                    wx_bulk_store_1d(xk + rw_col(0, L, d + 1, anc) * n, dst, nbytes);
+                    wx_bulk_commit();
+                }
+                cur = dst;
+            }
+        } else {
+            const T *src = (dstart == 0) ? (x + k * n) : (xk + rw_col(wpt, L, dstart, j0) * n);
+            if (tid == 0) {
+                wx_bulk_wait_read0();                                  // stores of the previous item have released smem
+                wx_mbar_expect_tx(&bar, nbytes);
+                wx_bulk_load_1d(bufs, src, nbytes, &bar);
+            }
+            wx_mbar_wait(&bar, parity);
+            parity ^= 1;
+            if (dstart == 0 && !wpt && tid == 0) {                     // xw[:,1] = x    SWT.jl:857
+                wx_bulk_store_1d(xk, bufs, nbytes);
+                wx_bulk_commit();
+            }
         }
         const int npairs = 1 << (E - 1);
         for (int c = 0; c < npairs; ++c) {
@@ -245,7 +279,7 @@ int rdwt_chain_plan(T *xw, const T *x, long n, int L, long N, const Taps<T> &t, 
 }
 
 template <typename T, int F, int AC>
-int rwpd_launch(T *xw, const T *x, long n, long ncols, int dstart, int dend, int L, int wpt, long N, const Taps<T> &t, cudaStream_t s)
+int rwpd_launch(T *xw, const T *x, long n, long ncols, int dstart, int dend, int L, int wpt, int chain, long N, const Taps<T> &t, cudaStream_t s)
 {
     using C = RwCfg<T, F>;
     WxDev dv; int rc = wx_devinfo(dv); if (rc) return rc;
@@ -260,7 +294,7 @@ int rwpd_launch(T *xw, const T *x, long n, long ncols, int dstart, int dend, int
     const long items = N << dstart;
     long blocks = (long)dv.sms * occ;
     if (blocks > items) blocks = items;
-    kern<<<(unsigned)blocks, threads, smem, s>>>(xw, x, (int)n, ncols, dstart, dend, L, wpt, items, t);
+    kern<<<(unsigned)blocks, threads, smem, s>>>(xw, x, (int)n, ncols, dstart, dend, L, wpt, chain, items, t);
     WX_LAUNCHED();
     return WX_OK;
 }
@@ -289,13 +323,23 @@ int rwpd_plan(T *xw, const T *x, long n, int L, int wpt, long N, const Taps<T> &
     if (elast > dend) elast = dend;
     int d = 0;
     const int top = dend - (int)elast;
+    static const bool nochain = getenv("WX_B200_RWPD_NO_CHAIN") != nullptr;      // measurement knob
+    if (top > 0 && top <= 4 && !nochain && !AC && sizeof(T) == 8) {
+        // short top: every item rebuilds its depth-`top` node from x itself (top extra single-child passes per item, ~5 % more
+        // arithmetic) -- one launch, and the depth-`top` nodes are never re-read from HBM.  Measured: stationary Float64 3.08 ->
+        // 2.91 ms; the autocorrelation filters (2F-1 taps) and Float32 (issue bound) lose to the extra passes, so they keep two launches
+        rc = rwpd_launch<T, F, AC>(xw, x, n, ncols, top, dend, L, wpt, 1, N, t, s);
+        if (rc) return rc;
+        *done = dend;
+        return WX_OK;
+    }
     while (d < top) {
         const int e = (top - d > efull) ? (int)efull : top - d;
-        rc = rwpd_launch<T, F, AC>(xw, x, n, ncols, d, d + e, L, wpt, N, t, s);
+        rc = rwpd_launch<T, F, AC>(xw, x, n, ncols, d, d + e, L, wpt, 0, N, t, s);
         if (rc) return rc;
         d += e;
     }
-    rc = rwpd_launch<T, F, AC>(xw, x, n, ncols, top, dend, L, wpt, N, t, s);
+    rc = rwpd_launch<T, F, AC>(xw, x, n, ncols, top, dend, L, wpt, 0, N, t, s);
     if (rc) return rc;
     *done = dend;
     return WX_OK;
