@@ -230,6 +230,36 @@ def main():
                           "timer": "host wall clock, pinned host buffers, copies inside the timed region"}), flush=True)
         del xh, ch, y
         torch.cuda.empty_cache()
+    # next row f-3: denoiseall on the 131072 x 1024 batch of config 5 (dwt coefficients and swpd tables of a smaller batch)
+    if want("denoise"):
+        n, N, L = 1024, int(131072 * a.scale), 10
+        wt = wx.wavelet("db4")
+        x = torch.randn((N, n), dtype=torch.float64, device=dev, generator=gen)
+        X = wx.dwtall(x, wt)
+        ms, nl = timeit(lambda: wx.noisest(X, False), steps=3, warmup=1)
+        report("noisest_dwt_f64", ms, nl, 8 * (n // 2) * N, n * N, "GSamples_per_s")
+        sig = wx.noisest(X, False)
+        Y = torch.empty_like(X)
+        ms, nl = timeit(lambda: wx.denoising._threshold_into(Y, X, wx.HardTH(), sig * 3.0), steps=3, warmup=1)
+        report("threshold_hard_f64", ms, nl, 2 * 8 * n * N, n * N, "GSamples_per_s")
+        ms, nl = timeit(lambda: wx.denoising._threshold_into(Y, X, wx.SoftTH(), sig * 3.0), steps=3, warmup=1)
+        report("threshold_soft_f64", ms, nl, 2 * 8 * n * N, n * N, "GSamples_per_s")
+        ms, nl = timeit(lambda: wx.denoiseall(X, "dwt", wt), steps=3, warmup=1)
+        report("denoiseall_dwt_visushrink_f64", ms, nl, (8 * (n // 2) + 4 * 8 * n) * N, n * N, "GSamples_per_s")
+        ms, nl = timeit(lambda: wx.surethreshold(X, False), steps=2, warmup=1)
+        report("surethreshold_dwt_f64", ms, nl, 8 * n * N, n * N, "GSamples_per_s")
+        ms, nl = timeit(lambda: wx.relerrorthreshold(X, False), steps=2, warmup=1)
+        report("relerrorthreshold_dwt_f64", ms, nl, 8 * n * N, n * N, "GSamples_per_s")
+        del x, X, Y
+        n, N, L = 2048, int(2048 * a.scale), 8
+        x = torch.randn((N, n), dtype=torch.float64, device=dev, generator=gen)
+        S = wx.swpdall(x, wt, L)
+        tree = wx.maketree(n, L, "full")
+        K = S.shape[1]
+        ms, nl = timeit(lambda: wx.denoiseall(S, "swpd", wt, tree=tree), steps=3, warmup=1)
+        report("denoiseall_swpd_fulltree_f64", ms, nl, 8 * n * N * (2 * K + (1 << L) + 2), n * N, "GSamples_per_s")
+        del x, S
+        torch.cuda.empty_cache()
     # config 5: JBB / LSDB best basis + getbasiscoefall + iwptall on 131072 signals x 1024 per GPU (1M over 8 GPUs)
     n, N, L = 1024, int(131072 * a.scale), 10
     if want("jbb") or want("lsdb") or want("basis_iwpt") or want("bb"):

@@ -179,6 +179,24 @@ int wx_energy_map_tf_f64(double *esum_dev, const double *X, const int *labels_de
 int wx_energy_map_tf_f32(double *esum_dev, const float *X, const int *labels_dev, int nc, long szK, long Nlocal, void *stream);
 int wx_ldb_discriminant(double *D_dev, const double *esum_dev, const double *inv_norm_dev, int nc, long szK, int kind, double p, int elt, void *stream);
 int wx_node_costs(double *costs_host, const double *term_dev, long m, long n, int K, int redundant, double mult, int elt, void *stream);
+/* Denoising (next row f-3): the threshold determination and thresholding between getbasiscoefall and the inverse transform.
+ * All arrays are device pointers except colmask (host bytes).  A signal's coefficients are an (n, K) column-major slab
+ * (K = 1 for dwt / wpt vectors, K = L+1 for sdwt / acdwt, K = 2^(L+1)-1 for swpd / acwpd), N slabs back to back.
+ * noisest  Denoising.jl:214-232 (Wavelets.jl Threshold.mad!): sigma[k] = median|y - median(y)| / 0.6745 over the range
+ *          [off, off+len) of slab k (the caller passes finestdetailrange Utils.jl:416-436, x[:,end] or x[n/2+1:end]).
+ * surethreshold      Denoising.jl:142-166 / relerrorthreshold :285-328 (orth2relerror :344-349, findelbow :366-381) over the
+ *          columns selected by colmask (NULL = all: dwt, wpt, sdwt; the leaves of the tree for swpd / acwpd); t: N Float64.
+ * threshold  Wavelets.jl Threshold.jl threshold! as called by denoise Denoising.jl:483-600: th 0 HardTH, 1 SoftTH,
+ *          2 SemiSoftTH, 3 SteinTH; t_k = sigma[k] * tmul (sigma NULL: t = tmul).  Columns with colmask[c] == 0 and the
+ *          element range [keep_lo, keep_hi) of every slab are copied unchanged (smooth = :undersmooth).  y may alias x. */
+int wx_noisest_f64(double *sigma, const double *x, long stride, long off, long len, long N, void *stream);
+int wx_noisest_f32(double *sigma, const float *x, long stride, long off, long len, long N, void *stream);
+int wx_surethreshold_f64(double *t, const double *x, long n, long K, const unsigned char *colmask, long N, void *stream);
+int wx_surethreshold_f32(double *t, const float *x, long n, long K, const unsigned char *colmask, long N, void *stream);
+int wx_relerrorthreshold_f64(double *t, const double *x, long n, long K, const unsigned char *colmask, int elbows, long N, void *stream);
+int wx_relerrorthreshold_f32(double *t, const float *x, long n, long K, const unsigned char *colmask, int elbows, long N, void *stream);
+int wx_threshold_f64(double *y, const double *x, long n, long K, const unsigned char *colmask, long keep_lo, long keep_hi, int th, const double *sigma, double tmul, long N, void *stream);
+int wx_threshold_f32(float *y, const float *x, long n, long K, const unsigned char *colmask, long keep_lo, long keep_hi, int th, const double *sigma, double tmul, long N, void *stream);
 /* bestbasis_treeselection  BestBasis.jl:59-110 (host, O(n)); costs are modified in place like the reference.
  * m = 0: binary tree with n-1 entries; m > 0: quad tree. minmax 0 = :min, 1 = :max */
 int wx_tree_select(unsigned char *tree_out, double *costs_host, long ncosts, long m, long n, int minmax);

@@ -561,3 +561,217 @@ def ldb_costs(DM):
         r0, c0, rr, cc = quadrange(nr, nc_, i)
         out.append(DM[d, c0:c0 + cc, r0:r0 + rr].sum())
     return np.array(out, DM.dtype)
+
+
+# ------------------------------------------------------------------ denoising (next row f-3), single signal, plain numpy
+# Wavelets.jl (dependency, compat "0.9, 0.10", not vendored in the reference tree) supplies Threshold.mad!, threshold! and
+# VisuShrink; their published algorithms are restated here.  Everything below computes in Float64 on the data as given.
+TH_HARD, TH_SOFT, TH_SEMISOFT, TH_STEIN = 0, 1, 2, 3
+
+
+def mad(y):
+    """Wavelets.Threshold.mad!: m = median!(y); y .= abs.(y .- m); median!(y)   (arithmetic in the element type)"""
+    y = np.array(y, copy=True).reshape(-1)
+    m = np.median(y).astype(y.dtype)
+    return np.median(np.abs(y - m)).astype(y.dtype)
+
+
+def finestdetailrange(n, tree, redundant=False):
+    """Utils.jl:416-436 -> 0-based (start, stop) of the vector range, or the 0-based node index for redundant tables"""
+    tree = np.asarray(tree).astype(bool)
+    assert getdepth(len(tree), "binary") + 1 == maxtransformlevels(n)
+    i, j = 1, 0
+    while i <= len(tree) and tree[i - 1]:
+        i = 2 * i + 1; j += 1
+    return (i - 1) if redundant else (n - (n >> j), n)
+
+
+def coarsestscalingrange(n, tree, redundant=False):
+    """Utils.jl:351-370"""
+    tree = np.asarray(tree).astype(bool)
+    assert getdepth(len(tree), "binary") + 1 == maxtransformlevels(n)
+    i, j = 1, 0
+    while i < len(tree) and tree[i - 1]:
+        i = 2 * i; j += 1
+    return (i - 1) if redundant else (0, n >> j)
+
+
+def noisest(x, redundant, tree=None):
+    """Denoising.jl:214-232.  x: vector (n,) or table (K, n) in Julia memory order"""
+    x = np.asarray(x)
+    n = x.shape[-1]
+    assert n & (n - 1) == 0
+    if not redundant and tree is None:
+        dr = x[n // 2:]
+    elif not redundant:
+        a, b = finestdetailrange(n, tree, False); dr = x[a:b]
+    elif tree is None:
+        dr = x[-1]
+    else:
+        dr = x[finestdetailrange(n, tree, True)]
+    return float(mad(dr)) / 0.6745
+
+
+def _selected(coef, redundant, tree):
+    coef = np.asarray(coef)
+    if not redundant:
+        return coef.reshape(-1)
+    if tree is None:
+        return coef.reshape(-1)
+    leaves = np.asarray(getleaf(tree, "binary")).astype(bool)
+    return coef[:len(leaves)][leaves].reshape(-1)
+
+
+def surethreshold(coef, redundant, tree=None):
+    """Denoising.jl:142-166"""
+    y = _selected(coef, redundant, tree).astype(np.float64)
+    a = np.sort(np.abs(y)) ** 2
+    b = np.cumsum(a)
+    n = len(y)
+    c = np.arange(n - 1, -1, -1)
+    s = b + c * a
+    risk = (n - 2 * np.arange(1, n + 1) + s) / n
+    return float(np.sqrt(a[int(np.argmin(risk))]))
+
+
+def orth2relerror(orth):
+    """Denoising.jl:344-349"""
+    o = np.sort(np.asarray(orth, np.float64) ** 2)[::-1]
+    S = o.sum()
+    return np.sqrt(np.abs(S - np.cumsum(o))) / np.sqrt(S)
+
+
+def findelbow(x, y):
+    """Denoising.jl:366-381 -> 0-based index"""
+    v = np.array([x[-1] - x[0], y[-1] - y[0]])
+    v = v / np.sqrt((v ** 2).sum())
+    dx, dy = x - x[0], y - y[0]
+    H = np.sqrt(dx ** 2 + dy ** 2)
+    A = dx * v[0] + dy * v[1]
+    O = np.sqrt(np.abs(H ** 2 - A ** 2))
+    return int(np.argmax(O))
+
+
+def relerrorthreshold(coef, redundant=False, tree=None, elbows=2):
+    """Denoising.jl:285-328 (makeplot = false)"""
+    assert elbows >= 1
+    c = _selected(coef, redundant, tree).astype(np.float64)
+    x = np.sort(np.abs(c))[::-1]
+    r = orth2relerror(c)
+    x = np.concatenate([x, [0.0]])
+    r = np.concatenate([[r[0]], r])
+    xmax, ymax = x.max(), r.max()
+    x = x[::-1] / xmax
+    y = r[::-1] / ymax
+    ix = findelbow(x, y)
+    for _ in range(1, elbows):
+        ix = findelbow(x[:ix + 1], y[:ix + 1])
+    return float(x[ix] * xmax)
+
+
+def threshold(x, th, t):
+    """Wavelets.jl threshold! for HardTH / SoftTH / SemiSoftTH / SteinTH (t a Float64; result stored in x's element type)"""
+    assert t >= 0
+    x = np.asarray(x)
+    xd = x.astype(np.float64)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        if th == TH_HARD:
+            out = np.where(np.abs(xd) <= t, 0.0, xd)
+        elif th == TH_SOFT:
+            sh = np.abs(xd) - t
+            out = np.where(sh < 0, 0.0, np.sign(xd) * sh)
+        elif th == TH_SEMISOFT:
+            sh = np.abs(xd) - t
+            inner = np.where(sh < 0, 0.0, np.where(sh - t < 0, np.sign(xd) * sh * 2, xd))
+            out = np.where(xd <= 2 * t, inner, xd)
+        elif th == TH_STEIN:
+            sh = 1.0 - t * t / (xd * xd)
+            out = np.where(sh < 0, 0.0, xd * sh)
+        else:
+            raise ValueError(th)
+    return out.astype(x.dtype)
+
+
+def visushrink_t(n):
+    """Wavelets.jl VisuShrink(n): t = sqrt(2 log n)"""
+    return float(np.sqrt(2 * np.log(n)))
+
+
+def denoise(x, inputtype, q, L=None, tree=None, th=TH_HARD, t=None, estnoise=noisest, smooth="regular"):
+    """Denoising.jl:483-600 for one signal.  q: the orthogonal filter's qmf (None = no reconstruction); (th, t) = dnt.th, dnt.t;
+    estnoise: a function (x, redundant, tree) or a number."""
+    assert smooth in ("undersmooth", "regular")
+    assert inputtype in ("sig", "dwt", "wpt", "sdwt", "swpd", "acdwt", "acwpd")
+    x = np.asarray(x)
+    n = x.shape[-1]
+    if L is None: L = maxtransformlevels(n)
+    if tree is None: tree = maketree1(n, L, "dwt")
+    if t is None: t = visushrink_t(n)
+    h = g = P = Q = None
+    if q is not None:
+        g, h = makereverseqmfpair(q)
+        P, Q = make_acreverseqmfpair(q)
+    sig = lambda red, tr: estnoise(x, red, tr) if callable(estnoise) else float(estnoise)
+    if inputtype == "sig":
+        x = wpt(x, maketree1(n, L, "dwt"), h, g); inputtype = "dwt"
+    if inputtype == "dwt":
+        s = sig(False, None)
+        if smooth == "regular":
+            xt = threshold(x, th, s * t)
+        else:
+            n0 = n >> L
+            xt = np.concatenate([x[:n0], threshold(x[n0:], th, s * t)])
+        return xt if q is None else iwpt(xt, maketree1(n, L, "dwt"), h, g)
+    if inputtype == "wpt":
+        s = sig(False, tree)
+        if smooth == "regular":
+            xt = threshold(x, th, s * t)
+        else:
+            a, b = coarsestscalingrange(n, tree, False)
+            xt = np.concatenate([x[a:b], threshold(x[b:], th, s * t)])
+        return xt if q is None else iwpt(xt, tree, h, g)
+    if inputtype in ("sdwt", "acdwt"):
+        assert x.ndim > 1
+        s = sig(True, None)
+        xt = x.copy()
+        if smooth == "regular":
+            xt = threshold(xt, th, s * t)
+        else:
+            xt[1:] = threshold(x[1:], th, s * t)
+        if inputtype == "sdwt":
+            return xt if q is None else isdwt(xt, h, g)
+        return iacdwt(xt)
+    assert x.ndim > 1
+    s = sig(True, tree)
+    leaves = np.flatnonzero(np.asarray(getleaf(tree, "binary")))
+    if smooth == "undersmooth":
+        leaves = leaves[leaves != coarsestscalingrange(n, tree, True)]
+    xt = x.copy()
+    xt[leaves] = threshold(x[leaves], th, s * t)
+    if inputtype == "swpd":
+        return xt if q is None else iswpd(xt, tree, h, g)
+    return iacwpd(xt, tree)
+
+
+def denoiseall(X, inputtype, q, L=None, tree=None, th=TH_HARD, t=None, estnoise=noisest, bestTH=None, smooth="regular"):
+    """Denoising.jl:651-713.  X: (N, n) or (N, K, n); estnoise: function or a vector of N numbers; bestTH: None or a function"""
+    X = np.asarray(X)
+    assert X.ndim > 1
+    N, n = X.shape[0], X.shape[-1]
+    if L is None: L = maxtransformlevels(n)
+    if tree is None: tree = maketree1(n, L, "dwt")
+    if inputtype == "sig":
+        g, h = makereverseqmfpair(q)
+        X = np.stack([wpt(X[i], maketree1(n, L, "dwt"), h, g) for i in range(N)]); inputtype = "dwt"
+    if bestTH is None:
+        est = [estnoise if callable(estnoise) else estnoise[i] for i in range(N)]
+    else:
+        if callable(estnoise):
+            red = inputtype not in ("dwt", "wpt")
+            tr = None if inputtype in ("dwt", "sdwt") else tree
+            # the reference passes the tree for every other input type (incl. :acdwt, Denoising.jl:692-700)
+            sg = [estnoise(X[i], red, tr) for i in range(N)]
+        else:
+            sg = list(estnoise)
+        est = [float(bestTH(np.asarray(sg, np.float64)))] * N
+    return np.stack([denoise(X[i], inputtype, q, L=L, tree=tree, th=th, t=t, estnoise=est[i], smooth=smooth) for i in range(N)])
