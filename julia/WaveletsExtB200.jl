@@ -228,4 +228,29 @@ function bestbasistreeall(X::B200Array{T,3}, method::WaveletsExt.BestBasis.BB) w
     return BitMatrix(Array(trees) .!= 0)
 end
 
+# noisest(x, false)   Denoising.jl:214-232 for every column of a batch of dwt coefficients (n, N): N noise levels on the device
+function noisestall(X::B200Array{T,2}) where T
+    n, N = size(X)
+    sigma = B200Array{Float64,1}((N,); dev=X.dev)
+    check(ccall((Symbol("wx_noisest_", sfx(T)), LIB), Cint, (Ptr{Cdouble}, Ptr{T}, Clong, Clong, Clong, Clong, Ptr{Cvoid}),
+                sigma.ptr, X.ptr, n, n ÷ 2, n - n ÷ 2, N, C_NULL))
+    return sigma
+end
+
+# denoiseall(x, :dwt, wt; L, dnt, smooth)   Denoising.jl:651-713 with estnoise = noisest, bestTH = nothing: per-signal thresholds
+# sigma_k * dnt.t applied on the device, then idwtall (the :dwt tree through wx_iwpt1d)
+function denoiseall_dwt(X::B200Array{T,2}, wt::OrthoFilter; L::Integer=maxtransformlevels(size(X,1)),
+                        dnt=VisuShrink(size(X,1)), smooth::Symbol=:regular) where T
+    n, N = size(X)
+    sigma = noisestall(X)
+    th = dnt.th isa Wavelets.Threshold.HardTH ? 0 : dnt.th isa Wavelets.Threshold.SoftTH ? 1 :
+         dnt.th isa Wavelets.Threshold.SemiSoftTH ? 2 : 3
+    keep_hi = smooth == :undersmooth ? nodelength(n, L) : 0
+    Xt = similar(X)
+    check(ccall((Symbol("wx_threshold_", sfx(T)), LIB), Cint,
+                (Ptr{T}, Ptr{T}, Clong, Clong, Ptr{UInt8}, Clong, Clong, Cint, Ptr{Cdouble}, Cdouble, Clong, Ptr{Cvoid}),
+                Xt.ptr, X.ptr, n, 1, C_NULL, 0, keep_hi, th, sigma.ptr, dnt.t, N, C_NULL))
+    return iwptall(Xt, wt, maketree(n, L, :dwt))
+end
+
 end # module

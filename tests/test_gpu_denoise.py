@@ -85,6 +85,22 @@ def test_sure_and_relerror_thresholds(wx, O, cuda, dt):
     assert isinstance(s.th, wx.SoftTH) and s.t == pytest.approx(O.surethreshold(Xh[0], True, dtree), rel=tol)
 
 
+def test_thresholds_cta_sort_path(wx, O, cuda):
+    """more than 1024 selected coefficients per signal: the per-CTA shared-memory sort instead of the warp-resident one"""
+    wt = wx.wavelet("db2")
+    n, N = 512, 6
+    x = signals(n, N, 8)
+    X = wx.sdwtall(dev(x, cuda), wt)                     # (N, 10, 512): 5120 coefficients per signal
+    Xh = X.cpu().numpy()
+    t = wx.surethreshold(X, True).cpu().numpy()
+    assert np.abs(t - [O.surethreshold(Xh[i], True) for i in range(N)]).max() <= 1e-12
+    t = wx.relerrorthreshold(X, True).cpu().numpy()
+    assert np.abs(t - [O.relerrorthreshold(Xh[i], True) for i in range(N)]).max() <= 1e-12
+    xl = signals(4096, 3, 9)
+    s = wx.noisest(dev(xl, cuda), False).cpu().numpy()   # 2048-element range
+    assert np.abs(s - [O.noisest(xl[i], False) for i in range(3)]).max() <= 1e-13
+
+
 def test_sure_large_selection_global_scratch(wx, O, cuda):
     wt = wx.wavelet("haar")
     n, N, L = 4096, 2, 3                   # 8 leaves x 4096 = 32768 doubles = 256 KB > shared memory

@@ -11,6 +11,7 @@
 #include "wx_2d.cuh"
 #include <vector>
 #include <limits>
+#include <cstdlib>
 
 namespace {
 
@@ -60,6 +61,91 @@ __global__ void __launch_bounds__(kTS) mad_k(double *__restrict__ sigma, const T
     __syncthreads();
     bitonic_sort(a, P);
     if (threadIdx.x == 0) sigma[blockIdx.x] = (double)sorted_median(a, len) / 0.6745;
+}
+
+// ---- warp-resident sort: one signal per warp, E elements per lane in registers (P = 32 E <= 1024) ----------------
+// Element g of the sorted sequence lives in lane g / E, register g % E.  Bitonic network in its "flip" form: stage k first
+// compares g with g ^ (k-1), then g with g ^ j for j = k/4 .. 1; every compare-exchange is ascending, so there are no
+// direction flags.  Partners at distance < E are registers of the same lane (compile-time indices), the others come
+// through shfl_xor.
+template <typename T> __device__ __forceinline__ T shfl_xor_t(T v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+template <typename T> __device__ __forceinline__ T shfl_idx_t(T v, int l) { return __shfl_sync(0xffffffffu, v, l); }
+
+template <typename T> __device__ __forceinline__ void cex(T &a, T &b) { const bool sw = a > b; const T lo = sw ? b : a, hi = sw ? a : b; a = lo; b = hi; }
+
+template <typename T, int E>
+__device__ __forceinline__ void warp_bitonic(T (&v)[E])
+{
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int k = 2; k <= 32 * E; k <<= 1) {
+        if (k <= E) {
+#pragma unroll
+            for (int e = 0; e < E; ++e) { const int p = e ^ (k - 1); if (p > e) cex(v[e], v[p]); }
+        } else {
+            const int lm = k / E - 1;
+            const bool keepmin = (lane & ((k / E) >> 1)) == 0;
+#pragma unroll
+            for (int e = 0; e < (E + 1) / 2; ++e) {
+                const int f = E - 1 - e;
+                const T o1 = shfl_xor_t(v[f], lm), o2 = shfl_xor_t(v[e], lm);
+                const T a = v[e], b = v[f];
+                v[e] = (keepmin ? (o1 < a) : (o1 > a)) ? o1 : a;
+                if (f != e) v[f] = (keepmin ? (o2 < b) : (o2 > b)) ? o2 : b;
+            }
+        }
+#pragma unroll
+        for (int j = k >> 2; j > 0; j >>= 1) {
+            if (j < E) {
+#pragma unroll
+                for (int e = 0; e < E; ++e) if ((e & j) == 0) cex(v[e], v[e | j]);
+            } else {
+                const int lm = j / E;
+                const bool keepmin = (lane & lm) == 0;
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    const T o = shfl_xor_t(v[e], lm), a = v[e];
+                    v[e] = (keepmin ? (o < a) : (o > a)) ? o : a;
+                }
+            }
+        }
+    }
+}
+
+// element g of the warp-sorted sequence, broadcast to all lanes
+template <typename T, int E>
+__device__ __forceinline__ T warp_elem(const T (&v)[E], int g)
+{
+    const int ge = g % E;
+    T x = v[0];
+#pragma unroll
+    for (int e = 1; e < E; ++e) if (e == ge) x = v[e];
+    return shfl_idx_t(x, g / E);
+}
+template <typename T, int E>
+__device__ __forceinline__ T warp_median(const T (&v)[E], int M)
+{
+    return (M & 1) ? warp_elem<T, E>(v, M >> 1) : warp_elem<T, E>(v, (M >> 1) - 1) / (T)2 + warp_elem<T, E>(v, M >> 1) / (T)2;
+}
+
+constexpr int kWS = 4;                          // signals (warps) per CTA of the warp-resident kernels
+template <typename T, int E>
+__global__ void __launch_bounds__(32 * kWS) mad_warp_k(double *__restrict__ sigma, const T *__restrict__ x, long stride, long off, int len, long N)
+{
+    const long k = (long)blockIdx.x * kWS + (threadIdx.x >> 5);
+    if (k >= N) return;
+    const int lane = threadIdx.x & 31;
+    const T *src = x + k * stride + off;
+    T v[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) { const int i = e * 32 + lane; v[e] = i < len ? src[i] : wx_inf<T>(); }     // any order will do
+    warp_bitonic<T, E>(v);
+    const T m = warp_median<T, E>(v, len);
+#pragma unroll
+    for (int e = 0; e < E; ++e) v[e] = (lane * E + e) < len ? (T)fabs(v[e] - m) : wx_inf<T>();
+    warp_bitonic<T, E>(v);
+    const T md = warp_median<T, E>(v, len);
+    if (lane == 0) sigma[k] = (double)md / 0.6745;
 }
 
 // srt (N, P): |coefficients| of the selected columns of each signal's (n, K) slab, ascending, padded with +inf
@@ -213,6 +299,117 @@ __global__ void __launch_bounds__(kTS) relerr_k(double *__restrict__ t, const T 
     if (threadIdx.x == 0) t[blockIdx.x] = ((end ? (double)asc[end - 1] : 0.0) / xmax) * xmax;
 }
 
+// ---- warp-resident surethreshold / relerrorthreshold (M <= 1024 selected coefficients per signal) ----------------------
+template <typename T, int E>
+__device__ __forceinline__ void warp_load_abs_sorted(T (&v)[E], const T *__restrict__ src, int n, const int *__restrict__ cols, int M)
+{
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        const int i = e * 32 + lane;
+        T a = wx_inf<T>();
+        if (i < M) { const int c = i / n, r = i - c * n; a = fabs(src[(long)(cols ? cols[c] : c) * n + r]); }
+        v[e] = a;
+    }
+    warp_bitonic<T, E>(v);
+}
+template <bool MAX>
+__device__ __forceinline__ void warp_argext(double &v, int &idx)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, v, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+        const bool better = oi >= 0 && (idx < 0 || (MAX ? (ov > v || (ov == v && oi < idx)) : (ov < v || (ov == v && oi < idx))));
+        if (better) { v = ov; idx = oi; }
+    }
+}
+
+template <typename T, int E>
+__global__ void __launch_bounds__(32 * kWS) sure_warp_k(double *__restrict__ t, const T *__restrict__ x, long slab, int n, const int *__restrict__ cols, int M, long N)
+{
+    const long k = (long)blockIdx.x * kWS + (threadIdx.x >> 5);
+    if (k >= N) return;
+    const int lane = threadIdx.x & 31;
+    T v[E];
+    warp_load_abs_sorted<T, E>(v, x + k * slab, n, cols, M);
+    double loc = 0;
+#pragma unroll
+    for (int e = 0; e < E; ++e) { const double a = (double)v[e]; if (lane * E + e < M) loc += a * a; }
+    double b = warp_incl_scan(loc) - loc;
+    double best = 0; int bi = -1;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        const int g = lane * E + e;
+        if (g < M) {
+            const double a = (double)v[e], av = a * a;
+            b += av;
+            const double risk = ((double)(M - 2 * (g + 1)) + (b + (double)(M - 1 - g) * av)) / (double)M;
+            if (bi < 0 || risk < best) { best = risk; bi = g; }
+        }
+    }
+    warp_argext<false>(best, bi);
+    const double a = (double)warp_elem<T, E>(v, bi);
+    if (lane == 0) t[k] = sqrt(a * a);
+}
+
+template <typename T, int E>
+__global__ void __launch_bounds__(32 * kWS) relerr_warp_k(double *__restrict__ t, const T *__restrict__ x, long slab, int n, const int *__restrict__ cols, int M, int elbows,
+                                                         long N)
+{
+    const long k = (long)blockIdx.x * kWS + (threadIdx.x >> 5);
+    if (k >= N) return;
+    const int lane = threadIdx.x & 31;
+    T v[E];
+    warp_load_abs_sorted<T, E>(v, x + k * slab, n, cols, M);
+    // sum of the squares above each element (descending running sum of orth2relerror), S = all of them
+    double Y[E];
+    double loc = 0;
+#pragma unroll
+    for (int e = E - 1; e >= 0; --e) { Y[e] = loc; const double a = (double)v[e]; if (lane * E + e < M) loc += a * a; }
+    double inc = loc;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const double u = __shfl_down_sync(0xffffffffu, inc, o); if (lane + o < 32) inc += u; }
+    const double S = __shfl_sync(0xffffffffu, inc, 0), above = inc - loc, rS = sqrt(S);
+    const double xmax = (double)warp_elem<T, E>(v, M - 1);
+#pragma unroll
+    for (int e = 0; e < E; ++e) Y[e] = lane * E + e < M ? sqrt(fabs(S - (above + Y[e]))) / rS : 0.0;      // point g+1 (g = M-1 is patched next)
+    const double r1 = M > 1 ? warp_elem<double, E>(Y, M - 2) : sqrt(fabs(S - S)) / rS;
+    double ymax = 0;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        if (lane * E + e == M - 1) Y[e] = r1;
+        ymax = fmax(ymax, Y[e]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ymax = fmax(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
+    const double x0 = 0.0 / xmax, y0 = (sqrt(fabs(S - S)) / rS) / ymax;          // point 0: (0, r_M)
+    int end = M;
+    for (int el = 0; el < elbows; ++el) {
+        const double xe = end > 0 ? (double)warp_elem<T, E>(v, end - 1) / xmax : x0;
+        const double ye = end > 0 ? warp_elem<double, E>(Y, end - 1) / ymax : y0;
+        double vx = xe - x0, vy = ye - y0;
+        const double nv = sqrt(vx * vx + vy * vy);
+        vx /= nv; vy /= nv;
+        double best = 0; int bi = -1;
+        if (lane == 0) { const double H = sqrt(0.0), A = 0.0 * vx + 0.0 * vy; best = sqrt(fabs(H * H - A * A)); bi = 0; }
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const int p = lane * E + e + 1;
+            if (p <= end) {
+                const double dx = (double)v[e] / xmax - x0, dy = Y[e] / ymax - y0;
+                const double H = sqrt(dx * dx + dy * dy), A = dx * vx + dy * vy;
+                const double O = sqrt(fabs(H * H - A * A));
+                if (bi < 0 || O > best) { best = O; bi = p; }
+            }
+        }
+        warp_argext<true>(best, bi);
+        end = bi < 0 ? 0 : bi;
+    }
+    const double xsel = end ? (double)warp_elem<T, E>(v, end - 1) : 0.0;
+    if (lane == 0) t[k] = (xsel / xmax) * xmax;
+}
+
 // ---- thresholding ----------------------------------------------------------------------------------------
 // th: 0 hard, 1 soft, 2 semisoft, 3 stein -- arithmetic in Float64 (the threshold is a Float64 in the reference), stored as T
 template <typename T>
@@ -235,25 +432,27 @@ __device__ __forceinline__ T apply_th(T xv, double t, int th)
 }
 
 constexpr int kTT = 256, kTE = 8;              // threads, elements per thread of the thresholding pass
+// the batch is one flat run of N slabs: a CTA takes kTT*kTE consecutive coefficients wherever the slab boundaries fall
 template <typename T>
-__global__ void __launch_bounds__(kTT) threshold_k(T *__restrict__ y, const T *__restrict__ x, long slab, Div32 dn, const unsigned char *__restrict__ colmask,
-                                                  long keep_lo, long keep_hi, int th, const double *__restrict__ sigma, double tmul, Div32 dchunks)
+__global__ void __launch_bounds__(kTT) threshold_k(T *__restrict__ y, const T *__restrict__ x, Div32 dslab, Div32 dn, const unsigned char *__restrict__ colmask,
+                                                  unsigned keep_lo, unsigned keep_hi, int th, const double *__restrict__ sigma, double tmul, long total)
 {
-    const unsigned k = div32(blockIdx.x, dchunks), chunk = blockIdx.x - k * dchunks.d;
-    const double t = sigma ? sigma[k] * tmul : tmul;
-    const long base = (long)chunk * (kTT * kTE);
-    const T *xs = x + (long)k * slab;
-    T *ys = y + (long)k * slab;
+    const long base = (long)blockIdx.x * (kTT * kTE);
+    const long k0 = base / dslab.d;
+    const unsigned e0 = (unsigned)(base - k0 * dslab.d);
     T v[kTE];
 #pragma unroll
-    for (int u = 0; u < kTE; ++u) { const long e = base + u * kTT + threadIdx.x; if (e < slab) v[u] = xs[e]; }
+    for (int u = 0; u < kTE; ++u) { const long i = base + u * kTT + threadIdx.x; if (i < total) v[u] = x[i]; }
 #pragma unroll
     for (int u = 0; u < kTE; ++u) {
-        const long e = base + u * kTT + threadIdx.x;
-        if (e < slab) {
+        const unsigned idx = u * kTT + threadIdx.x;
+        const long i = base + idx;
+        if (i < total) {
+            const unsigned kk = div32(e0 + idx, dslab), e = e0 + idx - kk * dslab.d;
+            const double t = sigma ? sigma[k0 + kk] * tmul : tmul;
             bool on = e < keep_lo || e >= keep_hi;
-            if (colmask) on = on && colmask[div32((unsigned)e, dn)];
-            ys[e] = on ? apply_th<T>(v[u], t, th) : v[u];
+            if (colmask) on = on && colmask[div32(e, dn)];
+            y[i] = on ? apply_th<T>(v[u], t, th) : v[u];
         }
     }
 }
@@ -287,6 +486,15 @@ int noisest_impl(double *sigma, const T *x, long stride, long off, long len, lon
     if (N == 0) return WX_OK;
     WxDev dv; int rc = wx_devinfo(dv); if (rc) return rc;
     const int P = next_pow2(len);
+    static const bool nowarp = getenv("WX_B200_NO_WARP_SORT") != nullptr;
+    if (P <= 1024 && !nowarp) {
+        const unsigned grid = (unsigned)((N + kWS - 1) / kWS);
+#define WX_MW(EE) case EE: mad_warp_k<T, EE><<<grid, 32 * kWS, 0, s>>>(sigma, x, stride, off, (int)len, N); break;
+        switch (P <= 32 ? 1 : P / 32) { WX_MW(1) WX_MW(2) WX_MW(4) WX_MW(8) WX_MW(16) WX_MW(32) }
+#undef WX_MW
+        WX_LAUNCHED();
+        return WX_OK;
+    }
     const size_t bytes = (size_t)P * sizeof(T);
     DevBuf gb(s);
     auto kern = mad_k<T>;
@@ -297,26 +505,35 @@ int noisest_impl(double *sigma, const T *x, long stride, long off, long len, lon
     return WX_OK;
 }
 
-// sorted magnitudes of the selected columns into srt (N, P)
-template <typename T>
-int sort_selected(DevBuf &srt, int *Mo, int *Po, const T *x, long n, long K, const unsigned char *colmask, long N, cudaStream_t s)
+// the selected columns: cols.p = device list (null = all K columns), *Mo = coefficients per signal
+static int select_columns(DevBuf &cols, long *Mo, long n, long K, const unsigned char *colmask, long N)
 {
     std::vector<int> sel;
     for (long c = 0; c < K; ++c) if (!colmask || colmask[c]) sel.push_back((int)c);
     WX_REQUIRE(!sel.empty(), "no column selected");
-    const long M = (long)sel.size() * n;
-    WX_REQUIRE(M <= (1L << 28) && n < (1L << 31) && N < (1L << 31), "too many coefficients per signal");
+    *Mo = (long)sel.size() * n;
+    WX_REQUIRE(*Mo <= (1L << 28) && n < (1L << 31) && N < (1L << 31), "too many coefficients per signal");
+    if ((long)sel.size() != K) return cols.upload(sel.data(), sel.size() * sizeof(int));
+    return WX_OK;
+}
+static inline bool warp_sortable(long M)
+{
+    static const bool nowarp = getenv("WX_B200_NO_WARP_SORT") != nullptr;
+    return M <= 1024 && !nowarp;
+}
+
+// sorted magnitudes of the selected columns into srt (N, P)
+template <typename T>
+int sort_selected(DevBuf &srt, int *Mo, int *Po, const T *x, long n, long K, long M, const DevBuf &cols, long N, cudaStream_t s)
+{
     WxDev dv; int rc = wx_devinfo(dv); if (rc) return rc;
-    const bool all = (long)sel.size() == K;
-    DevBuf cols(s);
-    if (!all) { rc = cols.upload(sel.data(), sel.size() * sizeof(int)); if (rc) return rc; }
     const int P = next_pow2(M);
     const size_t bytes = (size_t)P * sizeof(T);
     rc = srt.alloc(bytes * N); if (rc) return rc;
     const int in_smem = bytes <= dv.smem_optin;
     auto kern = sort_abs_k<T>;
     if (in_smem) WX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-    kern<<<(unsigned)N, sort_threads(P), in_smem ? bytes : 0, s>>>((T *)srt.p, x, n * K, (int)n, all ? nullptr : (const int *)cols.p, (int)M, P, in_smem);
+    kern<<<(unsigned)N, sort_threads(P), in_smem ? bytes : 0, s>>>((T *)srt.p, x, n * K, (int)n, (const int *)cols.p, (int)M, P, in_smem);
     WX_LAUNCHED();
     *Mo = (int)M; *Po = P;
     return WX_OK;
@@ -327,8 +544,17 @@ int sure_impl(double *t, const T *x, long n, long K, const unsigned char *colmas
 {
     WX_REQUIRE(t && x && n >= 1 && K >= 1 && N >= 0, "bad arguments");
     if (N == 0) return WX_OK;
-    DevBuf srt(s); int M, P;
-    int rc = sort_selected(srt, &M, &P, x, n, K, colmask, N, s); if (rc) return rc;
+    DevBuf srt(s), cols(s); int M, P; long Ml;
+    int rc = select_columns(cols, &Ml, n, K, colmask, N); if (rc) return rc;
+    if (warp_sortable(Ml)) {
+        const unsigned grid = (unsigned)((N + kWS - 1) / kWS);
+#define WX_SW(EE) case EE: sure_warp_k<T, EE><<<grid, 32 * kWS, 0, s>>>(t, x, n * K, (int)n, (const int *)cols.p, (int)Ml, N); break;
+        switch (Ml <= 32 ? 1 : next_pow2(Ml) / 32) { WX_SW(1) WX_SW(2) WX_SW(4) WX_SW(8) WX_SW(16) WX_SW(32) }
+#undef WX_SW
+        WX_LAUNCHED();
+        return WX_OK;
+    }
+    rc = sort_selected(srt, &M, &P, x, n, K, Ml, cols, N, s); if (rc) return rc;
     sure_k<T><<<(unsigned)N, kTS, 0, s>>>(t, (const T *)srt.p, M, P);
     WX_LAUNCHED();
     return WX_OK;
@@ -340,8 +566,17 @@ int relerr_impl(double *t, const T *x, long n, long K, const unsigned char *colm
     WX_REQUIRE(t && x && n >= 1 && K >= 1 && N >= 0, "bad arguments");
     WX_REQUIRE(elbows >= 1, "AssertionError: elbows >= 1");
     if (N == 0) return WX_OK;
-    DevBuf srt(s), Yw(s); int M, P;
-    int rc = sort_selected(srt, &M, &P, x, n, K, colmask, N, s); if (rc) return rc;
+    DevBuf srt(s), Yw(s), cols(s); int M, P; long Ml;
+    int rc = select_columns(cols, &Ml, n, K, colmask, N); if (rc) return rc;
+    if (warp_sortable(Ml)) {
+        const unsigned grid = (unsigned)((N + kWS - 1) / kWS);
+#define WX_RW(EE) case EE: relerr_warp_k<T, EE><<<grid, 32 * kWS, 0, s>>>(t, x, n * K, (int)n, (const int *)cols.p, (int)Ml, elbows, N); break;
+        switch (Ml <= 32 ? 1 : next_pow2(Ml) / 32) { WX_RW(1) WX_RW(2) WX_RW(4) WX_RW(8) WX_RW(16) WX_RW(32) }
+#undef WX_RW
+        WX_LAUNCHED();
+        return WX_OK;
+    }
+    rc = sort_selected(srt, &M, &P, x, n, K, Ml, cols, N, s); if (rc) return rc;
     rc = Yw.alloc((size_t)(M + 1) * N * sizeof(double)); if (rc) return rc;
     relerr_k<T><<<(unsigned)N, kTS, 0, s>>>(t, (const T *)srt.p, (double *)Yw.p, M, P, elbows);
     WX_LAUNCHED();
@@ -358,14 +593,14 @@ int threshold_impl(T *y, const T *x, long n, long K, const unsigned char *colmas
     WX_REQUIRE(keep_lo >= 0 && keep_hi <= n * K, "keep range outside the signal");
     if (N == 0) return WX_OK;
     const long slab = n * K;
-    WX_REQUIRE(slab < (1L << 31) && n < (1L << 31), "signal slab too large");
-    const long chunks = (slab + kTT * kTE - 1) / (kTT * kTE);
-    WX_REQUIRE(chunks * N < (1L << 31), "too many coefficients for one launch");
+    WX_REQUIRE(slab < (1L << 31) - kTT * kTE && n < (1L << 31), "signal slab too large");
+    const long total = slab * N, ctas = (total + kTT * kTE - 1) / (kTT * kTE);
+    WX_REQUIRE(ctas < (1L << 31), "too many coefficients for one launch");
     DevBuf mask(s);
     if (colmask) { int rc = mask.upload(colmask, (size_t)K); if (rc) return rc; }
     if (keep_hi < keep_lo) keep_hi = keep_lo;
-    threshold_k<T><<<(unsigned)(chunks * N), kTT, 0, s>>>(y, x, slab, make_div32((unsigned)n), (const unsigned char *)mask.p, keep_lo, keep_hi, th, sigma, tmul,
-                                                        make_div32((unsigned)chunks));
+    threshold_k<T><<<(unsigned)ctas, kTT, 0, s>>>(y, x, make_div32(slab), make_div32(n), (const unsigned char *)mask.p, (unsigned)keep_lo, (unsigned)keep_hi, th, sigma,
+                                                tmul, total);
     WX_LAUNCHED();
     return WX_OK;
 }
