@@ -179,6 +179,20 @@ int wx_energy_map_tf_f64(double *esum_dev, const double *X, const int *labels_de
 int wx_energy_map_tf_f32(double *esum_dev, const float *X, const int *labels_dev, int nc, long szK, long Nlocal, void *stream);
 int wx_ldb_discriminant(double *D_dev, const double *esum_dev, const double *inv_norm_dev, int nc, long szK, int kind, double p, int elt, void *stream);
 int wx_node_costs(double *costs_host, const double *term_dev, long m, long n, int K, int redundant, double mult, int elt, void *stream);
+/* SIWT steps and the nonstandard-form transform (next row f-4).
+ * sidwt_step!(w1,w2,v,h,g,s)  siwt/siwt_one_level.jl:71-98 and isidwt_step!(v,w1,w2,h,g,s) :153-184: dwt_step!/idwt_step! with the
+ *   input (output) circularly shifted by one sample when shifted != 0.
+ * ns_dwt(x, wt, L)  wavemult/transforms.jl:52-74: x (n, N) -> nxw (2n, N), levels stored at ndyad(l, Lmax, gender)
+ *   (wavemult/utils.jl:146-155); ns_idwt(nxw, wt, L) :120-139: nxw (n2 = 2n, N) -> x (n, N).  The reference transforms one
+ *   vector; N > 1 is the batch of them. */
+int wx_sidwt_step_f64(double *w1, double *w2, const double *v, long n, const double *h, const double *g, int F, int shifted, void *stream);
+int wx_sidwt_step_f32(float *w1, float *w2, const float *v, long n, const double *h, const double *g, int F, int shifted, void *stream);
+int wx_isidwt_step_f64(double *v, const double *w1, const double *w2, long n, const double *h, const double *g, int F, int shifted, void *stream);
+int wx_isidwt_step_f32(float *v, const float *w1, const float *w2, long n, const double *h, const double *g, int F, int shifted, void *stream);
+int wx_ns_dwt_f64(double *nxw, const double *x, long n, int L, long N, const double *h, const double *g, int F, void *stream);
+int wx_ns_dwt_f32(float *nxw, const float *x, long n, int L, long N, const double *h, const double *g, int F, void *stream);
+int wx_ns_idwt_f64(double *x, const double *nxw, long n2, int L, long N, const double *h, const double *g, int F, void *stream);
+int wx_ns_idwt_f32(float *x, const float *nxw, long n2, int L, long N, const double *h, const double *g, int F, void *stream);
 /* Denoising (next row f-3): the threshold determination and thresholding between getbasiscoefall and the inverse transform.
  * All arrays are device pointers except colmask (host bytes).  A signal's coefficients are an (n, K) column-major slab
  * (K = 1 for dwt / wpt vectors, K = L+1 for sdwt / acdwt, K = 2^(L+1)-1 for swpd / acwpd), N slabs back to back.

@@ -775,3 +775,94 @@ def denoiseall(X, inputtype, q, L=None, tree=None, th=TH_HARD, t=None, estnoise=
             sg = list(estnoise)
         est = [float(bestTH(np.asarray(sg, np.float64)))] * N
     return np.stack([denoise(X[i], inputtype, q, L=L, tree=tree, th=th, t=t, estnoise=est[i], smooth=smooth) for i in range(N)])
+
+
+# ------------------------------------------------------------------ SIWT steps and the nonstandard form (next row f-4)
+def sidwt_step(v, h, g, s):
+    """sidwt_step!  siwt/siwt_one_level.jl:71-98 (literal loop restatement, 1-based indices kept)"""
+    v = np.asarray(v); n = len(v); n1 = n // 2; F = len(h)
+    s = int(bool(s))
+    mod1 = lambda a, m: (a - 1) % m + 1
+    w1 = np.empty(n1, v.dtype); w2 = np.empty(n1, v.dtype)
+    h = np.asarray(h, v.dtype); g = np.asarray(g, v.dtype)
+    for i in range(1, n1 + 1):
+        k1 = mod1(2 * i - 1 - s, n); k2 = 2 * i - s
+        a1 = g[F - 1] * v[k1 - 1]; a2 = h[0] * v[k2 - 1]
+        for j in range(2, F + 1):
+            k1 = k1 + 1
+            if k1 > n: k1 = mod1(k1, n)
+            k2 = k2 - 1
+            if k2 <= 0: k2 = mod1(k2, n)
+            a1 = a1 + g[F - j] * v[k1 - 1]
+            a2 = a2 + h[j - 1] * v[k2 - 1]
+        w1[i - 1] = a1; w2[i - 1] = a2
+    return w1, w2
+
+
+def isidwt_step(w1, w2, h, g, s):
+    """isidwt_step!  siwt/siwt_one_level.jl:153-184"""
+    w1 = np.asarray(w1); w2 = np.asarray(w2); n1 = len(w1); n = 2 * n1; F = len(h)
+    s = int(bool(s))
+    mod1 = lambda a, m: (a - 1) % m + 1
+    h = np.asarray(h, w1.dtype); g = np.asarray(g, w1.dtype)
+    v = np.empty(n, w1.dtype)
+    for i in range(1, n + 1):
+        l = mod1(i - s, n)
+        j0 = mod1(i, 2); j1 = F - j0 + 1; j2 = mod1(i + 1, 2)
+        k1 = (i + 1) >> 1; k2 = (i + 1) >> 1
+        acc = g[j1 - 1] * w1[k1 - 1] + h[j2 - 1] * w2[k2 - 1]
+        for j in range(j0 + 2, F + 1, 2):
+            j1 = F - j + 1
+            j2 = j + (1 if j % 2 else -1)
+            k1 = k1 - 1
+            if k1 <= 0: k1 = mod1(k1, n1)
+            k2 = k2 + 1
+            if k2 > n1: k2 = mod1(k2, n1)
+            acc = acc + (g[j1 - 1] * w1[k1 - 1] + h[j2 - 1] * w2[k2 - 1])
+        v[l - 1] = acc
+    return v
+
+
+def ndyad(L, Lmax, gender):
+    """wavemult/utils.jl:146-155 -> 0-based half-open (start, stop)"""
+    assert L <= Lmax and L >= 1
+    k = Lmax - L
+    if gender:
+        return (1 << (k + 1)) + (1 << k), 1 << (k + 2)
+    return 1 << (k + 1), (1 << (k + 1)) + (1 << k)
+
+
+def ns_dwt(x, q, L=None):
+    """wavemult/transforms.jl:52-74"""
+    x = np.asarray(x); n = len(x)
+    Lmax = maxtransformlevels(n)
+    if L is None: L = Lmax
+    assert 1 <= L <= Lmax
+    assert n & (n - 1) == 0
+    g, h = makereverseqmfpair(q)
+    nxw = np.zeros(2 * n, x.dtype)
+    for l in range(1, L + 1):
+        v = x if l == 1 else nxw[slice(*ndyad(l - 1, Lmax, False))]
+        w1, w2 = dwt_step(v, h, g)
+        nxw[slice(*ndyad(l, Lmax, False))] = w1
+        nxw[slice(*ndyad(l, Lmax, True))] = w2
+    nxw[:1 << (Lmax - L)] = nxw[slice(*ndyad(L, Lmax, False))]
+    return nxw
+
+
+def ns_idwt(nxw, q, L=None):
+    """wavemult/transforms.jl:120-139"""
+    nxw = np.asarray(nxw)
+    Lmax = maxtransformlevels(len(nxw)) - 1
+    if L is None: L = Lmax
+    n = len(nxw) // 2
+    assert 1 <= L <= Lmax
+    assert n & (n - 1) == 0
+    g, h = makereverseqmfpair(q)
+    x = np.zeros(n, nxw.dtype)
+    x[:1 << (Lmax - L)] = nxw[:1 << (Lmax - L)]
+    for l in range(L, 0, -1):
+        w1 = nxw[slice(*ndyad(l, Lmax, False))] + x[:1 << (Lmax - l)]
+        w2 = nxw[slice(*ndyad(l, Lmax, True))]
+        x[:1 << (Lmax - l + 1)] = idwt_step(w1, w2, h, g)
+    return x

@@ -20,6 +20,7 @@ from .acwt import *           # noqa: E402,F401,F403
 from .bestbasis import *      # noqa: E402,F401,F403
 from .ldb import *            # noqa: E402,F401,F403
 from .denoising import *      # noqa: E402,F401,F403
+from .siwt import *           # noqa: E402,F401,F403
 from . import dist, host      # noqa: E402,F401
 
 launch_count = _lib.launch_count

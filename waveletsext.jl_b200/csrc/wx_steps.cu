@@ -82,13 +82,14 @@ static inline unsigned grid_for(long total) { return (unsigned)((total + kThread
 
 // a1 dwt_step!  dwt/dwt_one_level.jl:94-105
 template <typename T, int FF>
-__global__ void __launch_bounds__(kThreads) dwt_step_k(View<T> w1, View<T> w2, View<const T> v, long n, Geo geo, Taps<T> tp)
+__global__ void __launch_bounds__(kThreads) dwt_step_k(View<T> w1, View<T> w2, View<const T> v, long n, Geo geo, Taps<T> tp, int sh)
 {
     long i, b0, b1, b2;
     if (!decomp(geo, i, b0, b1, b2)) return;
     const T *pv = v.p + voff(v, b0, b1, b2);
     const int F = WX_F;
-    long k1 = 2 * i, k2 = 2 * i + 1;
+    long k1 = 2 * i - sh, k2 = 2 * i + 1 - sh;     // sh = 1: sidwt_step!(..., s = true) siwt/siwt_one_level.jl:88-89
+    if (k1 < 0) k1 += n;
     if (k2 >= n) k2 -= n;
     T a1 = tp.g[F - 1] * pv[k1 * v.es];
     T a2 = tp.h[0] * pv[k2 * v.es];
@@ -105,7 +106,7 @@ __global__ void __launch_bounds__(kThreads) dwt_step_k(View<T> w1, View<T> w2, V
 
 // a2 idwt_step! dwt/dwt_one_level.jl:207-221
 template <typename T, int FF>
-__global__ void __launch_bounds__(kThreads) idwt_step_k(View<T> v, View<const T> w1, View<const T> w2, long n, Geo geo, Taps<T> tp)
+__global__ void __launch_bounds__(kThreads) idwt_step_k(View<T> v, View<const T> w1, View<const T> w2, long n, Geo geo, Taps<T> tp, int sh)
 {
     long i0b, b0, b1, b2;
     if (!decomp(geo, i0b, b0, b1, b2)) return;
@@ -129,7 +130,9 @@ __global__ void __launch_bounds__(kThreads) idwt_step_k(View<T> v, View<const T>
         k2 += 1; if (k2 > n1) k2 -= n1;
         acc += fma(tp.g[j1 - 1], p1[(k1 - 1) * w1.es], tp.h[j2 - 1] * p2[(k2 - 1) * w2.es]);
     }
-    v.p[voff(v, b0, b1, b2) + i0b * v.es] = acc;
+    long l = i0b - sh;                             // sh = 1: isidwt_step!(..., s = true) siwt/siwt_one_level.jl:168
+    if (l < 0) l += n;
+    v.p[voff(v, b0, b1, b2) + l * v.es] = acc;
 }
 
 // a9 sdwt_step! swt/swt_one_level.jl:114-125  /  a16 acdwt_step! acwt/acwt_one_level.jl:115-126
@@ -269,25 +272,25 @@ static inline long btot(const Batch &b) { return b.B0 * b.B1 * b.B2; }
 }  // namespace
 
 template <typename T>
-int wx_launch_dwt_step(View<T> w1, View<T> w2, View<const T> v, long n, Batch b, const Taps<T> &t, cudaStream_t s)
+int wx_launch_dwt_step(View<T> w1, View<T> w2, View<const T> v, long n, Batch b, const Taps<T> &t, cudaStream_t s, int shift)
 {
     WX_REQUIRE(n >= 2 && n % 2 == 0, "dwt_step: parent length %ld must be even and >= 2", n);
     long total = (n / 2) * btot(b);
     if (total == 0) return WX_OK;
     const Geo geo = make_geo(n / 2, b);
-    WX_DISPATCH_F(t.F, (dwt_step_k<T, FF><<<grid_for(total), kThreads, 0, s>>>(w1, w2, v, n, geo, t)))
+    WX_DISPATCH_F(t.F, (dwt_step_k<T, FF><<<grid_for(total), kThreads, 0, s>>>(w1, w2, v, n, geo, t, shift)))
     WX_LAUNCHED();
     return WX_OK;
 }
 
 template <typename T>
-int wx_launch_idwt_step(View<T> v, View<const T> w1, View<const T> w2, long n, Batch b, const Taps<T> &t, cudaStream_t s)
+int wx_launch_idwt_step(View<T> v, View<const T> w1, View<const T> w2, long n, Batch b, const Taps<T> &t, cudaStream_t s, int shift)
 {
     WX_REQUIRE(n >= 2 && n % 2 == 0, "idwt_step: parent length %ld must be even and >= 2", n);
     long total = n * btot(b);
     if (total == 0) return WX_OK;
     const Geo geo = make_geo(n, b);
-    WX_DISPATCH_F(t.F, (idwt_step_k<T, FF><<<grid_for(total), kThreads, 0, s>>>(v, w1, w2, n, geo, t)))
+    WX_DISPATCH_F(t.F, (idwt_step_k<T, FF><<<grid_for(total), kThreads, 0, s>>>(v, w1, w2, n, geo, t, shift)))
     WX_LAUNCHED();
     return WX_OK;
 }
@@ -357,8 +360,8 @@ int wx_launch_copy(View<T> dst, View<const T> src, long n, Batch b, cudaStream_t
 }
 
 #define WX_INST(T)                                                                                                               \
-    template int wx_launch_dwt_step<T>(View<T>, View<T>, View<const T>, long, Batch, const Taps<T> &, cudaStream_t);             \
-    template int wx_launch_idwt_step<T>(View<T>, View<const T>, View<const T>, long, Batch, const Taps<T> &, cudaStream_t);      \
+    template int wx_launch_dwt_step<T>(View<T>, View<T>, View<const T>, long, Batch, const Taps<T> &, cudaStream_t, int);             \
+    template int wx_launch_idwt_step<T>(View<T>, View<const T>, View<const T>, long, Batch, const Taps<T> &, cudaStream_t, int);      \
     template int wx_launch_rdwt_step<T>(int, View<T>, View<T>, View<const T>, long, int, Batch, const Taps<T> &, cudaStream_t);  \
     template int wx_launch_isdwt_shift<T>(View<T>, View<const T>, View<const T>, long, int, long, long, int, Batch,              \
                                           const Taps<T> &, cudaStream_t);                                                        \
@@ -376,18 +379,77 @@ namespace {
 template <typename T> static View<const T> cview1(const T *p) { return View<const T>{p, 1, 0, 0, 0}; }
 
 template <typename T>
-int dwt_step_1d(T *w1, T *w2, const T *v, long n, const double *h, const double *g, int F, void *stream)
+int dwt_step_1d(T *w1, T *w2, const T *v, long n, const double *h, const double *g, int F, void *stream, int shift = 0)
 {
     WX_REQUIRE(w1 && w2 && v, "null signal pointer");
     Taps<T> t; int rc = wx_make_taps(t, h, g, F); if (rc) return rc;
-    return wx_launch_dwt_step<T>(view1(w1), view1(w2), cview1(v), n, batch1(), t, (cudaStream_t)stream);
+    return wx_launch_dwt_step<T>(view1(w1), view1(w2), cview1(v), n, batch1(), t, (cudaStream_t)stream, shift ? 1 : 0);
 }
 template <typename T>
-int idwt_step_1d(T *v, const T *w1, const T *w2, long n, const double *h, const double *g, int F, void *stream)
+int idwt_step_1d(T *v, const T *w1, const T *w2, long n, const double *h, const double *g, int F, void *stream, int shift = 0)
 {
     WX_REQUIRE(w1 && w2 && v, "null signal pointer");
     Taps<T> t; int rc = wx_make_taps(t, h, g, F); if (rc) return rc;
-    return wx_launch_idwt_step<T>(view1(v), cview1(w1), cview1(w2), n, batch1(), t, (cudaStream_t)stream);
+    return wx_launch_idwt_step<T>(view1(v), cview1(w1), cview1(w2), n, batch1(), t, (cudaStream_t)stream, shift ? 1 : 0);
+}
+
+// ---- nonstandard-form transform (row f-4): ns_dwt / ns_idwt  wavemult/transforms.jl:52-74, 120-139 ----
+// ndyad(l, Lmax, gender) wavemult/utils.jl:146-155 -> 0-based start of the range, length 1 << (Lmax - l)
+static inline long ndyad0(int l, int Lmax, bool female) { const long k = Lmax - l; return female ? (1L << (k + 1)) + (1L << k) : (1L << (k + 1)); }
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) ns_add_k(T *__restrict__ out, const T *__restrict__ a, long as0, const T *__restrict__ b, long bs0, long len, long N)
+{
+    const long idx = (long)blockIdx.x * kThreads + threadIdx.x;
+    if (idx >= len * N) return;
+    const long k = idx / len, i = idx - k * len;
+    out[idx] = a[k * as0 + i] + b[k * bs0 + i];
+}
+
+template <typename T>
+int ns_dwt_impl(T *nxw, const T *x, long n, int L, long N, const double *h, const double *g, int F, cudaStream_t s)
+{
+    WX_REQUIRE(nxw && x && N >= 0, "bad arguments");
+    WX_REQUIRE(wx_ispow2(n), "AssertionError: ispow2(n)");
+    const int Lmax = wx_maxlevels(n);
+    WX_REQUIRE(1 <= L && L <= Lmax, "AssertionError: 1 <= L <= Lmax");
+    if (N == 0) return WX_OK;
+    Taps<T> t; int rc = wx_make_taps(t, h, g, F); if (rc) return rc;
+    WX_CUDA(cudaMemsetAsync(nxw, 0, (size_t)2 * n * N * sizeof(T), s));
+    const Batch b{N, 1, 1, false};
+    for (int l = 1; l <= L; ++l) {
+        View<T> w1{nxw + ndyad0(l, Lmax, false), 1, 2 * n, 0, 0}, w2{nxw + ndyad0(l, Lmax, true), 1, 2 * n, 0, 0};
+        View<const T> v = l == 1 ? View<const T>{x, 1, n, 0, 0} : View<const T>{nxw + ndyad0(l - 1, Lmax, false), 1, 2 * n, 0, 0};
+        rc = wx_launch_dwt_step<T>(w1, w2, v, n >> (l - 1), b, t, s); if (rc) return rc;
+    }
+    // nxw[1 : 1<<(Lmax-L)] = nxw[ndyad(L, Lmax, false)]
+    return wx_launch_copy<T>(View<T>{nxw, 1, 2 * n, 0, 0}, View<const T>{nxw + ndyad0(L, Lmax, false), 1, 2 * n, 0, 0}, 1L << (Lmax - L), b, s);
+}
+
+template <typename T>
+int ns_idwt_impl(T *x, const T *nxw, long n2, int L, long N, const double *h, const double *g, int F, cudaStream_t s)
+{
+    WX_REQUIRE(nxw && x && N >= 0 && n2 >= 2, "bad arguments");
+    const long n = n2 / 2;
+    WX_REQUIRE(wx_ispow2(n) && n2 == 2 * n, "AssertionError: ispow2(n)");
+    const int Lmax = wx_maxlevels(n2) - 1;
+    WX_REQUIRE(1 <= L && L <= Lmax, "AssertionError: 1 <= L <= Lmax");
+    if (N == 0) return WX_OK;
+    Taps<T> t; int rc = wx_make_taps(t, h, g, F); if (rc) return rc;
+    WX_CUDA(cudaMemsetAsync(x, 0, (size_t)n * N * sizeof(T), s));
+    const Batch b{N, 1, 1, false};
+    rc = wx_launch_copy<T>(View<T>{x, 1, n, 0, 0}, View<const T>{nxw, 1, n2, 0, 0}, 1L << (Lmax - L), b, s); if (rc) return rc;
+    T *tmp; rc = wx_scratch(&tmp, (size_t)(n / 2) * N, s); if (rc) return rc;
+    for (int l = L; l >= 1 && !rc; --l) {
+        const long len = 1L << (Lmax - l);
+        // w1 = nxw[ndyad(l, Lmax, false)] + x[1 : len]  (the reference materialises it before idwt_step! overwrites x)
+        ns_add_k<T><<<grid_for(len * N), kThreads, 0, s>>>(tmp, nxw + ndyad0(l, Lmax, false), n2, x, n, len, N);
+        wx_launches.fetch_add(1, std::memory_order_relaxed);
+        rc = wx_launch_idwt_step<T>(View<T>{x, 1, n, 0, 0}, View<const T>{tmp, 1, len, 0, 0}, View<const T>{nxw + ndyad0(l, Lmax, true), 1, n2, 0, 0}, 2 * len, b, t, s);
+    }
+    int rc2 = wx_scratch_free(tmp, s);
+    if (!rc) WX_CUDA(cudaGetLastError());
+    return rc ? rc : rc2;
 }
 template <typename T>
 int rdwt_step_1d(int ac, T *w1, T *w2, const T *v, long n, int d, const double *h, const double *g, int F, void *stream)
@@ -511,6 +573,14 @@ int wx_dwt_step_f64(double *w1, double *w2, const double *v, long n, const doubl
 int wx_dwt_step_f32(float *w1, float *w2, const float *v, long n, const double *h, const double *g, int F, void *s) { return dwt_step_1d<float>(w1, w2, v, n, h, g, F, s); }
 int wx_idwt_step_f64(double *v, const double *w1, const double *w2, long n, const double *h, const double *g, int F, void *s) { return idwt_step_1d<double>(v, w1, w2, n, h, g, F, s); }
 int wx_idwt_step_f32(float *v, const float *w1, const float *w2, long n, const double *h, const double *g, int F, void *s) { return idwt_step_1d<float>(v, w1, w2, n, h, g, F, s); }
+int wx_sidwt_step_f64(double *w1, double *w2, const double *v, long n, const double *h, const double *g, int F, int shifted, void *s) { return dwt_step_1d<double>(w1, w2, v, n, h, g, F, s, shifted); }
+int wx_sidwt_step_f32(float *w1, float *w2, const float *v, long n, const double *h, const double *g, int F, int shifted, void *s) { return dwt_step_1d<float>(w1, w2, v, n, h, g, F, s, shifted); }
+int wx_isidwt_step_f64(double *v, const double *w1, const double *w2, long n, const double *h, const double *g, int F, int shifted, void *s) { return idwt_step_1d<double>(v, w1, w2, n, h, g, F, s, shifted); }
+int wx_isidwt_step_f32(float *v, const float *w1, const float *w2, long n, const double *h, const double *g, int F, int shifted, void *s) { return idwt_step_1d<float>(v, w1, w2, n, h, g, F, s, shifted); }
+int wx_ns_dwt_f64(double *nxw, const double *x, long n, int L, long N, const double *h, const double *g, int F, void *s) { return ns_dwt_impl<double>(nxw, x, n, L, N, h, g, F, (cudaStream_t)s); }
+int wx_ns_dwt_f32(float *nxw, const float *x, long n, int L, long N, const double *h, const double *g, int F, void *s) { return ns_dwt_impl<float>(nxw, x, n, L, N, h, g, F, (cudaStream_t)s); }
+int wx_ns_idwt_f64(double *x, const double *nxw, long n2, int L, long N, const double *h, const double *g, int F, void *s) { return ns_idwt_impl<double>(x, nxw, n2, L, N, h, g, F, (cudaStream_t)s); }
+int wx_ns_idwt_f32(float *x, const float *nxw, long n2, int L, long N, const double *h, const double *g, int F, void *s) { return ns_idwt_impl<float>(x, nxw, n2, L, N, h, g, F, (cudaStream_t)s); }
 int wx_sdwt_step_f64(double *w1, double *w2, const double *v, long n, int d, const double *h, const double *g, int F, void *s) { return rdwt_step_1d<double>(0, w1, w2, v, n, d, h, g, F, s); }
 int wx_sdwt_step_f32(float *w1, float *w2, const float *v, long n, int d, const double *h, const double *g, int F, void *s) { return rdwt_step_1d<float>(0, w1, w2, v, n, d, h, g, F, s); }
 int wx_acdwt_step_f64(double *w1, double *w2, const double *v, long n, int d, const double *h, const double *g, int Lf, void *s) { return rdwt_step_1d<double>(1, w1, w2, v, n, d, h, g, Lf, s); }

@@ -21,9 +21,9 @@ static inline Batch batch1() { return Batch{1, 1, 1, false}; }
 
 // forward steps ---------------------------------------------------------------------------------
 // dwt_step!  dwt/dwt_one_level.jl:79-107 ; v length n -> w1,w2 length n/2
-template <typename T> int wx_launch_dwt_step(View<T> w1, View<T> w2, View<const T> v, long n, Batch b, const Taps<T> &t, cudaStream_t s);
+template <typename T> int wx_launch_dwt_step(View<T> w1, View<T> w2, View<const T> v, long n, Batch b, const Taps<T> &t, cudaStream_t s, int shift = 0);
 // idwt_step! dwt/dwt_one_level.jl:192-223
-template <typename T> int wx_launch_idwt_step(View<T> v, View<const T> w1, View<const T> w2, long n, Batch b, const Taps<T> &t, cudaStream_t s);
+template <typename T> int wx_launch_idwt_step(View<T> v, View<const T> w1, View<const T> w2, long n, Batch b, const Taps<T> &t, cudaStream_t s, int shift = 0);
 // sdwt_step! swt/swt_one_level.jl:99-127 (ac = 0) / acdwt_step! acwt/acwt_one_level.jl:101-128 (ac = 1)
 template <typename T> int wx_launch_rdwt_step(int ac, View<T> w1, View<T> w2, View<const T> v, long n, int d, Batch b, const Taps<T> &t, cudaStream_t s);
 // isdwt_step! shift based swt/swt_one_level.jl:279-318 (writes only the sv coset of v)
