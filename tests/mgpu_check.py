@@ -69,6 +69,18 @@ def main():
         assert (xr - xl).abs().max().item() <= 1e-10 * xl.abs().max().item()
         if rank == 0:
             print(f"{type(method).__name__}: sharded == single (rel {rel:.2e}), tree nodes {int(t_sh.sum())}", flush=True)
+    # denoiseall: shard-local except for the bestTH summary over the noise levels of the WHOLE batch
+    dw = wx.dwtall(X, wt)
+    sh = wx.denoiseall(dw[lo:hi].contiguous(), "dwt", wt)
+    saved = wx.dist.is_dist
+    wx.dist.is_dist = lambda group=None: False
+    try:
+        one = wx.denoiseall(dw, "dwt", wt, bestTH=np.mean)
+        assert torch.equal(sh, wx.denoiseall(dw, "dwt", wt)[lo:hi])
+    finally:
+        wx.dist.is_dist = saved
+    shb = wx.denoiseall(dw[lo:hi].contiguous(), "dwt", wt, bestTH=np.mean)
+    assert torch.equal(shb, one[lo:hi]), "sharded denoiseall(bestTH) differs from the single-GPU result"
     dist.barrier()
     if rank == 0:
         print(f"mgpu_check ok on {world} GPUs", flush=True)

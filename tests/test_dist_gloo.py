@@ -70,6 +70,10 @@ def _worker(rank, world, port, q):
         g = [torch.empty_like(tot) for _ in range(world)]
         dist.all_gather(g, tot)
         assert torch.equal(g[0], g[1])                       # bitwise identical on every rank
+        # denoiseall's bestTH: per-signal noise levels of unequal shards, gathered in rank order
+        sig = np.arange(lo, hi, dtype=np.float64) * 0.5
+        allsig = wx.dist.allgather_host_vector(sig)
+        assert np.array_equal(allsig, np.arange(N) * 0.5)
         q.put((rank, "ok"))
     except Exception as e:      # pragma: no cover
         import traceback

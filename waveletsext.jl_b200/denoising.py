@@ -17,7 +17,7 @@ import torch
 
 from . import _dev as D
 from .utils import (maxtransformlevels, maketree, getleaf, isdyadic, nodelength, finestdetailrange, coarsestscalingrange)
-from . import dwt as _dwt, swt as _swt, acwt as _acwt
+from . import dwt as _dwt, swt as _swt, acwt as _acwt, dist as _dist
 
 __all__ = ["HardTH", "SoftTH", "SemiSoftTH", "SteinTH", "VisuShrink", "RelErrorShrink", "SureShrink", "noisest", "surethreshold",
            "relerrorthreshold", "threshold", "threshold_", "denoise", "denoiseall"]
@@ -233,13 +233,15 @@ def _estimate(X, estnoise, redundant, tree):
     return torch.tensor(vals, dtype=torch.float64, device=X.device)
 
 
-def denoiseall(x, inputtype: str, wt, L=None, tree=None, dnt=None, estnoise=noisest, bestTH=None, smooth: str = "regular"):
+def denoiseall(x, inputtype: str, wt, L=None, tree=None, dnt=None, estnoise=noisest, bestTH=None, smooth: str = "regular", group=None):
     """``denoiseall(x, inputtype, wt; L, tree, dnt, estnoise, bestTH, smooth)`` Denoising.jl:651-713 over ``denoise`` :483-600.
 
     x: (N, n) signals / dwt / wpt coefficients or (N, K, n) redundant tables (Julia (n, N) / (n, K, N)).  ``estnoise``: one of
     this module's estimators (run for the whole batch on the GPU), any callable ``(x_i, redundant, tree) -> float``, or a vector
     of N noise levels.  ``bestTH``: None or a function of the vector of noise levels (``np.mean``, ``np.median``).  ``wt = None``
-    returns the thresholded coefficients instead of reconstructing."""
+    returns the thresholded coefficients instead of reconstructing.  With an initialised process group x is this rank's shard of
+    the batch: nothing is exchanged unless ``bestTH`` is given, in which case the N noise levels are gathered (rank order) so that
+    the summary threshold is that of the whole batch."""
     inputtype = str(inputtype).lstrip(":")
     smooth = str(smooth).lstrip(":")
     assert inputtype in _TYPES, "AssertionError: inputtype in [:sig, :dwt, :wpt, :sdwt, :swpd, :acdwt, :acwpd]"
@@ -272,7 +274,7 @@ def denoiseall(x, inputtype: str, wt, L=None, tree=None, dnt=None, estnoise=nois
         sigma = torch.as_tensor(np.asarray(estnoise, dtype=np.float64)).to(X.device)
         assert sigma.numel() == N, "one noise level per signal"
     if bestTH is not None:
-        s = float(bestTH(sigma.cpu().numpy()))
+        s = float(bestTH(_dist.allgather_host_vector(sigma.cpu().numpy(), group)))
         t = s * dnt.t
     else:
         t = sigma * dnt.t

@@ -93,6 +93,18 @@ def allgather_parts(pair: torch.Tensor, group=None) -> torch.Tensor:
     return out
 
 
+def allgather_host_vector(v, group=None):
+    """concatenation, in rank order, of one small host vector per rank (shards may differ in length) -- the per-signal noise
+    levels a ``bestTH`` summary needs (Denoising.jl:684-705).  Host-side glue, like the user's ``bestTH`` function itself."""
+    import numpy as np
+    v = np.ascontiguousarray(np.asarray(v, dtype=np.float64))
+    if not (is_dist(group) and world_size(group) > 1):
+        return v
+    parts = [None] * world_size(group)
+    dist.all_gather_object(parts, v, group=group)
+    return np.concatenate(parts)
+
+
 def dd_sum_host(parts: torch.Tensor) -> torch.Tensor:
     """(nparts, 2, count) -> (2, count): the double-double sum in index order with elementwise torch ops (each op is
     correctly rounded; no fused multiply-add is involved).  Host mirror of ``wx_dd_sum`` for the gloo tests."""
