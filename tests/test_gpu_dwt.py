@@ -240,6 +240,22 @@ def test_wpd2d_parity(wx, O, cuda, dt, name, m, n, L):
 
 
 @pytest.mark.parametrize("dt", [np.float64, np.float32])
+@pytest.mark.parametrize("m,n,L", [(384, 96, 5), (160, 224, 4), (1024, 64, 6), (128, 32, 1), (256, 256, 5), (64, 64, 5), (48, 80, 3)])
+def test_wpd2d_haar_all_levels_kernel(wx, O, cuda, dt, m, n, L):
+    """two-tap filters: one launch keeps an image tile in shared memory for every level (no halo); tile shapes shrink to divide
+    the image, shapes that do not fit go through the level-by-level kernels -- all bit-identical to each other"""
+    import os
+    wt = wx.wavelet("haar")
+    h, g = pair(wx, wt)
+    x = np.random.default_rng(m * 7 + n + L).standard_normal((3, n, m)).astype(dt)
+    y = wx.wpdall(dev(x, cuda), wt, L)
+    ref = np.stack([O.wpd(x[k], h, g, L) for k in range(3)])
+    assert relerr(y.cpu().numpy(), ref) <= TOL[dt]
+    assert torch.equal(y[:, 0], dev(x, cuda))
+    assert relerr(wx.iwpdall(y, wt, L).cpu().numpy(), x) <= (1e-10 if dt == np.float64 else 3e-4)
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
 @pytest.mark.parametrize("name", ["haar", "db4", "sym8", "db10"])
 @pytest.mark.parametrize("m,n,L", [(256, 128, 4), (96, 160, 3), (512, 512, 5), (64, 1024, 2), (128, 128, 7)])
 def test_wpd2d_large_images(wx, O, cuda, dt, name, m, n, L):

@@ -90,8 +90,8 @@ __device__ __forceinline__ void warp_bitonic(T (&v)[E])
                 const int f = E - 1 - e;
                 const T o1 = shfl_xor_t(v[f], lm), o2 = shfl_xor_t(v[e], lm);
                 const T a = v[e], b = v[f];
-                v[e] = (keepmin ? (o1 < a) : (o1 > a)) ? o1 : a;
-                if (f != e) v[f] = (keepmin ? (o2 < b) : (o2 > b)) ? o2 : b;
+                v[e] = ((o1 < a) == keepmin) ? o1 : a;           // equal values: either copy will do
+                if (f != e) v[f] = ((o2 < b) == keepmin) ? o2 : b;
             }
         }
 #pragma unroll
@@ -105,7 +105,7 @@ __device__ __forceinline__ void warp_bitonic(T (&v)[E])
 #pragma unroll
                 for (int e = 0; e < E; ++e) {
                     const T o = shfl_xor_t(v[e], lm), a = v[e];
-                    v[e] = (keepmin ? (o < a) : (o > a)) ? o : a;
+                    v[e] = ((o < a) == keepmin) ? o : a;
                 }
             }
         }
@@ -139,12 +139,16 @@ __global__ void __launch_bounds__(32 * kWS) mad_warp_k(double *__restrict__ sigm
     T v[E];
 #pragma unroll
     for (int e = 0; e < E; ++e) { const int i = e * 32 + lane; v[e] = i < len ? src[i] : wx_inf<T>(); }     // any order will do
-    warp_bitonic<T, E>(v);
-    const T m = warp_median<T, E>(v, len);
+    T md = 0;
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {          // one copy of the (fully unrolled) network in the instruction stream
+        warp_bitonic<T, E>(v);
+        md = warp_median<T, E>(v, len);
+        if (pass == 0) {
 #pragma unroll
-    for (int e = 0; e < E; ++e) v[e] = (lane * E + e) < len ? (T)fabs(v[e] - m) : wx_inf<T>();
-    warp_bitonic<T, E>(v);
-    const T md = warp_median<T, E>(v, len);
+            for (int e = 0; e < E; ++e) v[e] = (lane * E + e) < len ? (T)fabs(v[e] - md) : wx_inf<T>();
+        }
+    }
     if (lane == 0) sigma[k] = (double)md / 0.6745;
 }
 
@@ -384,10 +388,14 @@ __global__ void __launch_bounds__(32 * kWS) relerr_warp_k(double *__restrict__ t
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) ymax = fmax(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
     const double x0 = 0.0 / xmax, y0 = (sqrt(fabs(S - S)) / rS) / ymax;          // point 0: (0, r_M)
+    // the normalised curve, once: X_p = x / xmax (kept in Float64 in place of Y's neighbour), Y_p = r / ymax
+    double X[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) { X[e] = (double)v[e] / xmax; Y[e] = Y[e] / ymax; }
     int end = M;
     for (int el = 0; el < elbows; ++el) {
-        const double xe = end > 0 ? (double)warp_elem<T, E>(v, end - 1) / xmax : x0;
-        const double ye = end > 0 ? warp_elem<double, E>(Y, end - 1) / ymax : y0;
+        const double xe = end > 0 ? warp_elem<double, E>(X, end - 1) : x0;
+        const double ye = end > 0 ? warp_elem<double, E>(Y, end - 1) : y0;
         double vx = xe - x0, vy = ye - y0;
         const double nv = sqrt(vx * vx + vy * vy);
         vx /= nv; vy /= nv;
@@ -397,7 +405,7 @@ __global__ void __launch_bounds__(32 * kWS) relerr_warp_k(double *__restrict__ t
         for (int e = 0; e < E; ++e) {
             const int p = lane * E + e + 1;
             if (p <= end) {
-                const double dx = (double)v[e] / xmax - x0, dy = Y[e] / ymax - y0;
+                const double dx = X[e] - x0, dy = Y[e] - y0;
                 const double H = sqrt(dx * dx + dy * dy), A = dx * vx + dy * vy;
                 const double O = sqrt(fabs(H * H - A * A));
                 if (bi < 0 || O > best) { best = O; bi = p; }
@@ -406,8 +414,8 @@ __global__ void __launch_bounds__(32 * kWS) relerr_warp_k(double *__restrict__ t
         warp_argext<true>(best, bi);
         end = bi < 0 ? 0 : bi;
     }
-    const double xsel = end ? (double)warp_elem<T, E>(v, end - 1) : 0.0;
-    if (lane == 0) t[k] = (xsel / xmax) * xmax;
+    const double xn = end ? warp_elem<double, E>(X, end - 1) : 0.0 / xmax;
+    if (lane == 0) t[k] = xn * xmax;
 }
 
 // ---- thresholding ----------------------------------------------------------------------------------------

@@ -394,6 +394,102 @@ __global__ void __launch_bounds__(kT2, 3) wpd2d_block_k(T *__restrict__ y, const
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Two-tap filters (haar): no halo, so a TR x TC tile of the IMAGE determines a (TR>>l) x (TC>>l) patch of every node of every
+// level.  One CTA keeps the tile in shared memory, runs all L levels there (one 2 x 2 butterfly per thread per step: column pass
+// and row pass fused in registers, same tap order as the separate passes) and scatters each level's patches to its slice: the
+// whole transform moves exactly the algorithmic (L+2) image sizes.  TR, TC are powers of two, TR >> L >= 2.
+// ---------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kT2) wpd2d_haar_k(T *__restrict__ y, const T *__restrict__ x, int m, int n, int L, int lr, int lc, Div32 dtiles, Div32 dtiles_r,
+                                                   Taps<T> tp)
+{
+    using P2 = typename Pair<T>::type;
+    extern __shared__ __align__(16) unsigned char wx_2d_smem[];
+    const int TR = 1 << lr, TC = 1 << lc, TR2 = TR >> 1;
+    T *A = reinterpret_cast<T *>(wx_2d_smem);
+    T *B = A + TR * TC;
+    const int tid = threadIdx.x;
+    const unsigned k = div32(blockIdx.x, dtiles), tl = blockIdx.x - k * dtiles.d;
+    const unsigned tcx = div32(tl, dtiles_r), trx = tl - tcx * dtiles_r.d;          // neighbouring CTAs walk down the rows
+    const int R0 = (int)trx << lr, C0 = (int)tcx << lc;
+    const long img = (long)m * n;
+    T *yk = y + (long)k * img * (L + 1);
+    const T *xk = x + (long)k * img + (long)C0 * m + R0;
+    const int npairs = TR2 * TC;
+    for (int q = tid; q < npairs; q += kT2) {
+        const int c = q >> (lr - 1), r2 = q & (TR2 - 1);
+        cp_async_pair<T>(A + c * TR + 2 * r2, xk + (long)c * m + 2 * r2);
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    {                                                     // y[:,:,1] = x   DWT.jl:176
+        T *y0 = yk + (long)C0 * m + R0;
+        for (int q = tid; q < npairs; q += kT2) {
+            const int c = q >> (lr - 1), r2 = q & (TR2 - 1);
+            *reinterpret_cast<P2 *>(y0 + (long)c * m + 2 * r2) = *reinterpret_cast<const P2 *>(A + c * TR + 2 * r2);
+        }
+    }
+    T *src = A, *dst = B;
+    for (int l = 0; l < L; ++l) {
+        // sub-block (a, b) of the tile at this level: rows a*mpl .., cols b*npl ..; its four children land in its quadrants
+        const int lm = lr - l, ln = lc - l;               // log2 of the sub-block extents
+        const int hr = 1 << (lm - 1), hc = 1 << (ln - 1);
+        const int nblk = TR2 * (TC >> 1);
+        for (int q = tid; q < nblk; q += kT2) {
+            const int ig = q & (TR2 - 1), jg = q >> (lr - 1);
+            const int a = ig >> (lm - 1), il = ig & (hr - 1), b = jg >> (ln - 1), jl = jg & (hc - 1);
+            const P2 v0 = *reinterpret_cast<const P2 *>(src + (2 * jg) * TR + 2 * ig);
+            const P2 v1 = *reinterpret_cast<const P2 *>(src + (2 * jg + 1) * TR + 2 * ig);
+            T w[2], lo0, hi0, lo1, hi1, ll, lh, hl, hh;
+            w[0] = v0.x; w[1] = v0.y; dwt_dots<T, 2>(w, tp, lo0, hi0);          // column pass, column 2jg
+            w[0] = v1.x; w[1] = v1.y; dwt_dots<T, 2>(w, tp, lo1, hi1);          // column 2jg+1
+            w[0] = lo0; w[1] = lo1; dwt_dots<T, 2>(w, tp, ll, lh);              // row pass over the scaling rows
+            w[0] = hi0; w[1] = hi1; dwt_dots<T, 2>(w, tp, hl, hh);              // ... and the detail rows
+            T *o = dst + ((b << ln) + jl) * TR + (a << lm) + il;
+            o[0] = ll; o[hr] = hl; o[hc * TR] = lh; o[hc * TR + hr] = hh;
+        }
+        __syncthreads();
+        // ---- scatter the level l+1 patches: sub-block (a', b') of extent (TR >> (l+1)) x (TC >> (l+1)) -> node (a', b') ----
+        const int lv = l + 1, er = lr - lv, ec = lc - lv; // log2 extents
+        const int mn = m >> lv, nn = n >> lv, r0 = R0 >> lv, c0 = C0 >> lv;
+        T *yl = yk + (long)lv * img;
+        for (int q = tid; q < npairs; q += kT2) {
+            const int c = q >> (lr - 1), r = 2 * (q & (TR2 - 1));
+            const int a = r >> er, ri = r & ((1 << er) - 1), b = c >> ec, ci = c & ((1 << ec) - 1);
+            *reinterpret_cast<P2 *>(yl + (long)(b * nn + c0 + ci) * m + a * mn + r0 + ri) = *reinterpret_cast<const P2 *>(dst + c * TR + r);
+        }
+        T *t2 = src; src = dst; dst = t2;                 // the next step reads what this one wrote (complete after the barrier above);
+        // its writes go to the buffer the scatter above does not read -- no barrier needed here
+    }
+}
+
+template <typename T>
+int wpd2d_haar_run(T *y, const T *x, long m, long n, int L, long N, const Taps<T> &t, cudaStream_t s, bool *done)
+{
+    *done = false;
+    static const bool off = getenv("WX_B200_NO_HAAR2D") != nullptr;
+    if (off) return WX_OK;
+    WxDev dv; int rc = wx_devinfo(dv); if (rc) return rc;
+    int lr = sizeof(T) == 8 ? 7 : 8, lc = 5;              // 128 (Float64) / 256 (Float32) x 32 tile: 64 KB for the two buffers, three CTAs
+                                                          // per SM; the deepest level of L = 5 still stores 32-byte runs
+    while ((1 << lc) < (1 << L)) ++lc;                    // every level needs at least one column ...
+    while ((1 << lr) < (2 << L)) ++lr;                    // ... and one row PAIR per node patch (16-byte stores)
+    while (lr > 1 && (m % (1L << lr)) != 0 && (1 << (lr - 1)) >= (2 << L)) --lr;
+    while (lc > 0 && (n % (1L << lc)) != 0 && (1 << (lc - 1)) >= (1 << L)) --lc;
+    if (m % (1L << lr) != 0 || n % (1L << lc) != 0) return WX_OK;
+    const size_t smem = (size_t)2 * sizeof(T) << (lr + lc);
+    if (smem > dv.smem_optin) return WX_OK;
+    const long tiles_r = m >> lr, tiles = tiles_r * (n >> lc);
+    if (tiles * N >= (1L << 31)) return WX_OK;
+    auto kern = wpd2d_haar_k<T>;
+    WX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)(tiles * N), kT2, smem, s>>>(y, x, (int)m, (int)n, L, lr, lc, make_div32(tiles), make_div32(tiles_r), t);
+    WX_LAUNCHED();
+    *done = true;
+    return WX_OK;
+}
+
 static int largest_divisor_le(long v, int cap)
 {
     int best = 1;
@@ -484,6 +580,12 @@ int wx_wpd2d_fused(T *y, const T *x, long m, long n, int L, long N, const Taps<T
     if (((((uintptr_t)y) | ((uintptr_t)x)) & 15) != 0) return WX_OK;
     if ((m >> (L - 1)) % 2 != 0 || (n >> (L - 1)) % 2 != 0) return WX_OK;
     int rc;
+    if (t.F == 2) {
+        bool done = false;
+        rc = wpd2d_haar_run<T>(y, x, m, n, L, N, t, s, &done);
+        if (rc) return rc;
+        if (done) { *handled = true; return WX_OK; }
+    }
 #define WX_2D_CASE(FF) case FF: rc = wpd2d_run<T, FF>(y, x, m, n, L, N, t, s); break;
     switch (t.F) {
         WX_2D_CASE(2) WX_2D_CASE(4) WX_2D_CASE(6) WX_2D_CASE(8) WX_2D_CASE(10) WX_2D_CASE(12) WX_2D_CASE(16) WX_2D_CASE(20)
