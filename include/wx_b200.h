@@ -211,6 +211,16 @@ int wx_relerrorthreshold_f64(double *t, const double *x, long n, long K, const u
 int wx_relerrorthreshold_f32(double *t, const float *x, long n, long K, const unsigned char *colmask, int elbows, long N, void *stream);
 int wx_threshold_f64(double *y, const double *x, long n, long K, const unsigned char *colmask, long keep_lo, long keep_hi, int th, const double *sigma, double tmul, long N, void *stream);
 int wx_threshold_f32(float *y, const float *x, long n, long K, const unsigned char *colmask, long keep_lo, long keep_hi, int th, const double *sigma, double tmul, long N, void *stream);
+/* LDB object, feature side (LDB.jl:246-330): out(nf, N) = X(nelem, N)[order[0..nf), :] (transform / fit_transform :291-294,
+ * :349-352), its inverse onto a zero-filled Xc (inverse_transform :372-378), and the per-class mean / corrected variance of every
+ * coefficient for FishersClassSeparability (ldb/ldb_measures.jl:441-479): E, V (nc, nelem) Float64; sig_dev = signal indices
+ * grouped by class, off_dev = nc+1 group offsets.  order_dev: 0-based int32 on the device. */
+int wx_select_features_f64(double *out, const double *X, const int *order_dev, long nf, long nelem, long N, void *stream);
+int wx_select_features_f32(float *out, const float *X, const int *order_dev, long nf, long nelem, long N, void *stream);
+int wx_scatter_features_f64(double *Xc, const double *F, const int *order_dev, long nf, long nelem, long N, void *stream);
+int wx_scatter_features_f32(float *Xc, const float *F, const int *order_dev, long nf, long nelem, long N, void *stream);
+int wx_class_moments_f64(double *E, double *V, const double *X, const int *sig_dev, const int *off_dev, int nc, long nelem, void *stream);
+int wx_class_moments_f32(double *E, double *V, const float *X, const int *sig_dev, const int *off_dev, int nc, long nelem, void *stream);
 /* bestbasis_treeselection  BestBasis.jl:59-110 (host, O(n)); costs are modified in place like the reference.
  * m = 0: binary tree with n-1 entries; m > 0: quad tree. minmax 0 = :min, 1 = :max */
 int wx_tree_select(unsigned char *tree_out, double *costs_host, long ncosts, long m, long n, int minmax);

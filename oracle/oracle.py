@@ -866,3 +866,69 @@ def ns_idwt(nxw, q, L=None):
         w2 = nxw[slice(*ndyad(l, Lmax, True))]
         x[:1 << (Lmax - l + 1)] = idwt_step(w1, w2, h, g)
     return x
+
+
+# ------------------------------------------------------------------ LDB object (fitdec! / transform), numpy restatement
+def ldb_costs_topk(DM, top_k):
+    """node costs of fitdec! LDB.jl:217-237 incl. the top_k < node size branch (sort descending, sum the first top_k)"""
+    DM = np.asarray(DM)
+    def cost(v):
+        v = v.reshape(-1)
+        return np.sort(v)[::-1][:top_k].sum() if top_k < v.size else v.sum()
+    if DM.ndim == 2:
+        K, n = DM.shape
+        return np.array([cost(DM[d, j * (n >> d):(j + 1) * (n >> d)]) for d in range(K) for j in range(1 << d)], DM.dtype)
+    K, nc_, nr = DM.shape
+    out = []
+    for i in range(1, (4 ** K - 1) // 3 + 1):
+        d = getdepth(i, "quad")
+        r0, c0, rr, cc = quadrange(nr, nc_, i)
+        out.append(cost(DM[d, c0:c0 + cc, r0:r0 + rr]))
+    return np.array(out, DM.dtype)
+
+
+def discriminant_power_basis(DM, tree):
+    """discriminant_power(D, tree, BasisDiscriminantMeasure()) ldb/ldb_measures.jl:427-439 -> (power, order 0-based)"""
+    power = getbasiscoef(np.ascontiguousarray(DM), tree)
+    order = np.argsort(-power.reshape(-1), kind="stable")
+    return power, order
+
+
+def discriminant_power_fisher(coefs, y):
+    """discriminant_power(coefs, y, FishersClassSeparability()) ldb/ldb_measures.jl:441-479.  coefs (N, n[, m])"""
+    coefs = np.asarray(coefs); y = list(y)
+    classes = list(dict.fromkeys(y))
+    N = coefs.shape[0]
+    flat = coefs.reshape(N, -1)
+    E = np.empty((flat.shape[1], len(classes)), coefs.dtype); V = np.empty_like(E); Ni = np.empty(len(classes), coefs.dtype)
+    for i, c in enumerate(classes):
+        idx = [k for k, v in enumerate(y) if v == c]
+        Ni[i] = len(idx)
+        E[:, i] = flat[idx].mean(axis=0)
+        V[:, i] = flat[idx].var(axis=0, ddof=1)
+    Ea = E.mean(axis=1, keepdims=True)
+    p = Ni / Ni.sum()
+    with np.errstate(divide="ignore", invalid="ignore"):
+        power = (((E - Ea * E) ** 2) @ p) / (V @ p)
+    order = np.argsort(-power, kind="stable")
+    return power.reshape(coefs.shape[1:]), order
+
+
+def ldb_fitdec(Xw, y, kind="are", p=2.0, top_k=None, dp="basis"):
+    """fitdec! LDB.jl:186-245 (TimeFrequency energy map) -> dict(G, DM, cost, tree, DP, order)"""
+    Xw = np.asarray(Xw)
+    nelem = int(np.prod(Xw.shape[2:]))
+    top_k = nelem if top_k is None else top_k
+    G = energy_map_tf(Xw, y)
+    DM = discriminant_measure(G, kind, p)
+    cost = ldb_costs_topk(DM, top_k)
+    if Xw.ndim == 3:
+        tree = tree_select(cost.copy(), Xw.shape[2], None, "max")
+    else:
+        tree = tree_select(cost.copy(), Xw.shape[3], Xw.shape[2], "max")
+    if dp == "basis":
+        DP, order = discriminant_power_basis(DM, tree)
+    else:
+        Xc = np.stack([getbasiscoef(Xw[i], tree) for i in range(Xw.shape[0])])
+        DP, order = discriminant_power_fisher(Xc, y)
+    return dict(G=G, DM=DM, cost=cost, tree=tree, DP=DP, order=order)
