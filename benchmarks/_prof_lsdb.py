@@ -1,0 +1,14 @@
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import waveletsext_b200 as wx
+dev = torch.device("cuda:0")
+n, N, L = 1024, 131072, 10
+wt = wx.wavelet("db4")
+x = torch.randn((N, n), dtype=torch.float64, device=dev)
+Xw = wx.wpdall(x, wt, L)
+del x
+for _ in range(2):
+    c = wx.tree_costs(Xw, wx.LSDB())
+    t = wx.bestbasistreeall(Xw, wx.BB())
+torch.cuda.synchronize()

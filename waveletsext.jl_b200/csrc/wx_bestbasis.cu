@@ -472,13 +472,11 @@ __global__ void __launch_bounds__(kT) lsdb_logpdf_part_k(double *part, const dou
 // kH threads share a position (each takes a slice of the CTA's signals).  The interpolation weight uses 1/delta instead of
 // 1/(g1-g0) and the logarithm is taken of the product of U consecutive pdf values (log of a product = sum of logs;
 // a zero pdf still gives -Inf, and U pdf values of order 1e-3..1e3 cannot over/underflow a double).
-constexpr int kL = 128, kH = 2;
-template <typename T>
+template <typename T, int kL, int kH, int U>
 __global__ void __launch_bounds__(kL * kH) lsdb_logpdf_smem_k(double *part, const double *dens, const double *stats, const T *X, long szK, long N,
                                                                long kchunk, double Ntot, int npts)
 {
     extern __shared__ double wx_dens[];
-    constexpr int U = 4;
     const int pos = threadIdx.x % kL, kh = threadIdx.x / kL;
     const long e = (long)blockIdx.x * kL + pos;
     const bool live = e < szK;
@@ -581,6 +579,9 @@ int lsdb_pass3(double *logsum, const double *counts, const double *stats, const 
     WxDev dv; int rc = wx_devinfo(dv); if (rc) return rc;
     const int ksplit = pick_ksplit(szK, Nlocal, dv.sms);
     const long kchunk = (Nlocal + ksplit - 1) / ksplit;
+    static const char *env = getenv("WX_B200_LSDB_P3");       // measurement knob: (positions per CTA, threads per position, logs fused)
+    const int variant = env ? atoi(env) : 3;
+    const int kL = variant >= 6 ? 32 : (variant >= 2 ? 64 : 128), kH = variant >= 6 ? 8 : (variant >= 2 ? 4 : 2);
     double *dens, *part;
     rc = wx_scratch(&dens, (size_t)g.npts * szK, s); if (rc) return rc;
     rc = wx_scratch(&part, (size_t)ksplit * kH * 2 * szK, s); if (rc) return rc;
@@ -590,9 +591,14 @@ int lsdb_pass3(double *logsum, const double *counts, const double *stats, const 
     int nparts = ksplit;
     if (smem <= dv.smem_optin) {
         dim3 grid((unsigned)((szK + kL - 1) / kL), (unsigned)ksplit);
-        auto kern = lsdb_logpdf_smem_k<T>;
-        WX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, kL * kH, smem, s>>>(part, dens, stats, X, szK, Nlocal, kchunk, (double)Ntotal, (int)g.npts);
+#define WX_P3(LL, HH, UU) { auto kern = lsdb_logpdf_smem_k<T, LL, HH, UU>; \
+        WX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        kern<<<grid, LL * HH, smem, s>>>(part, dens, stats, X, szK, Nlocal, kchunk, (double)Ntotal, (int)g.npts); }
+        switch (variant) {
+            case 0: WX_P3(128, 2, 4) break; case 1: WX_P3(128, 2, 8) break; case 2: WX_P3(64, 4, 4) break; default: WX_P3(64, 4, 8) break;
+            case 4: WX_P3(64, 4, 16) break; case 5: WX_P3(64, 4, 12) break; case 6: WX_P3(32, 8, 8) break; case 7: WX_P3(32, 8, 16) break;
+        }
+#undef WX_P3
         nparts = ksplit * kH;
     } else {
         dim3 grid((unsigned)((szK + kT - 1) / kT), (unsigned)ksplit);
