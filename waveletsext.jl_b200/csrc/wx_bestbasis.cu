@@ -145,7 +145,7 @@ __device__ __forceinline__ void dd_add(double &hi, double &lo, double bh, double
 template <typename T, int V>
 __global__ void __launch_bounds__(kT) lsdb_stats_part_k(double *part, const T *X, const double *shift, long szK, long N, long kchunk)
 {
-    constexpr int U = 8;
+    constexpr int U = 4;
     using VT = typename std::conditional<V == 1, T, typename std::conditional<sizeof(T) == 8, double2, float4>::type>::type;
     const long e = ((long)blockIdx.x * kT + threadIdx.x) * V;
     if (e >= szK) return;
@@ -168,12 +168,22 @@ __global__ void __launch_bounds__(kT) lsdb_stats_part_k(double *part, const T *X
     };
     const T *p = X + e;
     long k = k0;
-    for (; k + U <= k1; k += U) {
-        VT r[U];
+    if (k + U <= k1) {
+        // software pipeline: the next U loads are in flight while the current U samples go through the double-double chains
+        VT cur[U], nxt[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) r[u] = __ldcs(reinterpret_cast<const VT *>(p + (k + u) * szK));
+        for (int u = 0; u < U; ++u) cur[u] = __ldcs(reinterpret_cast<const VT *>(p + (k + u) * szK));
+        for (; k + 2 * U <= k1; k += U) {
 #pragma unroll
-        for (int u = 0; u < U; ++u) take(r[u]);
+            for (int u = 0; u < U; ++u) nxt[u] = __ldcs(reinterpret_cast<const VT *>(p + (k + U + u) * szK));
+#pragma unroll
+            for (int u = 0; u < U; ++u) take(cur[u]);
+#pragma unroll
+            for (int u = 0; u < U; ++u) cur[u] = nxt[u];
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) take(cur[u]);
+        k += U;
     }
     for (; k < k1; ++k) take(__ldcs(reinterpret_cast<const VT *>(p + k * szK)));
     double *o = part + ((long)blockIdx.y * 6) * szK + e;
