@@ -22,23 +22,24 @@ int wpdall_host(T *y, const T *x, long n, int L, long N, const double *h, const 
         if (chunk < 1) chunk = 1;
     }
     if (chunk > N) chunk = N;
+    { WxDev dv; int rc0 = wx_devinfo(dv); if (rc0) return rc0; }      // also keeps freed pool blocks cached across calls
     cudaStream_t st[kSlots] = {nullptr, nullptr, nullptr};
     T *dx[kSlots] = {nullptr, nullptr, nullptr}, *dy[kSlots] = {nullptr, nullptr, nullptr};
     int rc = WX_OK;
     auto cleanup = [&]() {
         for (int i = 0; i < kSlots; ++i) {
             if (st[i]) cudaStreamSynchronize(st[i]);
-            if (dx[i]) cudaFree(dx[i]);
-            if (dy[i]) cudaFree(dy[i]);
-            if (st[i]) cudaStreamDestroy(st[i]);
+            if (dx[i]) cudaFreeAsync(dx[i], st[i]);         // back to the default pool (release threshold = max, wx_devinfo):
+            if (dy[i]) cudaFreeAsync(dy[i], st[i]);         // the next call reuses the slots instead of paying cudaMalloc again
+            if (st[i]) { cudaStreamSynchronize(st[i]); cudaStreamDestroy(st[i]); }
         }
     };
     const long nchunks = (N + chunk - 1) / chunk;
     const int slots = nchunks < kSlots ? (int)nchunks : kSlots;
     for (int i = 0; i < slots; ++i) {
         cudaError_t e = cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking);
-        if (e == cudaSuccess) e = cudaMalloc((void **)&dx[i], in_b * (size_t)chunk);
-        if (e == cudaSuccess) e = cudaMalloc((void **)&dy[i], out_b * (size_t)chunk);
+        if (e == cudaSuccess) e = cudaMallocAsync((void **)&dx[i], in_b * (size_t)chunk, st[i]);
+        if (e == cudaSuccess) e = cudaMallocAsync((void **)&dy[i], out_b * (size_t)chunk, st[i]);
         if (e != cudaSuccess) {
             cleanup();
             cudaGetLastError();
