@@ -131,7 +131,9 @@ def run_reference(a):
     spec = util.spec_from_file_location("wx_filters", os.path.join(ROOT, "waveletsext.jl_b200", "filters.py"))
     F = util.module_from_spec(spec); sys.modules["wx_filters"] = F; spec.loader.exec_module(F)
     q = F.wavelet(a.wavelet).taps
-    threads = O.max_threads()
+    # every host core this process may run on -- NOT omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1 to its workers, which
+    # would silently turn the all-core reference arm into a single-thread run at N > 1
+    threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     dt = np.float64 if a.dtype == "f64" else np.float32
     ns = 4096                                               # signals per step (bounded sample of the 65536-signal workload)
     x = np.random.default_rng(20242).standard_normal((ns, a.n)).astype(dt)
