@@ -294,6 +294,11 @@ def main():
             xr = wx.iwptall(wx.getbasiscoefall(Xw, tree), wt, tree)
             report("getbasiscoefall+iwptall_f64", ms, nl, 3 * 8 * n * N, n * N, "GSamples_per_s",
                    {"tree_nodes": int(tree.sum()), "roundtrip_relerr": float((xr - x).abs().max() / x.abs().max())})
+            # the same reconstruction in one launch: iwpdall gathers the best-basis coefficients from the table inside the kernel
+            ms, nl = timeit(lambda: wx.iwpdall(Xw, wt, tree), steps=3, warmup=1)
+            xr = wx.iwpdall(Xw, wt, tree)
+            report("iwpdall_fused_gather_f64", ms, nl, 2 * 8 * n * N, n * N, "GSamples_per_s",
+                   {"roundtrip_relerr": float((xr - x).abs().max() / x.abs().max())})
 
 
 if __name__ == "__main__":
