@@ -241,6 +241,58 @@ __device__ __forceinline__ void load_window_pairs(T *win, const T *src, int star
     }
 }
 
+// One level of the whole-node kernel with EVERYTHING known at compile time: block edge BE, current node edge MPL (both powers
+// of two, MPL/2 a multiple of KSEG and KROW).  Node / offset splits are shifts, periodic wraps are masks (any number of wraps,
+// so filters longer than the node need no special case), and the integer work per output drops to a few instructions.
+template <typename T, int F, int BE, int MPL>
+__device__ __forceinline__ void wpd2d_block_level_ct(T *__restrict__ A, T *__restrict__ Tm, const Taps<T> &tp, int tid)
+{
+    using P2 = typename Pair<T>::type;
+    constexpr int S = (F - 2) / 2, LDA = wx_ld_pairs(BE), LDT = wx_ld_odd(BE);
+    constexpr int HR = MPL / 2, WS = 2 * KSEG + F - 2, WR = 2 * KROW + F - 2;
+    // ---- column pass A -> Tm ----
+    for (int t = tid; t < (BE / 2 / KSEG) * BE; t += kT2) {
+        const int sg = t / BE, c = t % BE, ig0 = sg * KSEG;
+        const int r0 = (ig0 / HR) * MPL, il0 = ig0 % HR;
+        const T *src = A + c * LDA + r0;
+        T win[WS];
+#pragma unroll
+        for (int q = 0; q < WS / 2; ++q) {
+            const P2 v = *reinterpret_cast<const P2 *>(src + ((2 * il0 + 2 * q) & (MPL - 1)));
+            win[2 * q] = v.x; win[2 * q + 1] = v.y;
+        }
+        T *dst = Tm + c * LDT + r0;
+#pragma unroll
+        for (int p = 0; p < KSEG; ++p) {
+            T lo, hi;
+            dwt_dots<T, F>(&win[2 * p], tp, lo, hi);
+            dst[il0 + p] = lo;
+            dst[HR + ((il0 + S + p) & (HR - 1))] = hi;
+        }
+    }
+    __syncthreads();
+    // ---- row pass Tm -> A ----
+    {
+        const int r = tid % BE;
+        for (int g = tid / BE; g < BE / (2 * KROW); g += kT2 / BE) {
+            const int kg0 = KROW * g, c0 = (kg0 / HR) * MPL, kl0 = kg0 % HR;
+            const T *src = Tm + c0 * LDT + r;
+            T win[WR];
+#pragma unroll
+            for (int j = 0; j < WR; ++j) win[j] = src[((2 * kl0 + j) & (MPL - 1)) * LDT];
+            T *dst = A + c0 * LDA + r;
+#pragma unroll
+            for (int p = 0; p < KROW; ++p) {
+                T lo, hi;
+                dwt_dots<T, F>(&win[2 * p], tp, lo, hi);
+                dst[(kl0 + p) * LDA] = lo;
+                dst[(HR + ((kl0 + S + p) & (HR - 1))) * LDA] = hi;
+            }
+        }
+    }
+    __syncthreads();
+}
+
 // BE > 0: square block of edge BE known at compile time (padded leading dimensions, sliding-window column pass)
 template <typename T, int F, int BE>
 __global__ void __launch_bounds__(kT2, 3) wpd2d_block_k(T *__restrict__ y, const T *__restrict__ x, int m, int n, int L, int db, int dend,
@@ -279,6 +331,15 @@ __global__ void __launch_bounds__(kT2, 3) wpd2d_block_k(T *__restrict__ y, const
     }
     for (int l = db; l < dend; ++l) {
         const int mpl = m >> l, npl = n >> l, hr = mpl / 2, hc = npl / 2;
+        if (BE == 64 && kT2 % 64 == 0 && mpl == npl && mpl >= 16) {
+            // compile-time-shaped levels (node edge 64, 32, 16): both passes with constant geometry
+            if (mpl == 64) wpd2d_block_level_ct<T, F, (BE > 0 ? BE : 64), 64>(A, Tm, tp, tid);
+            else if (mpl == 32) wpd2d_block_level_ct<T, F, (BE > 0 ? BE : 64), 32>(A, Tm, tp, tid);
+            else wpd2d_block_level_ct<T, F, (BE > 0 ? BE : 64), 16>(A, Tm, tp, tid);
+            T *ynext = yk + (long)(l + 1) * img + org;
+            for (int b = cb0; b < BC; b += cbs) *reinterpret_cast<P2 *>(ynext + b * m + ca) = *reinterpret_cast<const P2 *>(A + b * LDA + ca);
+            continue;
+        }
         // ---- column pass A -> Tm, per node: scaling rows on top, detail rows below (shift resolved here) ----
         constexpr int WS = 2 * KSEG + F - 2;
         if (BE > 0 && hr % KSEG == 0 && mpl >= WS) {
