@@ -142,7 +142,7 @@ def main():
         # config 4: 2-D wpd, 4096 images 512 x 512, L = 5
         m = n2 = 512
         N, L = int(4096 * a.scale), 5
-        for wname in ("haar", "db4"):
+        for wname in ("haar", "db4", "sym8"):
             if want(f"wpd2d_{tag}_{wname}"):
                 wt = wx.wavelet(wname)
                 x = torch.randn((N, n2, m), dtype=dt, device=dev, generator=gen)

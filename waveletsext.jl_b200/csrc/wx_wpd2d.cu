@@ -20,7 +20,9 @@
 namespace {
 
 // K consecutive output pairs from one window: win[0 .. 2K+F-3] = v[2i .. 2i+2K+F-3]; pair p uses win[2p .. 2p+F-1]
-constexpr int KROW = 8;       // row pass: output columns per thread (a window slides along the row)
+// row pass: output columns per thread (a window of 2*KROW+F-2 values slides along the row); halved for long filters so that the
+// window stays in registers (F = 16 / 20 spilled 1.7 - 2.3 KB per thread with 8)
+__host__ __device__ constexpr int wx_krow(int F) { return F >= 12 ? 4 : 8; }
 constexpr int KSEG = 4;       // column pass of the compile-time-shaped kernels: output pairs per thread (window slides down the column)
 
 // leading dimensions of the shared-memory arrays.  Column pass: lanes walk COLUMNS and read element pairs, conflict free when
@@ -40,7 +42,7 @@ __global__ void __launch_bounds__(kT2, 3) wpd2d_tile_k(T *__restrict__ y, const 
 {
     const int tr = TRC > 0 ? TRC : tr_, tc = TRC > 0 ? TRC : tc_;
     using P2 = typename Pair<T>::type;
-    constexpr int S = (F - 2) / 2;
+    constexpr int S = (F - 2) / 2, KROW = wx_krow(F);
     extern __shared__ __align__(16) unsigned char wx_2d_smem[];
     const int PR = 2 * tr + F - 2, PC = 2 * tc + F - 2, R2 = 2 * tr;
     const int LDP = TRC > 0 ? wx_ld_pairs(PR) : PR + 2 * (tr & 1);      // generic shape: odd tiles padded (see host)
@@ -248,7 +250,7 @@ template <typename T, int F, int BE, int MPL>
 __device__ __forceinline__ void wpd2d_block_level_ct(T *__restrict__ A, T *__restrict__ Tm, const Taps<T> &tp, int tid)
 {
     using P2 = typename Pair<T>::type;
-    constexpr int S = (F - 2) / 2, LDA = wx_ld_pairs(BE), LDT = wx_ld_odd(BE);
+    constexpr int S = (F - 2) / 2, LDA = wx_ld_pairs(BE), LDT = wx_ld_odd(BE), KROW = wx_krow(F);
     constexpr int HR = MPL / 2, WS = 2 * KSEG + F - 2, WR = 2 * KROW + F - 2;
     // ---- column pass A -> Tm ----
     for (int t = tid; t < (BE / 2 / KSEG) * BE; t += kT2) {
@@ -299,7 +301,7 @@ __global__ void __launch_bounds__(kT2, 3) wpd2d_block_k(T *__restrict__ y, const
                                                        Taps<T> tp)
 {
     using P2 = typename Pair<T>::type;
-    constexpr int S = (F - 2) / 2;
+    constexpr int S = (F - 2) / 2, KROW = wx_krow(F);
     extern __shared__ __align__(16) unsigned char wx_2d_smem[];
     const int BR = BE > 0 ? BE : (m >> db), BC = BE > 0 ? BE : (n >> db);
     const int LDA = BE > 0 ? wx_ld_pairs(BR) : BR, LDT = BE > 0 ? wx_ld_odd(BR) : BR;
