@@ -253,4 +253,32 @@ function denoiseall_dwt(X::B200Array{T,2}, wt::OrthoFilter; L::Integer=maxtransf
     return iwptall(Xt, wt, maketree(n, L, :dwt))
 end
 
+# sidwt_step!(w1, w2, v, h, g, s)   siwt/siwt_one_level.jl:71-98 and isidwt_step!(v, w1, w2, h, g, s) :153-184
+function sidwt_step!(w1::B200Array{T,1}, w2::B200Array{T,1}, v::B200Array{T,1}, h::Vector{Float64}, g::Vector{Float64}, s::Bool) where T
+    @assert length(w1) == length(w2) == length(v) ÷ 2
+    @assert length(h) == length(g)
+    check(ccall((Symbol("wx_sidwt_step_", sfx(T)), LIB), Cint, (Ptr{T}, Ptr{T}, Ptr{T}, Clong, Ptr{Cdouble}, Ptr{Cdouble}, Cint, Cint, Ptr{Cvoid}),
+                w1.ptr, w2.ptr, v.ptr, length(v), h, g, length(h), s, C_NULL))
+    return w1, w2
+end
+function isidwt_step!(v::B200Array{T,1}, w1::B200Array{T,1}, w2::B200Array{T,1}, h::Vector{Float64}, g::Vector{Float64}, s::Bool) where T
+    @assert length(w1) == length(w2) == length(v) ÷ 2
+    @assert length(h) == length(g)
+    check(ccall((Symbol("wx_isidwt_step_", sfx(T)), LIB), Cint, (Ptr{T}, Ptr{T}, Ptr{T}, Clong, Ptr{Cdouble}, Ptr{Cdouble}, Cint, Cint, Ptr{Cvoid}),
+                v.ptr, w1.ptr, w2.ptr, length(v), h, g, length(h), s, C_NULL))
+    return v
+end
+
+# ns_dwt(x, wt, L)   wavemult/transforms.jl:52-74 for a vector (n,) or a batch (n, N) of vectors -> (2n[, N])
+function ns_dwt(x::B200Array{T}, wt::OrthoFilter, L::Integer=maxtransformlevels(size(x, 1))) where T
+    n = size(x, 1); N = ndims(x) == 1 ? 1 : size(x, 2)
+    @assert 1 ≤ L ≤ maxtransformlevels(n)
+    @assert ispow2(n)
+    g, h = WT.makereverseqmfpair(wt, true)
+    nxw = B200Array{T,ndims(x)}(ndims(x) == 1 ? (2n,) : (2n, N); dev=x.dev)
+    check(ccall((Symbol("wx_ns_dwt_", sfx(T)), LIB), Cint, (Ptr{T}, Ptr{T}, Clong, Cint, Clong, Ptr{Cdouble}, Ptr{Cdouble}, Cint, Ptr{Cvoid}),
+                nxw.ptr, x.ptr, n, L, N, h, g, length(h), C_NULL))
+    return nxw
+end
+
 end # module
