@@ -346,6 +346,10 @@ def test_wpdall_host_pipeline(wx, O, cuda):
     assert np.array_equal(y, yd)
     ref = O.wpdall(x[:8], wt.taps, 9)
     assert relerr(y[:8], ref) <= 1e-12
+    # the slots come from the stream-ordered pool and stay cached; trimming returns them and the next call still works
+    wx.host.trim_scratch(0)
+    assert np.array_equal(wx.host.wpdall_host(x, wt, 9, chunk=300), yd)
+    wx.host.trim_scratch(1 << 20)
 
 
 @pytest.mark.parametrize("dt", [np.float64, np.float32])

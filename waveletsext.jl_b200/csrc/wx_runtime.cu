@@ -73,6 +73,17 @@ int wx_malloc(void **dptr, size_t bytes)
     return WX_OK;
 }
 
+int wx_trim_scratch(size_t keep_bytes)
+{
+    int dev = 0;
+    WX_CUDA(cudaGetDevice(&dev));
+    WX_CUDA(cudaDeviceSynchronize());
+    cudaMemPool_t pool;
+    WX_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+    WX_CUDA(cudaMemPoolTrimTo(pool, keep_bytes));
+    return WX_OK;
+}
+
 int wx_free(void *dptr)
 {
     if (dptr) WX_CUDA(cudaFree(dptr));

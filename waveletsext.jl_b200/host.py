@@ -9,7 +9,7 @@ from . import _lib
 from .filters import makereverseqmfpair
 from .utils import maxtransformlevels
 
-__all__ = ["wpdall_host", "pinned_empty"]
+__all__ = ["wpdall_host", "pinned_empty", "trim_scratch"]
 
 
 def pinned_empty(shape, dtype):
@@ -37,3 +37,10 @@ def wpdall_host(x: np.ndarray, wt, L=None, out: np.ndarray | None = None, chunk:
     with torch.cuda.device(device):
         _lib.call(f"wx_wpdall_host_{sfx}", out.ctypes.data, x.ctypes.data, n, L, N, h.ctypes.data, g.ctypes.data, len(h), int(chunk))
     return out
+
+
+def trim_scratch(keep_bytes: int = 0, device: int | None = None) -> None:
+    """hand the library's cached stream-ordered scratch above ``keep_bytes`` back to the driver (``wx_trim_scratch``)"""
+    import torch
+    with torch.cuda.device(torch.cuda.current_device() if device is None else device):
+        _lib.call("wx_trim_scratch", int(keep_bytes))
