@@ -38,7 +38,7 @@ __host__ __device__ constexpr int wx_ld_odd(int rows) { return rows | 1; }
 // ---------------------------------------------------------------------------------------------------------
 template <typename T, int F, int TRC>
 __global__ void __launch_bounds__(kT2, 3) wpd2d_tile_k(T *__restrict__ y, const T *__restrict__ x, int m, int n, int L, int d, int tr_, int tc_,
-                                                      Div32 drowtiles, Div32 dtiles_r, Div32 dtiles_c, Taps<T> tp)
+                                                      Div32 drowtiles, Div32 dtiles_r, Div32 dtiles_c, Div32 dgx, long ntiles, Taps<T> tp)
 {
     const int tr = TRC > 0 ? TRC : tr_, tc = TRC > 0 ? TRC : tc_;
     using P2 = typename Pair<T>::type;
@@ -51,38 +51,50 @@ __global__ void __launch_bounds__(kT2, 3) wpd2d_tile_k(T *__restrict__ y, const 
     T *Tm = P + LDP * PC;
     const int tid = threadIdx.x;
     const int mp = m >> d, np = n >> d, hr = mp / 2, hc = np / 2;
-    // grid.x = image * (row tiles of all nodes), grid.y = column tiles of all nodes: neighbouring CTAs walk down the rows
-    const unsigned k = div32(blockIdx.x, drowtiles), rt = blockIdx.x - k * drowtiles.d;
-    const int jr = (int)div32(rt, dtiles_r), ti = (int)(rt - (unsigned)jr * dtiles_r.d);
-    const int jc = (int)div32(blockIdx.y, dtiles_c), tk = (int)(blockIdx.y - (unsigned)jc * dtiles_c.d);
     const long img = (long)m * n;
-    T *yk = y + (long)k * img * (L + 1);
     const bool from_x = (d == 0 && x != nullptr);
-    const int nr0 = jr * mp, nc0 = jc * np;              // node origin in the image
-    const int i0 = ti * tr, k0 = tk * tc;                // tile origin in child coordinates
-    const T *par = (from_x ? (x + (long)k * img) : (yk + (long)d * img)) + (long)nc0 * m + nr0;
-
-    // ---- parent patch (periodic inside the node), two rows per asynchronous copy; a warp per column ----
     const int lane = tid & 31, warp = tid >> 5;
-    {
+
+    // tile id -> (bx, by) in the order the hardware would schedule a (gx, gy) grid: bx = image * (row tiles of all nodes) fastest,
+    // by = column tiles of all nodes; neighbouring CTAs walk down the rows (their halos meet in L2)
+    struct Tile { long k; int nr0, nc0, i0, k0; };
+    auto decode = [&](long id) {
+        const unsigned by = div32((unsigned)id, dgx), bx = (unsigned)id - by * dgx.d;
+        const unsigned k = div32(bx, drowtiles), rt = bx - k * drowtiles.d;
+        const int jr = (int)div32(rt, dtiles_r), ti = (int)(rt - (unsigned)jr * dtiles_r.d);
+        const int jc = (int)div32(by, dtiles_c), tk = (int)(by - (unsigned)jc * dtiles_c.d);
+        Tile t; t.k = k; t.nr0 = jr * mp; t.nc0 = jc * np; t.i0 = ti * tr; t.k0 = tk * tc;
+        return t;
+    };
+    // parent patch of a tile (periodic inside the node) into P, two rows per asynchronous copy; a warp per column
+    auto prefetch = [&](const Tile &t) {
+        const T *par = (from_x ? (x + t.k * img) : (y + t.k * img * (L + 1) + (long)d * img)) + (long)t.nc0 * m + t.nr0;
         const int PR2 = PR / 2;
-        int rr = 2 * i0 + 2 * lane; while (rr >= mp) rr -= mp;
+        int rr = 2 * t.i0 + 2 * lane; while (rr >= mp) rr -= mp;
         for (int b = warp; b < PC; b += kT2 / 32) {
-            int cc = 2 * k0 + b; while (cc >= np) cc -= np;
+            int cc = 2 * t.k0 + b; while (cc >= np) cc -= np;
             if (lane < PR2) cp_async_pair<T>(P + b * LDP + 2 * lane, par + cc * m + rr);
         }
         const int rem = PR2 - 32;                         // pairs 32.. of every column (halo rows of a 32-row tile)
         if (rem > 0) {
             for (int idx = tid; idx < rem * PC; idx += kT2) {
                 const int b = idx / rem, a = 2 * (32 + idx - b * rem);
-                int r2 = 2 * i0 + a; while (r2 >= mp) r2 -= mp;
-                int cc = 2 * k0 + b; while (cc >= np) cc -= np;
+                int r2 = 2 * t.i0 + a; while (r2 >= mp) r2 -= mp;
+                int cc = 2 * t.k0 + b; while (cc >= np) cc -= np;
                 cp_async_pair<T>(P + b * LDP + a, par + cc * m + r2);
             }
         }
-        cp_async_wait_all();
-    }
-    __syncthreads();
+    };
+
+    long id = blockIdx.x;
+    if (id >= ntiles) return;
+    Tile cur = decode(id);
+    prefetch(cur);
+    for (; id < ntiles; id += gridDim.x) {
+    const int nr0 = cur.nr0, nc0 = cur.nc0, i0 = cur.i0, k0 = cur.k0;
+    T *yk = y + cur.k * img * (L + 1);
+    cp_async_wait_all();
+    __syncthreads();                                      // patch complete; every thread is past the previous tile's row pass (Tm free)
     if (from_x && lane < tr) {                            // y[:,:,1] = x   DWT.jl:176 : the core of the patch (tr <= 32 pairs per column)
         T *y0 = yk + (long)(nc0 + 2 * k0) * m + nr0 + 2 * i0 + 2 * lane;
         for (int b = warp; b < 2 * tc; b += kT2 / 32)
@@ -155,6 +167,8 @@ __global__ void __launch_bounds__(kT2, 3) wpd2d_tile_k(T *__restrict__ y, const 
         }
     }
     __syncthreads();
+    // P is dead from here on: the next tile's patch streams in while this tile's row pass runs
+    if (id + gridDim.x < ntiles) { cur = decode(id + gridDim.x); prefetch(cur); }
     // ---- row pass + store: (2tr rows) x (tc output pairs) ----
     T *ynext = yk + (long)(d + 1) * img + (long)nc0 * m + nr0;
     if ((kT2 % R2) == 0 && (tc % KROW) == 0) {
@@ -207,6 +221,7 @@ __global__ void __launch_bounds__(kT2, 3) wpd2d_tile_k(T *__restrict__ y, const 
             }
         }
     }
+    }   // tiles of this CTA
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -579,16 +594,23 @@ int wpd2d_run_chunk(T *y, const T *x, long m, long n, int L, long N, const Taps<
                                    : ((size_t)(PR + 2 * (tr & 1)) * PC + (size_t)2 * tr * (PC + 2 * (tc & 1))) * sizeof(T);
         if (smem > dv.smem_optin) return wx_fail(WX_EUNSUPPORTED, "wpd 2-D tile does not fit shared memory");
         const long gx = (hr / tr) * (1L << d) * N, gy = (hc / tc) * (1L << d);
-        if (gx >= (1L << 31) || gy > 65535) return wx_fail(WX_EUNSUPPORTED, "wpd 2-D: too many tiles for one launch");
-        const Div32 drt = make_div32((hr / tr) * (1L << d)), dtr = make_div32(hr / tr), dtc = make_div32(hc / tc);
+        if (gx * gy >= (1L << 32) || gx >= (1L << 31)) return wx_fail(WX_EUNSUPPORTED, "wpd 2-D: too many tiles for one launch");
+        const Div32 drt = make_div32((hr / tr) * (1L << d)), dtr = make_div32(hr / tr), dtc = make_div32(hc / tc), dgx = make_div32(gx);
+        const long ntiles = gx * gy;
+        // Measurement knob: CTAs per SM of a persistent tile loop that prefetches the next tile's patch under the current row pass.
+        // Measured in round 1 (4096 x 512^2, db4 F64): 3 per SM 18.7 ms, 6 per SM 18.3 ms, one CTA per tile 16.7 ms -- the hardware
+        // scheduler refilling three CTA slots overlaps loads and passes better than the in-CTA pipeline, so the default is 0.
+        static const char *penv = getenv("WX_B200_WPD2D_PERSIST");
+        const int per_sm = penv ? atoi(penv) : 0;
+        const long ctas = per_sm > 0 && ntiles > (long)dv.sms * per_sm ? (long)dv.sms * per_sm : ntiles;
         if (tr == 32 && tc == 32) {
             auto kern = wpd2d_tile_k<T, F, 32>;
             WX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            kern<<<dim3((unsigned)gx, (unsigned)gy), kT2, smem, s>>>(y, d == 0 ? x : nullptr, (int)m, (int)n, L, d, tr, tc, drt, dtr, dtc, t);
+            kern<<<(unsigned)ctas, kT2, smem, s>>>(y, d == 0 ? x : nullptr, (int)m, (int)n, L, d, tr, tc, drt, dtr, dtc, dgx, ntiles, t);
         } else {
             auto kern = wpd2d_tile_k<T, F, 0>;
             WX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            kern<<<dim3((unsigned)gx, (unsigned)gy), kT2, smem, s>>>(y, d == 0 ? x : nullptr, (int)m, (int)n, L, d, tr, tc, drt, dtr, dtc, t);
+            kern<<<(unsigned)ctas, kT2, smem, s>>>(y, d == 0 ? x : nullptr, (int)m, (int)n, L, d, tr, tc, drt, dtr, dtc, dgx, ntiles, t);
         }
         WX_LAUNCHED();
     }
