@@ -594,7 +594,7 @@ int wpd2d_run_chunk(T *y, const T *x, long m, long n, int L, long N, const Taps<
                                    : ((size_t)(PR + 2 * (tr & 1)) * PC + (size_t)2 * tr * (PC + 2 * (tc & 1))) * sizeof(T);
         if (smem > dv.smem_optin) return wx_fail(WX_EUNSUPPORTED, "wpd 2-D tile does not fit shared memory");
         const long gx = (hr / tr) * (1L << d) * N, gy = (hc / tc) * (1L << d);
-        if (gx * gy >= (1L << 32) || gx >= (1L << 31)) return wx_fail(WX_EUNSUPPORTED, "wpd 2-D: too many tiles for one launch");
+        if (gx * gy >= (1L << 31)) return wx_fail(WX_EUNSUPPORTED, "wpd 2-D: too many tiles for one launch");
         const Div32 drt = make_div32((hr / tr) * (1L << d)), dtr = make_div32(hr / tr), dtc = make_div32(hc / tc), dgx = make_div32(gx);
         const long ntiles = gx * gy;
         // Measurement knob: CTAs per SM of a persistent tile loop that prefetches the next tile's patch under the current row pass.
