@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(256) wpd1d_fused_k(T *__restrict__ y, const T 
 // before the barrier that lets level l+2 overwrite that buffer, so the wait is normally already satisfied.
 // Tensor maps view x and y as 2-D arrays of 128-byte rows: coordinates {0, row}.
 template <typename T, int F>
-__global__ void __launch_bounds__(256) wpd1d_tma_k(const __grid_constant__ CUtensorMap mapx, const __grid_constant__ CUtensorMap mapy, long n, int L,
+__global__ void __launch_bounds__(512) wpd1d_tma_k(const __grid_constant__ CUtensorMap mapx, const __grid_constant__ CUtensorMap mapy, long n, int L,
                                                   int d0, long items, int bufelems, int boxrows, Taps<T> tp)
 {
     constexpr int RE = 128 / (int)sizeof(T);          // elements per 128-byte row
@@ -194,12 +194,21 @@ int wpd1d_launch_tma(T *y, const T *x, long n, int L, long N, int d0, const Taps
     long units = n0 / (2 * C::K);
     int threads = (int)((units + 31) / 32 * 32);
     if (threads < 64) threads = 64;
-    if (threads > 256) threads = 256;
+    // Resident CTAs per SM.  Shared memory allows three 256-thread CTAs; for the 8-tap filters in Float64 TWO are faster -- measured
+    // on 65536 x 4096, L = 12 (same box, same run): db4 5.31 ms with three CTAs, 4.70 ms with two (0.977 of the measured HBM copy
+    // peak), 4.80 ms with two 512-thread CTAs; haar / db2 / db3 do not care (5.2 ms either way), coif4 and sym8 lose with two
+    // (5.0 -> 5.4 ms, 5.3 -> 6.6 ms) and lose more with 512 threads.  Fewer concurrent store streams per SM suit the DRAM better as
+    // long as two CTAs still cover the FP64 work.  Knobs for re-measuring: WX_B200_WPD1D_THREADS (256 / 512), WX_B200_WPD1D_OCC.
+    static const char *tenv = getenv("WX_B200_WPD1D_THREADS");
+    static const char *oenv = getenv("WX_B200_WPD1D_OCC");
+    if (threads > 256) threads = (tenv && atoi(tenv) == 512 && threads >= 512) ? 512 : 256;
     auto kern = wpd1d_tma_k<T, F>;
     WX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
     WX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
     if (occ < 1) return WX_OK;
+    if (oenv && atoi(oenv) >= 1) { if (atoi(oenv) < occ) occ = atoi(oenv); }
+    else if (F == 8 && sizeof(T) == 8 && occ == 3) occ = 2;            // exactly the measured shape: 32 KB nodes, three CTAs by shared memory
     const long items = N << d0;
     long blocks = (long)dv.sms * occ;
     if (blocks > items) blocks = items;
