@@ -175,3 +175,38 @@ def test_ldb_class_numbering_and_bb_types(wx):
     assert lab.tolist() == [1, 2] and classes == ["b", "a", 3]
     assert isinstance(wx.BB().cost, wx.ShannonEntropyCost) and wx.BB().redundant is False
     assert wx.LpDistance().p == 2 and wx.JBB().cost.p == 2 and wx.NormCost().p == 1
+
+
+def test_denoising_host_objects(wx):
+    """DNFT constructors (Denoising.jl:42-119, Wavelets.jl VisuShrink), the leaf masks the thresholding and the BitVector-indexed
+    estimators use, ndyad (wavemult/utils.jl:146-155) -- host logic only, no device work"""
+    import math
+    from waveletsext_b200 import denoising as dn
+    v = wx.VisuShrink(256)
+    assert isinstance(v.th, wx.HardTH) and v.t == math.sqrt(2 * math.log(256))
+    v = wx.VisuShrink(2, wx.SoftTH())
+    assert isinstance(v.th, wx.SoftTH) and v.t == math.sqrt(2 * math.log(2))
+    v = wx.VisuShrink(wx.HardTH(), 8)                       # test/denoising.jl:2
+    assert v.t == 8.0
+    r = wx.RelErrorShrink()
+    assert isinstance(r.th, wx.HardTH) and r.t == 1.0
+    assert wx.RelErrorShrink(wx.HardTH(), 1).t == 1.0 and isinstance(wx.RelErrorShrink(wx.SteinTH()).th, wx.SteinTH)
+    s = wx.SureShrink(wx.HardTH(), 1)
+    assert s.t == 1.0
+    assert [c().code for c in (wx.HardTH, wx.SoftTH, wx.SemiSoftTH, wx.SteinTH)] == [0, 1, 2, 3]
+    # leaves of maketree(8, 1, :full) in a 15-node table: nodes 2 and 3
+    tree = wx.maketree(8, 1, "full")
+    m = dn._leafmask(tree, 15)
+    assert m.tolist() == [0, 1, 1] + [0] * 12
+    assert dn._leafmask(tree, 3, strict=False).tolist() == [0, 1, 1]            # findall-style: a shallower table is fine
+    with pytest.raises(IndexError):
+        dn._leafmask(tree, 3)                                                    # BitVector-style: BoundsError
+    with pytest.raises(IndexError):
+        dn._leafmask(wx.maketree(8, 3, "full"), 7, strict=False)                 # leaves beyond the table
+    assert wx.ndyad(1, 4, False) == range(16, 24) and wx.ndyad(4, 4, True) == range(3, 4)
+    assert wx.finestdetailrange(8, wx.maketree(8, 3, "dwt")) == range(4, 8)
+    assert wx.coarsestscalingrange(8, wx.maketree(8, 3, "dwt")) == range(0, 1)
+    # the LDB object keeps the reference's defaults (LDB.jl:89-110)
+    f = wx.LocalDiscriminantBasis()
+    assert f.wt.name == "haar" and isinstance(f.dm, wx.AsymmetricRelativeEntropy) and isinstance(f.en, wx.TimeFrequency)
+    assert isinstance(f.dp, wx.BasisDiscriminantMeasure) and f.top_k is None and f.n_features is None and f.tree is None
