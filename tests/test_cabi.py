@@ -17,7 +17,9 @@ def test_header_symbols_exported(wx):
     missing = [n for n in protos if not hasattr(l, n)]
     assert not missing, f"libwx_b200.so lacks {missing}"
     for stem in ("wx_wpd1d", "wx_wpd2d", "wx_iwpt1d", "wx_rwt", "wx_irwt", "wx_dwt_step", "wx_idwt_step", "wx_sdwt_step", "wx_acdwt_step",
-                 "wx_gather_basis", "wx_jbb_moments", "wx_lsdb_pass1", "wx_wpdall_host"):
+                 "wx_gather_basis", "wx_jbb_moments", "wx_lsdb_pass1", "wx_wpdall_host", "wx_noisest", "wx_surethreshold",
+                 "wx_relerrorthreshold", "wx_threshold", "wx_sidwt_step", "wx_isidwt_step", "wx_ns_dwt", "wx_ns_idwt", "wx_select_features",
+                 "wx_scatter_features", "wx_class_moments"):
         assert stem + "_f64" in protos and stem + "_f32" in protos
     assert _lib.lib().wx_version() >= 100
 
@@ -47,6 +49,23 @@ def test_argument_validation_needs_no_gpu(wx):
     assert rc == _lib.WX_EINVAL and "sv" in _lib.last_error()
     # empty batch: nothing to do, success even without a device
     assert _lib.lib().wx_wpd1d_f64(0, 0, 16, 4, 0, h.ctypes.data, g.ctypes.data, 8, 0) == 0
+    # the "next" rows validate the same way: threshold type / negative threshold (Wavelets.jl @assert t >= 0), elbows >= 1
+    # (Denoising.jl:291), ns_dwt's 1 <= L <= Lmax and ispow2(n) (wavemult/transforms.jl:57-58), a noisest range outside the slab
+    L = _lib.lib()
+    p = buf.ctypes.data
+    rc = L.wx_threshold_f64(p, p, 8, 1, 0, 0, 0, 7, 0, C.c_double(1.0), 1, 0)
+    assert rc == _lib.WX_EINVAL and "threshold type" in _lib.last_error()
+    rc = L.wx_threshold_f64(p, p, 8, 1, 0, 0, 0, 0, 0, C.c_double(-1.0), 1, 0)
+    assert rc == _lib.WX_EINVAL and "t >= 0" in _lib.last_error()
+    rc = L.wx_relerrorthreshold_f64(p, p, 8, 1, 0, 0, 1, 0)
+    assert rc == _lib.WX_EINVAL and "elbows" in _lib.last_error()
+    rc = L.wx_noisest_f64(p, p, 8, 4, 8, 1, 0)
+    assert rc == _lib.WX_EINVAL
+    rc = L.wx_ns_dwt_f64(p, p, 8, 4, 1, h.ctypes.data, g.ctypes.data, 8, 0)
+    assert rc == _lib.WX_EINVAL and "1 <= L <= Lmax" in _lib.last_error()
+    rc = L.wx_ns_dwt_f64(p, p, 12, 1, 1, h.ctypes.data, g.ctypes.data, 8, 0)
+    assert rc == _lib.WX_EINVAL and "ispow2" in _lib.last_error()
+    assert L.wx_threshold_f64(p, p, 8, 1, 0, 0, 0, 0, 0, C.c_double(1.0), 0, 0) == 0          # N = 0
 
 
 def test_compute_fails_loudly_without_gpu(wx):
