@@ -229,11 +229,68 @@ int wx_class_moments_f32(double *E, double *V, const float *X, const int *sig_de
  * m = 0: binary tree with n-1 entries; m > 0: quad tree. minmax 0 = :min, 1 = :max */
 int wx_tree_select(unsigned char *tree_out, double *costs_host, long ncosts, long m, long n, int minmax);
 
+/* ---- the collective of the path: NCCL communicators and the fused best-basis drivers (wx_comm.cu) -------------------
+ * The reference reduces over the whole batch inside tree_costs: sum(X, dims=3) bestbasis/bestbasis_tree.jl:153-154 (JBB) and
+ * the per-position statistics / ASH counts / log-pdf sums of bestbasis/bestbasis_costs.jl:135-164 (LSDB).  When the batch is
+ * sharded over GPUs those reductions become the ONE exchange step of the path, an NCCL all-reduce / all-gather over NVLink of
+ * the small per-position state; everything else is shard-local.  NCCL is resolved at run time (the libnccl.so.2 the host
+ * process already mapped, else $WX_B200_NCCL, else the loader path); without it these calls return WX_EUNSUPPORTED.
+ *  - one process (or thread) per GPU: rank 0 calls wx_comm_unique_id, hands the 128 bytes to the other ranks by whatever means
+ *    the host has (a file, MPI, torch.distributed, Distributed.jl), every rank calls wx_comm_init_rank on its current device.
+ *  - one host thread driving all GPUs (the reference is single threaded): wx_comm_init_all (ncclCommInitAll) returns one
+ *    communicator per device; use the *_multi drivers, or bracket per-device wx_allreduce calls with wx_group_start/_end.
+ * dtype codes WX_DT_*, reduction codes WX_OP_*; buffers are device pointers; collectives are in place and asynchronous on
+ * `stream`. */
+typedef struct wx_comm wx_comm_t;
+#define WX_COMM_ID_BYTES 128
+#define WX_DT_F64 0
+#define WX_DT_F32 1
+#define WX_DT_I64 2
+#define WX_DT_U8 3
+#define WX_OP_SUM 0
+#define WX_OP_MIN 1
+#define WX_OP_MAX 2
+int wx_nccl_version(int *version);
+int wx_comm_unique_id(unsigned char *id128);
+int wx_comm_init_rank(wx_comm_t **comm, const unsigned char *id128, int rank, int world);
+int wx_comm_init_all(wx_comm_t **comms, int ndev, const int *devlist);          /* devlist NULL: devices 0..ndev-1 */
+int wx_comm_info(const wx_comm_t *comm, int *rank, int *world, int *dev, void **stream);
+int wx_comm_destroy(wx_comm_t *comm);
+int wx_group_start(void);
+int wx_group_end(void);
+int wx_allreduce(wx_comm_t *comm, void *buf, long count, int dtype, int op, void *stream);
+int wx_allgather(wx_comm_t *comm, void *recv, const void *send, long count, int dtype, void *stream);   /* recv: world * count */
+int wx_broadcast(wx_comm_t *comm, void *buf, long count, int dtype, int root, void *stream);
+/* tree_costs(X, ::JBB | ::LSDB) of the GLOBAL batch from the local shard X(sz,K,Nlocal) (bestbasis/bestbasis_tree.jl:104-207):
+ * local reduction kernels -> NCCL exchange -> per-node costs in costs_host (every rank gets the same vector).  comm NULL or a
+ * 1-rank communicator: single GPU.  JBB exchanges one all-reduce of 2*sz*K+1 doubles; LSDB exchanges double-double sums by
+ * all-gather (combined in rank order, so grid, counts and costs do not depend on the sharding), min / max / bin counts by
+ * all-reduce.  Arguments as wx_jbb_costs / wx_lsdb_costs. */
+int wx_tree_costs_jbb_f64(wx_comm_t *comm, double *costs_host, const double *X, long m, long n, int K, long Nlocal, int redundant, int cost_kind, double p, void *stream);
+int wx_tree_costs_jbb_f32(wx_comm_t *comm, double *costs_host, const float *X, long m, long n, int K, long Nlocal, int redundant, int cost_kind, double p, void *stream);
+int wx_tree_costs_lsdb_f64(wx_comm_t *comm, double *costs_host, const double *X, long m, long n, int K, long Nlocal, int redundant, void *stream);
+int wx_tree_costs_lsdb_f32(wx_comm_t *comm, double *costs_host, const float *X, long m, long n, int K, long Nlocal, int redundant, void *stream);
+/* bestbasistree(X, ::JBB | ::LSDB)  BestBasis.jl:185-217 in one call: costs as above, then bestbasis_treeselection (:min).
+ * method 0 = JBB (cost_kind, p as wx_jbb_costs), 1 = LSDB.  tree_out: ntree bytes (n-1, or gettreelength(m,n) for images);
+ * costs_host may be NULL, else it receives the node costs as tree_costs returns them (before the selection pass). */
+int wx_bestbasistree_f64(wx_comm_t *comm, int method, unsigned char *tree_out, long ntree, double *costs_host, const double *X, long m, long n, int K, long Nlocal, int redundant, int cost_kind, double p, void *stream);
+int wx_bestbasistree_f32(wx_comm_t *comm, int method, unsigned char *tree_out, long ntree, double *costs_host, const float *X, long m, long n, int K, long Nlocal, int redundant, int cost_kind, double p, void *stream);
+/* the same from ONE host thread driving ndev devices: comms from wx_comm_init_all in rank order, X[i] / Nlocal[i] the shard on
+ * comms[i]'s device; launches go to each communicator's own stream (wx_comm_info), NCCL calls are grouped. */
+int wx_bestbasistree_multi_f64(wx_comm_t *const *comms, int ndev, int method, unsigned char *tree_out, long ntree, double *costs_host, const double *const *X, const long *Nlocal, long m, long n, int K, int redundant, int cost_kind, double p);
+int wx_bestbasistree_multi_f32(wx_comm_t *const *comms, int ndev, int method, unsigned char *tree_out, long ntree, double *costs_host, const float *const *X, const long *Nlocal, long m, long n, int K, int redundant, int cost_kind, double p);
+
 /* ---- host-buffer entry points (the call a drop-in user makes with host arrays) ----------------------- */
 /* wpdall with x and y in HOST memory: chunks the batch, overlaps H2D / kernel / D2H on internal streams.
  * Synchronous.  chunk = signals per chunk (0 = auto). */
 int wx_wpdall_host_f64(double *y_host, const double *x_host, long n, int L, long N, const double *h, const double *g, int F, long chunk);
 int wx_wpdall_host_f32(float *y_host, const float *x_host, long n, int L, long N, const double *h, const double *g, int F, long chunk);
+/* wpdall -> bestbasistree(JBB: method 0 | LSDB: method 1) -> getbasiscoefall with x and the best-basis coefficients in HOST
+ * memory (the pipeline of paper/paper.md:60-118: dwt/dwt_all.jl:260-282, BestBasis.jl:185-217, Utils.jl:169-197).  The packet
+ * table stays in HBM; x (n,N) goes up and coef (n,N) comes back in chunks overlapped with the kernels.  comm NULL = single GPU;
+ * otherwise x_host is this rank's shard and the tree is that of the global batch.  tree_out: n-1 bytes.  Synchronous. */
+int wx_wpd_bestbasis_host_f64(wx_comm_t *comm, double *coef_host, unsigned char *tree_out, long ntree, const double *x_host, long n, int L, long N, const double *h, const double *g, int F, int method, int cost_kind, double p, long chunk);
+int wx_wpd_bestbasis_host_f32(wx_comm_t *comm, float *coef_host, unsigned char *tree_out, long ntree, const float *x_host, long n, int L, long N, const double *h, const double *g, int F, int method, int cost_kind, double p, long chunk);
 
 #ifdef __cplusplus
 }

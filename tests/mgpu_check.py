@@ -59,6 +59,8 @@ def main():
         t_sh = wx.bestbasis_treeselection(c_sh.copy(), n)
         t_one = wx.bestbasis_treeselection(c_one.copy(), n)
         assert np.array_equal(t_sh, t_one), type(method).__name__
+        # the fused driver (reduction kernels -> NCCL exchange -> costs -> selection inside libwx_b200) gives the same tree
+        assert np.array_equal(wx.bestbasistree(yl, method), t_one), "fused bestbasistree differs"
         tt = torch.from_numpy(t_sh.astype(np.int64)).to(dev)
         a, b = tt.clone(), tt.clone()
         dist.all_reduce(a, op=dist.ReduceOp.MIN); dist.all_reduce(b, op=dist.ReduceOp.MAX)
@@ -69,6 +71,33 @@ def main():
         assert (xr - xl).abs().max().item() <= 1e-10 * xl.abs().max().item()
         if rank == 0:
             print(f"{type(method).__name__}: sharded == single (rel {rel:.2e}), tree nodes {int(t_sh.sum())}", flush=True)
+    # the raw collectives of the C ABI over the library's own communicator
+    import ctypes as C
+    cm = wx.dist.comm(dev)
+    assert cm is not None
+    st = int(torch.cuda.current_stream().cuda_stream)
+    b = torch.full((1001,), float(rank + 1), dtype=torch.float64, device=dev)
+    wx._lib.call("wx_allreduce", cm, b.data_ptr(), b.numel(), 0, 0, st)
+    assert float(b[1000]) == world * (world + 1) / 2
+    b = torch.full((5,), float(rank), dtype=torch.float32, device=dev)
+    wx._lib.call("wx_allreduce", cm, b.data_ptr(), 5, 1, 2, st)
+    assert float(b[0]) == world - 1
+    g = torch.empty((world, 3), dtype=torch.int64, device=dev)
+    mine = torch.full((3,), rank, dtype=torch.int64, device=dev)
+    wx._lib.call("wx_allgather", cm, g.data_ptr(), mine.data_ptr(), 3, 2, st)
+    assert g[:, 0].tolist() == list(range(world))
+    bb = torch.full((4,), float(rank), dtype=torch.float64, device=dev)
+    wx._lib.call("wx_broadcast", cm, bb.data_ptr(), 4, 0, world - 1, st)
+    assert float(bb[0]) == world - 1
+    # host pipeline: x shard (host) -> wpdall -> JBB tree of the GLOBAL batch -> coefficients (host)
+    coef, th = wx.host.wpd_bestbasis_host(xl.cpu().numpy(), wt, None, wx.JBB(), device=local)
+    saved = wx.dist.is_dist
+    wx.dist.is_dist = lambda group=None: False
+    try:
+        t_one = wx.bestbasistree(yfull, wx.JBB())
+    finally:
+        wx.dist.is_dist = saved
+    assert np.array_equal(th, t_one) and np.array_equal(coef, wx.getbasiscoefall(yl, t_one).cpu().numpy()), "host pipeline differs"
     # denoiseall: shard-local except for the bestTH summary over the noise levels of the WHOLE batch
     dw = wx.dwtall(X, wt)
     sh = wx.denoiseall(dw[lo:hi].contiguous(), "dwt", wt)
@@ -82,6 +111,7 @@ def main():
     shb = wx.denoiseall(dw[lo:hi].contiguous(), "dwt", wt, bestTH=np.mean)
     assert torch.equal(shb, one[lo:hi]), "sharded denoiseall(bestTH) differs from the single-GPU result"
     dist.barrier()
+    wx.dist.destroy_comms()
     if rank == 0:
         print(f"mgpu_check ok on {world} GPUs", flush=True)
     dist.destroy_process_group()

@@ -1,9 +1,10 @@
 """Joint best basis (JBB) and least statistically dependent basis (LSDB) on the B200: host mirror of BestBasis.jl,
 bestbasis/bestbasis_tree.jl and bestbasis/bestbasis_costs.jl (JBB / LSDB rows of the hot path).
 
-``tree_costs`` runs the per-position reductions on the local shard of the batch, all-reduces the small
-per-position state over ``torch.distributed`` when a process group is initialised (dist.py), and returns the
-per-node costs as a numpy vector; ``bestbasis_treeselection`` is the O(n) host pass of the reference.
+``tree_costs`` / ``bestbasistree`` are single calls into libwx_b200 (``wx_tree_costs_*`` / ``wx_bestbasistree_*``): the
+per-position reductions on the local shard of the batch, the NCCL exchange of the small per-position state over the
+library's own communicator when a process group is initialised (``dist.comm``), the per-node costs and the O(n) host
+selection pass of the reference all run inside the library.
 """
 from __future__ import annotations
 
@@ -89,18 +90,6 @@ def _ncosts(m, K, redundant):
     return (4 ** K - 1) // 3 if m > 0 else (1 << K) - 1
 
 
-def _dd_allreduce(pair, group, st):
-    """in-place exact sum over ranks of a (2, count) double-double buffer (rows hi, lo)"""
-    if not (dist.is_dist(group) and dist.world_size(group) > 1):
-        return pair
-    parts = dist.allgather_parts(pair, group)
-    out = torch.empty_like(parts[0])
-    with torch.cuda.device(pair.device):
-        _lib.call("wx_dd_sum", D.ptr(out), D.ptr(parts), pair.shape[1], parts.shape[0], st)
-    pair.copy_(out)
-    return pair
-
-
 def _bb_kind(method):
     if isinstance(method.cost, ShannonEntropyCost):
         return 0
@@ -134,10 +123,19 @@ def bestbasistreeall(X, method=None):
     return trees.bool()
 
 
+def _jbb_kind(method):
+    if isinstance(method.cost, LoglpCost):
+        return 0
+    if isinstance(method.cost, NormCost):
+        return 1
+    raise TypeError("JBB cost must be LoglpCost or NormCost")
+
+
 def tree_costs(X, method, group=None):
     """``tree_costs(X, method)`` bestbasis/bestbasis_tree.jl:104-256.  JBB / LSDB: X is the LOCAL shard (N_local, K, ...) of the
-    packet table; with an initialised process group the costs are those of the concatenated batch.  BB: X is ONE decomposed
-    signal (K, n[, m]) like in the reference."""
+    packet table; with an initialised process group the costs are those of the concatenated batch -- the exchange of the
+    per-position state runs inside libwx_b200 over its own NCCL communicator (``dist.comm``; ``wx_tree_costs_jbb`` /
+    ``wx_tree_costs_lsdb``), not in Python.  BB: X is ONE decomposed signal (K, n[, m]) like in the reference."""
     X = D.dev(X, "X")
     if isinstance(method, BB):
         assert 2 <= X.dim() <= 3, "AssertionError: 2 <= ndims(X) <= 3"
@@ -145,46 +143,13 @@ def tree_costs(X, method, group=None):
         c = costs[0].cpu().numpy()
         return c.astype(np.float32).astype(np.float64) if X.dtype == torch.float32 else c
     m, n, K, Nloc, szK = _geom(X)
-    Ntot = dist.total_count(Nloc, X.device, group)
-    elt = X.element_size()
     costs = np.empty(_ncosts(m, K, method.redundant), np.float64)
-    st = D.stream(X)
+    cm = dist.comm(X.device, group)
     if isinstance(method, JBB):
-        if isinstance(method.cost, LoglpCost):
-            kind = 0
-        elif isinstance(method.cost, NormCost):
-            kind = 1
-        else:
-            raise TypeError("JBB cost must be LoglpCost or NormCost")
-        mom = torch.empty((2, szK), dtype=torch.float64, device=X.device)
-        D.call("jbb_moments", X, D.ptr(mom[0]), D.ptr(mom[1]), D.ptr(X), szK, Nloc, st)
-        dist.allreduce_sum(mom, group)           # the only collective of the JBB path (2*n*K doubles)
-        with torch.cuda.device(X.device):
-            _lib.call("wx_jbb_costs", costs.ctypes.data, D.ptr(mom[0]), D.ptr(mom[1]), Ntot, m, n, K, int(method.redundant), kind,
-                      C.c_double(float(method.cost.p)), elt, st)
+        D.call("tree_costs_jbb", X, cm, costs.ctypes.data, D.ptr(X), m, n, K, Nloc, int(method.redundant), _jbb_kind(method),
+               C.c_double(float(method.cost.p)), D.stream(X))
     elif isinstance(method, LSDB):
-        assert Ntot >= 2, "LSDB needs at least two signals"
-        stats = torch.empty((7, szK), dtype=torch.float64, device=X.device)
-        # a COPY: the broadcast below writes into this buffer on every rank but the first (never into the caller's X)
-        first = X[0].reshape(-1).to(torch.float64, copy=True) if Nloc > 0 else torch.zeros(szK, dtype=torch.float64, device=X.device)
-        stats[0] = dist.broadcast_from_first(first, group)       # common shift: first signal of the global batch
-        D.call("lsdb_pass1", X, D.ptr(stats), D.ptr(X), szK, Nloc, st)
-        # sums travel as double-double pairs and are combined in rank order: the grid every sample is binned on must not
-        # depend on the sharding (a 1-ulp change of a sum would move bin edges)
-        _dd_allreduce(stats[1:3], group, st)
-        _dd_allreduce(stats[3:5], group, st)
-        dist.allreduce_min(stats[5], group)
-        dist.allreduce_max(stats[6], group)
-        nb, mb, npts = C.c_long(), C.c_long(), C.c_long()
-        _lib.call("wx_lsdb_grid", Ntot, C.byref(nb), C.byref(mb), C.byref(npts))
-        counts = torch.empty((npts.value, szK), dtype=torch.float64, device=X.device)
-        D.call("lsdb_pass2", X, D.ptr(counts), D.ptr(stats), D.ptr(X), szK, Nloc, Ntot, st)
-        dist.allreduce_sum(counts, group)                        # integer-valued: exact in any order
-        logsum = torch.empty((2, szK), dtype=torch.float64, device=X.device)
-        D.call("lsdb_pass3", X, D.ptr(logsum), D.ptr(counts), D.ptr(stats), D.ptr(X), szK, Nloc, Ntot, st)
-        _dd_allreduce(logsum, group, st)
-        with torch.cuda.device(X.device):
-            _lib.call("wx_lsdb_costs", costs.ctypes.data, D.ptr(logsum), Ntot, m, n, K, int(method.redundant), st)
+        D.call("tree_costs_lsdb", X, cm, costs.ctypes.data, D.ptr(X), m, n, K, Nloc, int(method.redundant), D.stream(X))
     else:
         raise TypeError(f"unsupported best-basis method {type(method).__name__} on the B200 path (JBB and LSDB)")
     return costs
@@ -222,14 +187,20 @@ def delete_subtree_(bt, i, tree_type):
 
 
 def bestbasistree(X, method=None, group=None):
-    """``bestbasistree(X, method)`` BestBasis.jl:185-217 for JBB / LSDB.  X: local shard (N_local, K, ...)."""
+    """``bestbasistree(X, method)`` BestBasis.jl:185-217 for JBB / LSDB.  X: local shard (N_local, K, ...).  One call into
+    the library: reduction kernels, NCCL exchange, node costs and ``bestbasis_treeselection`` (``wx_bestbasistree``)."""
     method = JBB() if method is None else method
     X = D.dev(X, "X")
     if isinstance(method, BB):                       # one signal (K, n[, m])   BestBasis.jl:206-213
         assert 2 <= X.dim() <= 3, "AssertionError: 2 <= ndims(X) <= 3"
         return bestbasistreeall(X.unsqueeze(0), method)[0].cpu().numpy()
-    costs = tree_costs(X, method, group)
-    if X.dim() == 3:
-        return bestbasis_treeselection(costs, X.shape[2])
-    # Julia sz = (rows, cols) = (shape[3], shape[2])
-    return bestbasis_treeselection(costs, X.shape[3], X.shape[2])
+    if not isinstance(method, (JBB, LSDB)):
+        raise TypeError(f"unsupported best-basis method {type(method).__name__} on the B200 path (JBB, LSDB, BB)")
+    m, n, K, Nloc, _ = _geom(X)
+    # Julia sz = (rows, cols) = (shape[3], shape[2]); gettreelength is symmetric in them
+    tree = np.zeros(gettreelength(m, n) if m > 0 else max(n - 1, 0), np.uint8)
+    kind = _jbb_kind(method) if isinstance(method, JBB) else 0
+    p = float(method.cost.p) if isinstance(method, JBB) else 0.0
+    D.call("bestbasistree", X, dist.comm(X.device, group), 0 if isinstance(method, JBB) else 1, tree.ctypes.data, len(tree), None,
+           D.ptr(X), m, n, K, Nloc, int(method.redundant), kind, C.c_double(p), D.stream(X))
+    return tree.astype(bool)

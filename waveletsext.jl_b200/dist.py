@@ -9,8 +9,44 @@ from __future__ import annotations
 import torch
 import torch.distributed as dist
 
-__all__ = ["shard_range", "shard", "is_dist", "rank", "world_size", "allreduce_sum", "allreduce_min", "allreduce_max",
+__all__ = ["comm", "destroy_comms", "shard_range", "shard", "is_dist", "rank", "world_size", "allreduce_sum", "allreduce_min", "allreduce_max",
            "total_count", "broadcast_from_first", "allgather_parts", "dd_sum_host"]
+
+
+_COMMS: dict = {}
+
+
+def comm(device, group=None):
+    """libwx_b200's own NCCL communicator for this process group (``wx_comm_t*`` as an integer; ``None`` = single GPU).
+    Created on first use: rank 0 asks the library for an NCCL unique id (``wx_comm_unique_id``), the 128 bytes travel over
+    the existing torch.distributed group (any backend -- this is the only thing torch.distributed carries for the best-basis
+    path), every rank calls ``wx_comm_init_rank`` on its device.  Collective: all ranks of the group must call it together."""
+    if not (is_dist(group) and world_size(group) > 1):
+        return None
+    import ctypes as C
+    from . import _lib
+    device = torch.device(device)
+    key = (id(group) if group is not None else 0, device.index)
+    c = _COMMS.get(key)
+    if c is None:
+        ident = [None]
+        if rank(group) == 0:
+            buf = (C.c_ubyte * 128)()
+            _lib.call("wx_comm_unique_id", buf)
+            ident[0] = bytes(buf)
+        dist.broadcast_object_list(ident, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        h = C.c_void_p()
+        with torch.cuda.device(device):
+            _lib.call("wx_comm_init_rank", C.byref(h), ident[0], rank(group), world_size(group))
+        c = _COMMS[key] = h.value
+    return c
+
+
+def destroy_comms() -> None:
+    from . import _lib
+    for c in _COMMS.values():
+        _lib.call("wx_comm_destroy", c)
+    _COMMS.clear()
 
 
 def is_dist(group=None) -> bool:
