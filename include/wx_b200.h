@@ -56,9 +56,10 @@ int wx_h2d(void *dst_dev, const void *src_host, size_t bytes, void *stream);
 int wx_d2h(void *dst_host, const void *src_dev, size_t bytes, void *stream);
 int wx_stream_sync(void *stream);
 int wx_device_sync(void);
-/* Scratch of the batched entry points is stream-ordered memory from the device's default pool, whose release threshold this
- * library raises so that freed blocks stay cached across synchronisations.  wx_trim_scratch hands everything above keep_bytes
- * back to the driver (call it when the embedding application needs the memory: it synchronises the device first). */
+/* Scratch of the batched entry points is stream-ordered memory from a PRIVATE pool per device (the process-wide default pool is
+ * left alone).  Freed blocks stay cached there up to a quarter of the device memory ($WX_B200_SCRATCH_KEEP_MB overrides the
+ * bound) so that repeated calls do not re-map their workspace; wx_trim_scratch hands everything above keep_bytes back to the
+ * driver (call it when the embedding application needs the memory: it synchronises the device first). */
 int wx_trim_scratch(size_t keep_bytes);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 unsigned long long wx_launch_count(void);

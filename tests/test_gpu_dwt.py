@@ -376,3 +376,53 @@ def test_dwtall_idwtall(wx, O, cuda, dt):
     assert relerr(wx.idwtall(y2, wt, 2).cpu().numpy(), img) <= (1e-10 if dt == np.float64 else 3e-4)
     with pytest.raises(AssertionError):
         wx.dwtall(dev(x, cuda), wt, 9)
+
+
+# ------------------------------------------------------------------ strided views as OUTPUT arguments
+def test_in_place_wrappers_write_through_strided_views(wx, O, cuda):
+    """The reference's own wpd! hands sub-block views of y to dwt_step! (DWT.jl:145-156).  An output argument that is a strided view
+    must receive the result (it used to be silently replaced by a temporary contiguous copy)."""
+    wt = wx.wavelet("db4")
+    h, g = pair(wx, wt)
+    rng = np.random.default_rng(5)
+    n, L = 64, 3
+    x = rng.standard_normal(n)
+    # Julia column-major y(n, L+1) with level columns as views: here a (n, L+1) tensor whose COLUMNS are strided views
+    y = torch.full((n, L + 1), float("nan"), dtype=torch.float64, device=cuda)
+    y[:, 0] = dev(x, cuda)
+    for d in range(L):                                    # the loop of wpd! (DWT.jl:145-156)
+        n0 = n >> d
+        for j in range(1 << d):
+            v = y[j * n0:(j + 1) * n0, d]
+            w1 = y[j * n0:j * n0 + n0 // 2, d + 1]
+            w2 = y[j * n0 + n0 // 2:(j + 1) * n0, d + 1]
+            assert not w1.is_contiguous() or n0 // 2 == 1
+            wx.dwt_step_(w1, w2, v, h, g)
+    ref = O.wpd(x, h, g, L)
+    assert relerr(y.cpu().numpy().T[None], ref[None]) <= 1e-12
+    # inverse into a strided view, batched kernels into strided outputs, redundant and SIWT steps
+    back = torch.zeros((n, 2), dtype=torch.float64, device=cuda)
+    wx.idwt_step_(back[:, 1], y[:n // 2, 1].contiguous(), y[n // 2:, 1].contiguous(), h, g)
+    assert relerr(back[:, 1].cpu().numpy()[None], x[None]) <= 1e-12 and float(back[:, 0].abs().max()) == 0.0
+    xb = dev(rng.standard_normal((6, n)), cuda)
+    big = torch.zeros((6, L + 1, 2 * n), dtype=torch.float64, device=cuda)
+    yv = big[:, :, ::2]
+    wx.dwt._wpd_batch(xb, wt, L, yv)
+    assert torch.equal(yv, wx.wpdall(xb, wt, L)) and float(big[:, :, 1::2].abs().max()) == 0.0
+    holder = torch.zeros((n, 4), dtype=torch.float64, device=cuda)
+    w1s, w2s = wx.sdwt_step_(holder[:, 0], holder[:, 2], dev(x, cuda), 1, h, g)
+    r1, r2 = wx.sdwt_step(dev(x, cuda), 1, h, g)
+    assert torch.equal(holder[:, 0], r1) and torch.equal(holder[:, 2], r2) and w1s.data_ptr() == holder[:, 0].data_ptr()
+    # accumulate-into-output kernel: the packed copy must start with the view's contents
+    acc = torch.ones((n, 2), dtype=torch.float64, device=cuda)
+    ref_acc = torch.ones(n, dtype=torch.float64, device=cuda)
+    wx.isdwt_step_(acc[:, 0], r1, r2, 1, 0, 0, h, g, add2out=True)
+    wx.isdwt_step_(ref_acc, r1, r2, 1, 0, 0, h, g, add2out=True)
+    assert torch.equal(acc[:, 0], ref_acc) and float((acc[:, 1] - 1).abs().max()) == 0.0
+    t = torch.randn((8, 2 * n), dtype=torch.float64, device=cuda)
+    keep = t.clone()
+    wx.threshold_(t[:, ::2], wx.HardTH(), 0.5)
+    exp = keep[:, ::2].clone(); exp[exp.abs() <= 0.5] = 0
+    assert torch.equal(t[:, ::2], exp) and torch.equal(t[:, 1::2], keep[:, 1::2])
+    with pytest.raises(RuntimeError):
+        wx.dwt_step_(torch.zeros(2), torch.zeros(2), dev(x[:4], cuda), h, g)       # host outputs are rejected, not copied

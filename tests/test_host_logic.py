@@ -210,3 +210,18 @@ def test_denoising_host_objects(wx):
     f = wx.LocalDiscriminantBasis()
     assert f.wt.name == "haar" and isinstance(f.dm, wx.AsymmetricRelativeEntropy) and isinstance(f.en, wx.TimeFrequency)
     assert isinstance(f.dp, wx.BasisDiscriminantMeasure) and f.top_k is None and f.n_features is None and f.tree is None
+
+
+def test_wavelet_only_returns_verified_filters(wx):
+    """Wavelets.jl's table filters without a verified copy here raise instead of returning a heuristic root choice"""
+    import numpy as np
+    for name in ("haar", "db2", "db4", "db7", "db10", "sym4", "sym8", "coif4"):
+        q = wx.wavelet(name).taps
+        assert wx.filters.check_orthonormal(q) < 1e-12, name
+    for name in ("sym5", "sym6", "sym7", "sym9", "sym10", "coif2", "coif6", "beyl", "vaid", "batt2", "db11"):
+        with pytest.raises(ValueError):
+            wx.wavelet(name)
+    # any other filter crosses as data
+    q = wx.wavelet("db3").taps
+    f = wx.filters.OrthoFilter(tuple(q), "custom")
+    assert np.array_equal(wx.makereverseqmfpair(f, True)[0], q[::-1])

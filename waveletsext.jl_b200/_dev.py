@@ -21,16 +21,38 @@ def sfx(t: torch.Tensor) -> str:
     raise TypeError(f"unsupported element type {t.dtype}: the B200 path supports Float64 and Float32")
 
 
-def dev(t: torch.Tensor, name: str = "x") -> torch.Tensor:
-    """validate a device array (CUDA, contiguous, Float64/Float32). No silent host fallback."""
+def _check(t, name):
     if not isinstance(t, torch.Tensor):
         raise TypeError(f"{name}: expected a torch CUDA tensor (device array), got {type(t).__name__}")
     if not t.is_cuda:
         raise RuntimeError(f"{name}: tensor lives on {t.device}; the B200 path has no CPU fallback")
     sfx(t)
+
+
+def dev(t: torch.Tensor, name: str = "x") -> torch.Tensor:
+    """validate a READ-ONLY device array (CUDA, Float64/Float32); a strided view is packed into a contiguous copy.
+    Never use this for an argument the kernel writes: see ``out``.  No silent host fallback."""
+    _check(t, name)
     if not t.is_contiguous():
         t = t.contiguous()
     return t
+
+
+class out:
+    """an argument the kernel WRITES (the ``!`` arguments of the reference).  A contiguous tensor is used as it is; a strided
+    view (the reference's own ``wpd!`` hands sub-block views to ``dwt_step!``) is packed into a contiguous buffer that starts
+    with the view's contents (some kernels accumulate or write only a coset) and ``commit()`` copies the result back into
+    the caller's tensor.  ``.t`` is what the kernel gets; ``commit()`` returns the caller's tensor."""
+
+    def __init__(self, t: torch.Tensor, name: str = "y"):
+        _check(t, name)
+        self.orig = t
+        self.t = t if t.is_contiguous() else t.contiguous()
+
+    def commit(self) -> torch.Tensor:
+        if self.t is not self.orig:
+            self.orig.copy_(self.t)
+        return self.orig
 
 
 def same(a: torch.Tensor, *others: torch.Tensor) -> None:

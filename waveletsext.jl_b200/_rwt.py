@@ -57,17 +57,16 @@ def forward(ac: bool, mode: str, x, wt, L=None, xw=None):
     nc = ncols(mode, L, two)
     if xw is None:
         xw = x.new_empty((N, nc) + tuple(x.shape[1:]))
-    else:
-        xw = D.dev(xw, "xw")
-        D.same(x, xw)
-        assert tuple(xw.shape) == (N, nc) + tuple(x.shape[1:]), "AssertionError: size(xw) does not match the transform"
+    xo = D.out(xw, "xw")
+    D.same(x, xw)
+    assert tuple(xw.shape) == (N, nc) + tuple(x.shape[1:]), "AssertionError: size(xw) does not match the transform"
     if two:
         _, cols, rows = x.shape
         m, n = rows, cols
     else:
         m, n = 0, x.shape[1]
-    D.call("rwt", x, int(ac), MODE[mode], D.ptr(xw), D.ptr(x), m, n, L, N, h.ctypes.data, g.ctypes.data, len(h), D.stream(x))
-    return xw
+    D.call("rwt", x, int(ac), MODE[mode], D.ptr(xo.t), D.ptr(x), m, n, L, N, h.ctypes.data, g.ctypes.data, len(h), D.stream(x))
+    return xo.commit()
 
 
 def inverse(ac: bool, mode: str, xw, wt, tree=None, sm=None, x=None):
@@ -78,19 +77,18 @@ def inverse(ac: bool, mode: str, xw, wt, tree=None, sm=None, x=None):
     h, g = taps_for(ac, wt)
     if x is None:
         x = xw.new_empty((N,) + tuple(xw.shape[2:]))
-    else:
-        x = D.dev(x, "x")
-        D.same(x, xw)
-        assert tuple(x.shape) == (N,) + tuple(xw.shape[2:]), "AssertionError: size(x) == size(xw)[1:end-1]"
+    xo = D.out(x, "x")
+    D.same(x, xw)
+    assert tuple(x.shape) == (N,) + tuple(xw.shape[2:]), "AssertionError: size(x) == size(xw)[1:end-1]"
     if two:
         _, _, cols, rows = xw.shape
         m, n = rows, cols
     else:
         m, n = 0, xw.shape[2]
     t = D.tree_bytes(tree) if tree is not None else np.zeros(0, np.uint8)
-    D.call("irwt", xw, int(ac), MODE[mode], D.ptr(x), D.ptr(xw), m, n, nc, 0, N, t.ctypes.data if len(t) else 0, len(t),
+    D.call("irwt", xw, int(ac), MODE[mode], D.ptr(xo.t), D.ptr(xw), m, n, nc, 0, N, t.ctypes.data if len(t) else 0, len(t),
            -1 if sm is None else int(sm), h.ctypes.data, g.ctypes.data, len(h), D.stream(xw))
-    return x
+    return xo.commit()
 
 
 def sig_shape(x_single):

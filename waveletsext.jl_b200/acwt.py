@@ -20,13 +20,13 @@ def acdwt_step_(w1, w2, *rest):
     """``acdwt_step!(w1, w2, v, d, h, g)`` acwt/acwt_one_level.jl:101-128 / 2-D ``(w1..w4, v, d, h, g, temp)`` :240-276"""
     if len(rest) == 4:
         v, d, h, g = rest
-        v, w1, w2 = D.dev(v, "v"), D.dev(w1, "w1"), D.dev(w2, "w2")
+        v, o1, o2 = D.dev(v, "v"), D.out(w1, "w1"), D.out(w2, "w2")
         D.same(v, w1, w2)
         assert w1.numel() == w2.numel() == v.numel(), "AssertionError: length(w1) == length(w2) == length(v)"
         assert len(h) == len(g), "AssertionError: length(h) == length(g)"
         h, g = D.taps(h), D.taps(g)
-        D.call("acdwt_step", v, D.ptr(w1), D.ptr(w2), D.ptr(v), v.numel(), int(d), h.ctypes.data, g.ctypes.data, len(h), D.stream(v))
-        return w1, w2
+        D.call("acdwt_step", v, D.ptr(o1.t), D.ptr(o2.t), D.ptr(v), v.numel(), int(d), h.ctypes.data, g.ctypes.data, len(h), D.stream(v))
+        return o1.commit(), o2.commit()
     w3, w4, v, d, h, g = rest[:6]
     return _rstep2(1, w1, w2, w3, w4, v, d, h, g)
 
@@ -41,16 +41,16 @@ def acdwt_step(v, d, h, g):
 
 def iacdwt_step_(v, *ws):
     """``iacdwt_step!(v, w1, w2)`` acwt/acwt_one_level.jl:217-224 / 2-D ``(v, w1..w4, temp)`` :288-322"""
-    v = D.dev(v, "v")
+    ov = D.out(v, "v")
     ws = [D.dev(w, "w") for w in ws[:4] if isinstance(w, torch.Tensor)]
     D.same(v, *ws)
     assert all(w.shape == v.shape for w in ws), "AssertionError: length(v) == length(w1) == length(w2)"
     if v.dim() == 1:
-        D.call("iacdwt_step", v, D.ptr(v), D.ptr(ws[0]), D.ptr(ws[1]), v.numel(), D.stream(v))
-        return v
+        D.call("iacdwt_step", v, D.ptr(ov.t), D.ptr(ws[0]), D.ptr(ws[1]), v.numel(), D.stream(v))
+        return ov.commit()
     nc, nr = v.shape
-    D.call("irdwt_step2", v, 2, D.ptr(v), *[D.ptr(w) for w in ws[:4]], nr, nc, 0, 0, 0, 0, 0, 0, D.stream(v))
-    return v
+    D.call("irdwt_step2", v, 2, D.ptr(ov.t), *[D.ptr(w) for w in ws[:4]], nr, nc, 0, 0, 0, 0, 0, 0, D.stream(v))
+    return ov.commit()
 
 
 def iacdwt_step(*ws):

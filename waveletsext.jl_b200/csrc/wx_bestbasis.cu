@@ -1129,12 +1129,46 @@ int wx_bb_select(unsigned char *trees, double *costs, long nnodes, long m, long 
 
 }  // extern "C"
 
+// the checks of getbasiscoefall(Xw, tree::BitArray{2}) Utils.jl:204-218 on the device: every tree valid (a split node's parent is
+// split) and no split node at depth >= K-1 ("Not enough decomposition levels in Xw"); flag bit 0 / bit 1
+__global__ void __launch_bounds__(kT) trees_check_k(int *flag, const unsigned char *trees, long ntree, long N, int ar, int K)
+{
+    const long gid = (long)blockIdx.x * kT + threadIdx.x;
+    if (gid >= ntree * N) return;
+    const long k = gid / ntree, i = gid - k * ntree + 1;                 // 1-based node
+    const unsigned char *t = trees + k * ntree;
+    if (!t[i - 1]) return;
+    int bad = 0;
+    if (i > 1) {
+        const long p = ar == 2 ? i / 2 : (i + 2) / 4;
+        if (!t[p - 1]) bad |= 1;
+    }
+    const int d = ar == 2 ? ilog2d(i) : quaddepthd(i);
+    if (d >= K - 1) bad |= 2;
+    if (bad) atomicOr(flag, bad);
+}
+
 // per-signal-tree gather (wx_trees.cu exports the C entry points)
 template <typename T>
 int wx_gather_multi(T *out, const T *Xw, long m, long n, int K, long N, const unsigned char *trees, long ntree, cudaStream_t s)
 {
     const long sz = (m > 0 ? m : 1) * n;
     if (sz * N == 0) return WX_OK;
+    long expect = n - 1;
+    if (m > 0) { const int Lm = wx_maxlevels(m < n ? m : n); expect = ((1L << (2 * Lm)) - 1) / 3; }
+    WX_REQUIRE(ntree == expect, "AssertionError: n_t == gettreelength(sz...) (%ld != %ld)", ntree, expect);
+    if (ntree > 0) {
+        int *flag; int rc = wx_scratch(&flag, 1, s); if (rc) return rc;
+        WX_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), s));
+        trees_check_k<<<gridf(ntree * N), kT, 0, s>>>(flag, trees, ntree, N, m > 0 ? 4 : 2, K);
+        WX_LAUNCHED();
+        int h = 0;
+        WX_CUDA(cudaMemcpyAsync(&h, flag, sizeof(int), cudaMemcpyDeviceToHost, s));
+        WX_CUDA(cudaStreamSynchronize(s));
+        rc = wx_scratch_free(flag, s); if (rc) return rc;
+        if (h & 1) return wx_fail(WX_EINVAL, "AssertionError: all trees must be valid (isvalidtree)");
+        if (h & 2) return wx_fail(WX_EINVAL, "ArgumentError: Not enough decomposition levels in Xw.");
+    }
     gather_multi_k<T><<<gridf(sz * N), kT, 0, s>>>(out, Xw, m, n, K, N, trees, ntree);
     WX_LAUNCHED();
     return WX_OK;

@@ -80,8 +80,9 @@ static inline void wx_quadrangel(long m, long n, long idx, long *r0, long *c0, l
     *c0 = (idx % 2 == 0) ? pc0 : pc0 + pnc / 2;
 }
 
-struct WxDev { int sms; size_t smem_optin; int dev; };
-int wx_devinfo(WxDev &d);   // cached per device
+struct WxDev { int sms; size_t smem_optin; int dev; cudaMemPool_t pool; };
+int wx_devinfo(WxDev &d);   // cached per device (thread safe); creates the library's private scratch pool on first use
+int wx_pool_alloc(void **p, size_t bytes, cudaStream_t s);   // stream-ordered allocation from that pool (free: cudaFreeAsync)
 
 // ----------------------------------------------------------------------------------------------
 // device helpers

@@ -22,14 +22,14 @@ int wpdall_host(T *y, const T *x, long n, int L, long N, const double *h, const 
         if (chunk < 1) chunk = 1;
     }
     if (chunk > N) chunk = N;
-    { WxDev dv; int rc0 = wx_devinfo(dv); if (rc0) return rc0; }      // also keeps freed pool blocks cached across calls
+    WxDev dv; { int rc0 = wx_devinfo(dv); if (rc0) return rc0; }      // the library's scratch pool keeps freed slots cached across calls
     cudaStream_t st[kSlots] = {nullptr, nullptr, nullptr};
     T *dx[kSlots] = {nullptr, nullptr, nullptr}, *dy[kSlots] = {nullptr, nullptr, nullptr};
     int rc = WX_OK;
     auto cleanup = [&]() {
         for (int i = 0; i < kSlots; ++i) {
             if (st[i]) cudaStreamSynchronize(st[i]);
-            if (dx[i]) cudaFreeAsync(dx[i], st[i]);         // back to the default pool (release threshold = max, wx_devinfo):
+            if (dx[i]) cudaFreeAsync(dx[i], st[i]);         // back to the library's scratch pool (wx_devinfo):
             if (dy[i]) cudaFreeAsync(dy[i], st[i]);         // the next call reuses the slots instead of paying cudaMalloc again
             if (st[i]) { cudaStreamSynchronize(st[i]); cudaStreamDestroy(st[i]); }
         }
@@ -38,8 +38,8 @@ int wpdall_host(T *y, const T *x, long n, int L, long N, const double *h, const 
     const int slots = nchunks < kSlots ? (int)nchunks : kSlots;
     for (int i = 0; i < slots; ++i) {
         cudaError_t e = cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking);
-        if (e == cudaSuccess) e = cudaMallocAsync((void **)&dx[i], in_b * (size_t)chunk, st[i]);
-        if (e == cudaSuccess) e = cudaMallocAsync((void **)&dy[i], out_b * (size_t)chunk, st[i]);
+        if (e == cudaSuccess) e = cudaMallocFromPoolAsync((void **)&dx[i], in_b * (size_t)chunk, dv.pool, st[i]);
+        if (e == cudaSuccess) e = cudaMallocFromPoolAsync((void **)&dy[i], out_b * (size_t)chunk, dv.pool, st[i]);
         if (e != cudaSuccess) {
             cleanup();
             cudaGetLastError();
@@ -83,7 +83,7 @@ int wpd_bestbasis_host(wx_comm_t *comm, T *coef, unsigned char *tree, long ntree
     const size_t in_b = (size_t)n * sizeof(T), row_b = in_b * (size_t)(L + 1);
     if (chunk <= 0) { chunk = (long)(((size_t)256 << 20) / in_b); if (chunk < 1) chunk = 1; }
     if (chunk > N && N > 0) chunk = N;
-    { WxDev dv; int rc0 = wx_devinfo(dv); if (rc0) return rc0; }
+    WxDev dv; { int rc0 = wx_devinfo(dv); if (rc0) return rc0; }
     cudaStream_t st[2] = {nullptr, nullptr};
     T *dx[2] = {nullptr, nullptr}, *y = nullptr;
     cudaEvent_t ev = nullptr;
@@ -92,8 +92,8 @@ int wpd_bestbasis_host(wx_comm_t *comm, T *coef, unsigned char *tree, long ntree
     cudaError_t e = cudaSuccess;
     for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaMallocAsync((void **)&y, row_b * (size_t)(N > 0 ? N : 1), st[0]);
-    for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaMallocAsync((void **)&dx[i], in_b * (size_t)(chunk > 0 ? chunk : 1), st[i]);
+    if (e == cudaSuccess) e = cudaMallocFromPoolAsync((void **)&y, row_b * (size_t)(N > 0 ? N : 1), dv.pool, st[0]);
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaMallocFromPoolAsync((void **)&dx[i], in_b * (size_t)(chunk > 0 ? chunk : 1), dv.pool, st[i]);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st[0]);          // y is used from both streams
     if (e != cudaSuccess) fail(e, "wpd_bestbasis_host setup");
     const long nchunks = N > 0 ? (N + chunk - 1) / chunk : 0;

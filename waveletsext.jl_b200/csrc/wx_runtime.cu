@@ -1,29 +1,54 @@
 // wx_runtime.cu -- runtime part of the C ABI (device memory, copies, sync, error text).
 #include "wx_common.cuh"
+#include <cstdlib>
 
 thread_local char wx_errbuf[512] = "";
 std::atomic<unsigned long long> wx_launches{0};
 
+// Per-device context, created once under a mutex (two host threads may make their first call at the same time).
+// Library scratch is stream-ordered memory of a PRIVATE pool per device: the process-wide default pool (and whoever else uses
+// it) keeps its own release threshold.  Freed blocks stay cached in the pool up to a quarter of the device memory (so a
+// repeated call does not re-map its workspace after every synchronisation); WX_B200_SCRATCH_KEEP_MB overrides the bound and
+// wx_trim_scratch hands the cache back to the driver.
+#include <mutex>
+static std::mutex wx_dev_mutex;
+static WxDev wx_dev_cache[64];
+static bool wx_dev_have[64] = {false};
+
 int wx_devinfo(WxDev &d)
 {
-    static WxDev cache[64];
-    static bool have[64] = {false};
     int dev = 0;
     WX_CUDA(cudaGetDevice(&dev));
-    if (dev >= 0 && dev < 64 && have[dev]) { d = cache[dev]; return WX_OK; }
+    if (dev < 0 || dev >= 64) return wx_fail(WX_EUNSUPPORTED, "device index %d outside 0..63", dev);
+    std::lock_guard<std::mutex> lock(wx_dev_mutex);
+    if (wx_dev_have[dev]) { d = wx_dev_cache[dev]; return WX_OK; }
     int sms = 0, smem = 0;
     WX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     WX_CUDA(cudaDeviceGetAttribute(&smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    d.sms = sms; d.smem_optin = (size_t)smem; d.dev = dev;
-    // stream-ordered scratch (wx_scratch) comes from the default pool: keep freed blocks cached across synchronisations
-    // instead of returning them to the driver (the default threshold of 0 makes every call after a sync re-map memory)
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-        unsigned long long keep = ~0ULL;
-        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-    }
-    cudaGetLastError();
-    if (dev >= 0 && dev < 64) { cache[dev] = d; have[dev] = true; }
+    d.sms = sms; d.smem_optin = (size_t)smem; d.dev = dev; d.pool = nullptr;
+    cudaMemPoolProps props;
+    memset(&props, 0, sizeof(props));
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = dev;
+    WX_CUDA(cudaMemPoolCreate(&d.pool, &props));
+    size_t freeb = 0, totalb = 0;
+    unsigned long long keep = 0;
+    if (cudaMemGetInfo(&freeb, &totalb) == cudaSuccess) keep = (unsigned long long)(totalb / 4);
+    if (const char *env = getenv("WX_B200_SCRATCH_KEEP_MB")) keep = (unsigned long long)atoll(env) << 20;
+    WX_CUDA(cudaMemPoolSetAttribute(d.pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    wx_dev_cache[dev] = d; wx_dev_have[dev] = true;
+    return WX_OK;
+}
+
+int wx_pool_alloc(void **p, size_t bytes, cudaStream_t s)
+{
+    *p = nullptr;
+    WxDev d; int rc = wx_devinfo(d); if (rc) return rc;
+    cudaError_t e = cudaMallocFromPoolAsync(p, bytes ? bytes : 1, d.pool, s);
+    if (e == cudaErrorMemoryAllocation) { cudaGetLastError(); return wx_fail(WX_ENOMEM, "scratch of %zu bytes: out of device memory", bytes); }
+    WX_CUDA(e);
     return WX_OK;
 }
 
@@ -75,12 +100,9 @@ int wx_malloc(void **dptr, size_t bytes)
 
 int wx_trim_scratch(size_t keep_bytes)
 {
-    int dev = 0;
-    WX_CUDA(cudaGetDevice(&dev));
+    WxDev d; int rc = wx_devinfo(d); if (rc) return rc;
     WX_CUDA(cudaDeviceSynchronize());
-    cudaMemPool_t pool;
-    WX_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
-    WX_CUDA(cudaMemPoolTrimTo(pool, keep_bytes));
+    WX_CUDA(cudaMemPoolTrimTo(d.pool, keep_bytes));
     return WX_OK;
 }
 

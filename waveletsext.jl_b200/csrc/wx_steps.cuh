@@ -39,11 +39,7 @@ template <typename T> int wx_launch_copy(View<T> dst, View<const T> src, long n,
 template <typename T>
 static inline int wx_scratch(T **p, size_t elems, cudaStream_t s)
 {
-    *p = nullptr;
-    cudaError_t e = cudaMallocAsync((void **)p, (elems ? elems : 1) * sizeof(T), s);
-    if (e == cudaErrorMemoryAllocation) { cudaGetLastError(); return wx_fail(WX_ENOMEM, "scratch of %zu bytes: out of device memory", elems * sizeof(T)); }
-    WX_CUDA(e);
-    return WX_OK;
+    return wx_pool_alloc((void **)p, (elems ? elems : 1) * sizeof(T), s);
 }
 static inline int wx_scratch_free(void *p, cudaStream_t s)
 {

@@ -206,10 +206,10 @@ def _threshold_into(Y, X, th, t, colmask=None, keep=(0, 0)):
 
 def threshold_(x, th, t):
     """``threshold!(x, th, t)`` (Wavelets.jl) on every coefficient of a device array, in place"""
-    x = D.dev(x, "x")
-    flat = x.view(-1, x.shape[-1]) if x.dim() > 1 else x.view(1, -1)
+    xo = D.out(x, "x")
+    flat = xo.t.view(-1, xo.t.shape[-1]) if xo.t.dim() > 1 else xo.t.view(1, -1)
     _threshold_into(flat, flat, th, float(t))
-    return x
+    return xo.commit()
 
 
 def threshold(x, th, t):

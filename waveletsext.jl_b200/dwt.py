@@ -29,23 +29,23 @@ def dwt_step_(w1, w2, *rest):
     ``dwt_step!(w1, w2, w3, w4, v, h, g, temp)`` :319-354 (``temp`` accepted and ignored: scratch is internal)."""
     if len(rest) == 3:
         v, h, g = rest
-        v, w1, w2 = D.dev(v, "v"), D.dev(w1, "w1"), D.dev(w2, "w2")
+        v, o1, o2 = D.dev(v, "v"), D.out(w1, "w1"), D.out(w2, "w2")
         D.same(v, w1, w2)
         assert w1.numel() == w2.numel() == v.numel() // 2, "AssertionError: length(w1) == length(w2) == length(v)/2"
         assert len(h) == len(g), "AssertionError: length(h) == length(g)"
         h, g = D.taps(h), D.taps(g)
-        D.call("dwt_step", v, D.ptr(w1), D.ptr(w2), D.ptr(v), v.numel(), h.ctypes.data, g.ctypes.data, len(h), D.stream(v))
-        return w1, w2
+        D.call("dwt_step", v, D.ptr(o1.t), D.ptr(o2.t), D.ptr(v), v.numel(), h.ctypes.data, g.ctypes.data, len(h), D.stream(v))
+        return o1.commit(), o2.commit()
     w3, w4, v, h, g = rest[:5]
     v = D.dev(v, "v")
-    ws = [D.dev(w, "w") for w in (w1, w2, w3, w4)]
-    D.same(v, *ws)
-    nc, nr = ws[0].shape
-    assert all(tuple(w.shape) == (nc, nr) for w in ws), "AssertionError: size(w1) == size(w2) == size(w3) == size(w4)"
+    ws = [D.out(w, "w") for w in (w1, w2, w3, w4)]
+    D.same(v, w1, w2, w3, w4)
+    nc, nr = w1.shape
+    assert all(tuple(w.shape) == (nc, nr) for w in (w1, w2, w3, w4)), "AssertionError: size(w1) == size(w2) == size(w3) == size(w4)"
     assert tuple(v.shape) == (2 * nc, 2 * nr), "AssertionError: size(w1)*2 == size(v)"
     h, g = D.taps(h), D.taps(g)
-    D.call("dwt_step2", v, *[D.ptr(w) for w in ws], D.ptr(v), nr, nc, h.ctypes.data, g.ctypes.data, len(h), D.stream(v))
-    return tuple(ws)
+    D.call("dwt_step2", v, *[D.ptr(w.t) for w in ws], D.ptr(v), nr, nc, h.ctypes.data, g.ctypes.data, len(h), D.stream(v))
+    return tuple(w.commit() for w in ws)
 
 
 def dwt_step(v, h, g):
@@ -63,23 +63,23 @@ def idwt_step_(v, *rest):
     """``idwt_step!(v, w1, w2, h, g)`` :192-223  /  ``idwt_step!(v, w1, w2, w3, w4, h, g, temp)`` :401-436"""
     if len(rest) == 4:
         w1, w2, h, g = rest
-        v, w1, w2 = D.dev(v, "v"), D.dev(w1, "w1"), D.dev(w2, "w2")
+        ov, w1, w2 = D.out(v, "v"), D.dev(w1, "w1"), D.dev(w2, "w2")
         D.same(v, w1, w2)
         assert w1.numel() == w2.numel() == v.numel() // 2, "AssertionError: length(w1) == length(w2) == length(v)/2"
         assert len(h) == len(g), "AssertionError: length(h) == length(g)"
         h, g = D.taps(h), D.taps(g)
-        D.call("idwt_step", v, D.ptr(v), D.ptr(w1), D.ptr(w2), v.numel(), h.ctypes.data, g.ctypes.data, len(h), D.stream(v))
-        return v
+        D.call("idwt_step", v, D.ptr(ov.t), D.ptr(w1), D.ptr(w2), v.numel(), h.ctypes.data, g.ctypes.data, len(h), D.stream(v))
+        return ov.commit()
     w1, w2, w3, w4, h, g = rest[:6]
-    v = D.dev(v, "v")
+    ov = D.out(v, "v")
     ws = [D.dev(w, "w") for w in (w1, w2, w3, w4)]
     D.same(v, *ws)
     nc, nr = ws[0].shape
     assert all(tuple(w.shape) == (nc, nr) for w in ws), "AssertionError: size(w1) == size(w2) == size(w3) == size(w4)"
     assert tuple(v.shape) == (2 * nc, 2 * nr), "AssertionError: size(w1)*2 == size(v)"
     h, g = D.taps(h), D.taps(g)
-    D.call("idwt_step2", v, D.ptr(v), *[D.ptr(w) for w in ws], nr, nc, h.ctypes.data, g.ctypes.data, len(h), D.stream(v))
-    return v
+    D.call("idwt_step2", v, D.ptr(ov.t), *[D.ptr(w) for w in ws], nr, nc, h.ctypes.data, g.ctypes.data, len(h), D.stream(v))
+    return ov.commit()
 
 
 def idwt_step(*args):
@@ -100,16 +100,15 @@ def _wpd_batch(x, wt, L, y=None):
     N = x.shape[0]
     if y is None:
         y = x.new_empty((N, L + 1) + tuple(x.shape[1:]))
-    else:
-        y = D.dev(y, "y")
-        D.same(x, y)
-        assert tuple(y.shape) == (N, L + 1) + tuple(x.shape[1:]), "AssertionError: size(y) == (n, L+1)"
+    yo = D.out(y, "y")
+    D.same(x, y)
+    assert tuple(y.shape) == (N, L + 1) + tuple(x.shape[1:]), "AssertionError: size(y) == (n, L+1)"
     if x.dim() == 2:
-        D.call("wpd1d", x, D.ptr(y), D.ptr(x), x.shape[1], L, N, h.ctypes.data, g.ctypes.data, len(h), D.stream(x))
+        D.call("wpd1d", x, D.ptr(yo.t), D.ptr(x), x.shape[1], L, N, h.ctypes.data, g.ctypes.data, len(h), D.stream(x))
     else:
         _, n, m = x.shape
-        D.call("wpd2d", x, D.ptr(y), D.ptr(x), m, n, L, N, h.ctypes.data, g.ctypes.data, len(h), D.stream(x))
-    return y
+        D.call("wpd2d", x, D.ptr(yo.t), D.ptr(x), m, n, L, N, h.ctypes.data, g.ctypes.data, len(h), D.stream(x))
+    return yo.commit()
 
 
 def _tree_batch(name, x, wt, tree, y=None):
@@ -120,16 +119,15 @@ def _tree_batch(name, x, wt, tree, y=None):
     N = x.shape[0]
     if y is None:
         y = torch.empty_like(x)
-    else:
-        y = D.dev(y, "y")
-        D.same(x, y)
-        assert y.shape == x.shape, "AssertionError: size(y) == size(x)"
+    yo = D.out(y, "y")
+    D.same(x, y)
+    assert y.shape == x.shape, "AssertionError: size(y) == size(x)"
     if x.dim() == 2:
-        D.call(f"{name}1d", x, D.ptr(y), D.ptr(x), x.shape[1], N, t.ctypes.data, len(t), h.ctypes.data, g.ctypes.data, len(h), D.stream(x))
+        D.call(f"{name}1d", x, D.ptr(yo.t), D.ptr(x), x.shape[1], N, t.ctypes.data, len(t), h.ctypes.data, g.ctypes.data, len(h), D.stream(x))
     else:
         _, n, m = x.shape
-        D.call(f"{name}2d", x, D.ptr(y), D.ptr(x), m, n, N, t.ctypes.data, len(t), h.ctypes.data, g.ctypes.data, len(h), D.stream(x))
-    return y
+        D.call(f"{name}2d", x, D.ptr(yo.t), D.ptr(x), m, n, N, t.ctypes.data, len(t), h.ctypes.data, g.ctypes.data, len(h), D.stream(x))
+    return yo.commit()
 
 
 def _sigshape(x_single):
@@ -192,15 +190,15 @@ def _iwpd_batch(Xw, wt, tree, x=None):
     N, K = Xw.shape[0], Xw.shape[1]
     if x is None:
         x = Xw.new_empty((N,) + tuple(Xw.shape[2:]))
-    else:
-        x = D.dev(x, "x")
-        D.same(x, Xw)
+    xo = D.out(x, "x")
+    D.same(x, Xw)
+    assert tuple(x.shape) == (N,) + tuple(Xw.shape[2:]), "AssertionError: size(x) == size(xw)[1:end-1]"
     if Xw.dim() == 3:
         m, n = 0, Xw.shape[2]
     else:
         n, m = Xw.shape[2], Xw.shape[3]
-    D.call("iwpd", Xw, D.ptr(x), D.ptr(Xw), m, n, K, N, t.ctypes.data, len(t), h.ctypes.data, g.ctypes.data, len(h), D.stream(Xw))
-    return x
+    D.call("iwpd", Xw, D.ptr(xo.t), D.ptr(Xw), m, n, K, N, t.ctypes.data, len(t), h.ctypes.data, g.ctypes.data, len(h), D.stream(Xw))
+    return xo.commit()
 
 
 # ------------------------------------------------------------------ wpt / iwpt (single signal)
@@ -311,7 +309,12 @@ def getbasiscoefall(Xw, tree):
             m, n = 0, Xw.shape[2]
         else:
             n, m = Xw.shape[2], Xw.shape[3]
-        D.call("gather_basis_multi", Xw, D.ptr(out), D.ptr(Xw), m, n, K, N, D.ptr(t8), t8.shape[1], D.stream(Xw))
+        try:        # the library checks n_t == gettreelength, isvalidtree of every tree and the depth against K (Utils.jl:204-218)
+            D.call("gather_basis_multi", Xw, D.ptr(out), D.ptr(Xw), m, n, K, N, D.ptr(t8), t8.shape[1], D.stream(Xw))
+        except AssertionError as e:
+            if "Not enough decomposition levels" in str(e):
+                raise ValueError(str(e)) from None      # ArgumentError in the reference
+            raise
         return out
     tree = np.asarray(tree, dtype=bool)
     if tree.ndim == 2:

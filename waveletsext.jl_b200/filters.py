@@ -94,15 +94,6 @@ _COIF4_ANCHOR = [0.016387336463522112, -0.04146493678175915, -0.0673725547219630
                  -0.0007205494453645122]
 
 
-def _phase_nonlinearity(q: np.ndarray) -> float:
-    w = np.linspace(0.05, math.pi * 0.95, 96)
-    H = np.array([np.sum(q * np.exp(-1j * ww * np.arange(len(q)))) for ww in w])
-    ph = np.unwrap(np.angle(H))
-    A = np.vstack([w, np.ones_like(w)]).T
-    coef, *_ = np.linalg.lstsq(A, ph, rcond=None)
-    return float(np.sum((ph - A @ coef) ** 2))
-
-
 @lru_cache(maxsize=None)
 def _symlet(N: int) -> tuple:
     ys = _halfband_roots(N)
@@ -131,10 +122,8 @@ def _symlet(N: int) -> tuple:
             best = best[::-1]
         if np.abs(best - a).max() > 1e-6:
             raise RuntimeError(f"sym{N}: no root subset matches the recalled table")
-    else:
-        best = min(cands, key=_phase_nonlinearity)
-        if abs(best[0]) > abs(best[-1]):
-            best = best[::-1]
+    else:       # unreachable through wavelet(): only anchored symlets are advertised
+        raise ValueError(f"sym{N}: no verified table to select the root subset and orientation against")
     return tuple(float(v) for v in np.array(best))
 
 
@@ -181,17 +170,22 @@ WT = _WT()
 
 
 def wavelet(name: str) -> OrthoFilter:
-    """``wavelet(WT.db4)`` -> OrthoFilter. Supported: haar, db1..db10, sym4..sym10, coif4."""
+    """``wavelet(WT.db4)`` -> OrthoFilter.  Supported: haar, db1..db10 (spectral factorisation, the construction Wavelets.jl
+    itself uses for dbN), sym4, sym8 and coif4 (each checked against a recalled copy of the tabulated filter).  Wavelets.jl's
+    other table filters (sym5-7, sym9-10, coif2/6/8, batt*, beyl, vaid) have no verified table in this offline image: they
+    raise instead of returning taps that may differ from the reference's by a root choice or a time reversal -- pass the taps
+    as data (``OrthoFilter(qmf, name)``), which is what crosses the C ABI anyway."""
     name = str(name).lower()
     if name in ("haar", "db1"):
         return OrthoFilter(_daubechies(1), "haar")
     if name.startswith("db") and name[2:].isdigit() and 1 <= int(name[2:]) <= 10:
         return OrthoFilter(_daubechies(int(name[2:])), name)
-    if name.startswith("sym") and name[3:].isdigit() and 4 <= int(name[3:]) <= 10:
+    if name in ("sym4", "sym8"):
         return OrthoFilter(_symlet(int(name[3:])), name)
     if name == "coif4":
         return OrthoFilter(_coif4(), name)
-    raise ValueError(f"unknown or unsupported wavelet class {name!r}")
+    raise ValueError(f"unknown or unverified wavelet class {name!r}: supported names are haar, db1..db10, sym4, sym8, coif4; "
+                     f"for any other filter pass its qmf taps as data: OrthoFilter(taps, name)")
 
 
 def _qmf(wt) -> np.ndarray:

@@ -16,24 +16,24 @@ __all__ = ["sidwt_step_", "isidwt_step_", "ndyad", "ns_dwt", "ns_idwt"]
 
 def sidwt_step_(w1, w2, v, h, g, s: bool):
     """``sidwt_step!(w1, w2, v, h, g, s)`` siwt/siwt_one_level.jl:71-98"""
-    v, w1, w2 = D.dev(v, "v"), D.dev(w1, "w1"), D.dev(w2, "w2")
+    v, o1, o2 = D.dev(v, "v"), D.out(w1, "w1"), D.out(w2, "w2")
     D.same(v, w1, w2)
     assert w1.numel() == w2.numel() == v.numel() // 2, "AssertionError: length(w1) == length(w2) == length(v)/2"
     assert len(h) == len(g), "AssertionError: length(h) == length(g)"
     h, g = D.taps(h), D.taps(g)
-    D.call("sidwt_step", v, D.ptr(w1), D.ptr(w2), D.ptr(v), v.numel(), h.ctypes.data, g.ctypes.data, len(h), int(bool(s)), D.stream(v))
-    return w1, w2
+    D.call("sidwt_step", v, D.ptr(o1.t), D.ptr(o2.t), D.ptr(v), v.numel(), h.ctypes.data, g.ctypes.data, len(h), int(bool(s)), D.stream(v))
+    return o1.commit(), o2.commit()
 
 
 def isidwt_step_(v, w1, w2, h, g, s: bool):
     """``isidwt_step!(v, w1, w2, h, g, s)`` siwt/siwt_one_level.jl:153-184"""
-    v, w1, w2 = D.dev(v, "v"), D.dev(w1, "w1"), D.dev(w2, "w2")
+    ov, w1, w2 = D.out(v, "v"), D.dev(w1, "w1"), D.dev(w2, "w2")
     D.same(v, w1, w2)
     assert w1.numel() == w2.numel() == v.numel() // 2, "AssertionError: length(w1) == length(w2) == length(v)/2"
     assert len(h) == len(g), "AssertionError: length(h) == length(g)"
     h, g = D.taps(h), D.taps(g)
-    D.call("isidwt_step", v, D.ptr(v), D.ptr(w1), D.ptr(w2), v.numel(), h.ctypes.data, g.ctypes.data, len(h), int(bool(s)), D.stream(v))
-    return v
+    D.call("isidwt_step", v, D.ptr(ov.t), D.ptr(w1), D.ptr(w2), v.numel(), h.ctypes.data, g.ctypes.data, len(h), int(bool(s)), D.stream(v))
+    return ov.commit()
 
 
 def ndyad(L: int, Lmax: int, gender: bool) -> range:

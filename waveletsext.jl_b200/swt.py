@@ -20,26 +20,26 @@ def sdwt_step_(w1, w2, *rest):
     """``sdwt_step!(w1, w2, v, d, h, g)`` swt/swt_one_level.jl:99-127 / 2-D ``(w1,w2,w3,w4,v,d,h,g,temp)`` :334-370"""
     if len(rest) == 4:
         v, d, h, g = rest
-        v, w1, w2 = D.dev(v, "v"), D.dev(w1, "w1"), D.dev(w2, "w2")
+        v, o1, o2 = D.dev(v, "v"), D.out(w1, "w1"), D.out(w2, "w2")
         D.same(v, w1, w2)
         assert w1.numel() == w2.numel() == v.numel(), "AssertionError: length(w1) == length(w2) == length(v)"
         assert len(h) == len(g), "AssertionError: length(h) == length(g)"
         h, g = D.taps(h), D.taps(g)
-        D.call("sdwt_step", v, D.ptr(w1), D.ptr(w2), D.ptr(v), v.numel(), int(d), h.ctypes.data, g.ctypes.data, len(h), D.stream(v))
-        return w1, w2
+        D.call("sdwt_step", v, D.ptr(o1.t), D.ptr(o2.t), D.ptr(v), v.numel(), int(d), h.ctypes.data, g.ctypes.data, len(h), D.stream(v))
+        return o1.commit(), o2.commit()
     w3, w4, v, d, h, g = rest[:6]
     return _rstep2(0, w1, w2, w3, w4, v, d, h, g)
 
 
 def _rstep2(ac, w1, w2, w3, w4, v, d, h, g):
     v = D.dev(v, "v")
-    ws = [D.dev(w, "w") for w in (w1, w2, w3, w4)]
-    D.same(v, *ws)
-    assert all(w.shape == v.shape for w in ws), "AssertionError: size(v) == size(w1) == size(w2) == size(w3) == size(w4)"
+    ws = [D.out(w, "w") for w in (w1, w2, w3, w4)]
+    D.same(v, w1, w2, w3, w4)
+    assert all(w.shape == v.shape for w in (w1, w2, w3, w4)), "AssertionError: size(v) == size(w1) == size(w2) == size(w3) == size(w4)"
     nc, nr = v.shape
     h, g = D.taps(h), D.taps(g)
-    D.call("rdwt_step2", v, ac, *[D.ptr(w) for w in ws], D.ptr(v), nr, nc, int(d), h.ctypes.data, g.ctypes.data, len(h), D.stream(v))
-    return tuple(ws)
+    D.call("rdwt_step2", v, ac, *[D.ptr(w.t) for w in ws], D.ptr(v), nr, nc, int(d), h.ctypes.data, g.ctypes.data, len(h), D.stream(v))
+    return tuple(w.commit() for w in ws)
 
 
 def sdwt_step(v, d, h, g):
@@ -53,20 +53,21 @@ def sdwt_step(v, d, h, g):
 def isdwt_step_(v, *rest, add2out=False):
     """``isdwt_step!(v, w1, w2, d, h, g)`` (average, :257-277) / ``(v, w1, w2, d, sv, sw, h, g; add2out)`` (shift, :279-318)
     and the 2-D forms ``(v, w1..w4, d, h, g, temp)`` :395-431 / ``(v, w1..w4, d, sv, sw, h, g, temp)`` :433-469"""
-    v = D.dev(v, "v")
+    ov = D.out(v, "v")
     if v.dim() == 1:
         w1, w2 = D.dev(rest[0], "w1"), D.dev(rest[1], "w2")
         D.same(v, w1, w2)
         if len(rest) == 5:
             d, h, g = rest[2:]
             h, g = D.taps(h), D.taps(g)
-            D.call("isdwt_step_avg", v, D.ptr(v), D.ptr(w1), D.ptr(w2), v.numel(), int(d), h.ctypes.data, g.ctypes.data, len(h), D.stream(v))
+            D.call("isdwt_step_avg", v, D.ptr(ov.t), D.ptr(w1), D.ptr(w2), v.numel(), int(d), h.ctypes.data, g.ctypes.data, len(h), D.stream(v))
+            ov.commit()
             return None                      # the reference's average-based method returns nothing
         d, sv, sw, h, g = rest[2:7]
         h, g = D.taps(h), D.taps(g)
-        D.call("isdwt_step_shift", v, D.ptr(v), D.ptr(w1), D.ptr(w2), v.numel(), int(d), int(sv), int(sw), h.ctypes.data, g.ctypes.data, len(h),
+        D.call("isdwt_step_shift", v, D.ptr(ov.t), D.ptr(w1), D.ptr(w2), v.numel(), int(d), int(sv), int(sw), h.ctypes.data, g.ctypes.data, len(h),
                int(bool(add2out)), D.stream(v))
-        return v
+        return ov.commit()
     ws = [D.dev(w, "w") for w in rest[:4]]
     D.same(v, *ws)
     nc, nr = v.shape
@@ -78,9 +79,9 @@ def isdwt_step_(v, *rest, add2out=False):
         d, sv, sw, h, g = tail[:5]
         mode = 1
     h, g = D.taps(h), D.taps(g)
-    D.call("irdwt_step2", v, mode, D.ptr(v), *[D.ptr(w) for w in ws], nr, nc, int(d), int(sv), int(sw), h.ctypes.data, g.ctypes.data, len(h),
+    D.call("irdwt_step2", v, mode, D.ptr(ov.t), *[D.ptr(w) for w in ws], nr, nc, int(d), int(sv), int(sw), h.ctypes.data, g.ctypes.data, len(h),
            D.stream(v))
-    return v
+    return ov.commit()
 
 
 def isdwt_step(*args):
