@@ -199,8 +199,8 @@ int wpd1d_launch_tma(T *y, const T *x, long n, int L, long N, int d0, const Taps
     // peak), 4.80 ms with two 512-thread CTAs; haar / db2 / db3 do not care (5.2 ms either way), coif4 and sym8 lose with two
     // (5.0 -> 5.4 ms, 5.3 -> 6.6 ms) and lose more with 512 threads.  Fewer concurrent store streams per SM suit the DRAM better as
     // long as two CTAs still cover the FP64 work.  Knobs for re-measuring: WX_B200_WPD1D_THREADS (256 / 512), WX_B200_WPD1D_OCC.
-    static const char *tenv = getenv("WX_B200_WPD1D_THREADS");
-    static const char *oenv = getenv("WX_B200_WPD1D_OCC");
+    const char *tenv = getenv("WX_B200_WPD1D_THREADS");             // read per call so that one process can sweep them
+    const char *oenv = getenv("WX_B200_WPD1D_OCC");
     if (threads > 256) threads = (tenv && atoi(tenv) == 512 && threads >= 512) ? 512 : 256;
     auto kern = wpd1d_tma_k<T, F>;
     WX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
