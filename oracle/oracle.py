@@ -474,6 +474,8 @@ def tree_costs_lsdb(X, redundant=False):
         N, K, n, m = X.shape
         costs = np.empty(K if redundant else (4 ** K - 1) // 3, X.dtype)
         _call(f"wxo_tree_costs_lsdb2_{_sfx(X.dtype)}", "PPlllli", costs, X, m, n, K, N, int(redundant))
+    if np.isnan(costs).any():                      # a position that is constant over the batch: zero range step (see diffentropy)
+        raise ValueError("ArgumentError: range step cannot be zero")
     return costs
 
 
@@ -493,8 +495,13 @@ def tree_costs_bb(X, redundant=False, cost="shannon"):
 
 
 def diffentropy(x):
+    """coefcost(x, DifferentialEntropyCost()) bestbasis_costs.jl:135-155; a constant sample (zero range step) raises like the
+    reference's ``a:0.0:b`` (ArgumentError -> ValueError)"""
     x = np.ascontiguousarray(x)
-    return _call(f"wxo_diffentropy_{_sfx(x.dtype)}", "Pll", x, 1, len(x), restype=C.c_double)
+    v = _call(f"wxo_diffentropy_{_sfx(x.dtype)}", "Pll", x, 1, len(x), restype=C.c_double)
+    if np.isnan(v):
+        raise ValueError("ArgumentError: range step cannot be zero")
+    return v
 
 
 def tree_select(costs, n, m=None, minmax="min"):

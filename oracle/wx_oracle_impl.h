@@ -828,6 +828,9 @@ WXO_API double SUF(diffentropy)(const T *x, long st, long N)
     double delta = ((double)(T)(mx - mn) + sigma) / (double)(npts - 1);
     delta = (double)(T)delta;
     double a = (double)(T)(mn - s * sigma);
+    /* a constant sample gives a zero step: the reference's range construction `a:0.0:b` throws ArgumentError
+     * (bestbasis_costs.jl:146); the restatement reports NaN and its Python wrapper raises */
+    if (!(delta > 0.0) || !isfinite(delta)) return NAN;
     double *cnt = (double *)calloc((size_t)npts, sizeof(double));
     double *y = (double *)calloc((size_t)npts, sizeof(double));
     double dinv = 1.0 / delta;

@@ -86,6 +86,8 @@ def check(rc: int) -> None:
         return
     msg = last_error()
     if rc == WX_EINVAL:
+        if msg.startswith("ArgumentError"):
+            raise ValueError(msg)       # the reference's ArgumentError
         raise AssertionError(msg)       # the reference signals these with @assert -> AssertionError
     if rc == WX_ENOMEM:
         raise MemoryError(msg)

@@ -444,8 +444,10 @@ __global__ void __launch_bounds__(kT) lsdb_density_k(double *dens, const double 
         dens[(i - 1) * szK + e] = y;
         tot += y;
     }
-    const double den = 1.0 / (tot * delta);
-    for (long i = 0; i < npts; ++i) dens[i * szK + e] *= den;
+    // a position that is constant over the batch has delta == 0: the reference's range `a:0.0:b` throws (bestbasis_costs.jl:146).
+    // Poison the column with NaN; wx_lsdb_costs turns a NaN cost into that error.
+    const double den = (delta > 0.0 && isfinite(delta)) ? 1.0 / (tot * delta) : NAN;
+    for (long i = 0; i < npts; ++i) dens[i * szK + e] = (den == den) ? dens[i * szK + e] * den : NAN;
 }
 
 template <typename T>
@@ -474,6 +476,7 @@ __global__ void __launch_bounds__(kT) lsdb_logpdf_part_k(double *part, const dou
         dd_acc(acc, accl, log(pdf));
     }
     dd_norm(acc, accl);
+    if (!(delta > 0.0) || !isfinite(delta)) { acc = NAN; accl = 0.0; }     // zero range step: see lsdb_density_k / wx_lsdb_costs
     double *o = part + ((long)blockIdx.y * 2) * szK + e;
     o[0] = acc; o[szK] = accl;
 }
@@ -528,6 +531,7 @@ __global__ void __launch_bounds__(kL * kH) lsdb_logpdf_smem_k(double *part, cons
     }
     for (; k < k1; ++k) dd_acc(acc, accl, log(pdf_at((double)p[k * szK])));
     dd_norm(acc, accl);
+    if (!(delta > 0.0) || !isfinite(delta)) { acc = NAN; accl = 0.0; }     // zero range step: see lsdb_density_k / wx_lsdb_costs
     double *o = part + ((long)(blockIdx.y * kH + kh) * 2) * szK + e;
     o[0] = acc; o[szK] = accl;
 }
@@ -978,7 +982,12 @@ int wx_lsdb_costs(double *costs_host, const double *logsum, long Ntotal, long m,
     WX_LAUNCHED();
     rc = node_costs_to_host(costs_host, term, m, n, K, redundant, 1.0, 8, s);
     int rc2 = wx_scratch_free(term, s);
-    return rc ? rc : rc2;
+    if (rc || rc2) return rc ? rc : rc2;
+    const long nn = count_nodes(m, K, redundant);
+    for (long i = 0; i < nn; ++i)
+        if (costs_host[i] != costs_host[i])
+            return wx_fail(WX_EINVAL, "ArgumentError: range step cannot be zero (a coefficient position is constant over the batch, bestbasis_costs.jl:146)");
+    return WX_OK;
 }
 
 // bestbasis_treeselection  BestBasis.jl:59-110 + delete_subtree! :128-140 (host)

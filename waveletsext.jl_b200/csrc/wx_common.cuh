@@ -85,6 +85,18 @@ int wx_devinfo(WxDev &d);   // cached per device (thread safe); creates the libr
 int wx_pool_alloc(void **p, size_t bytes, cudaStream_t s);   // stream-ordered allocation from that pool (free: cudaFreeAsync)
 
 // ----------------------------------------------------------------------------------------------
+// Residency tuning of the persistent kernels (wx_runtime.cu).  The write-dominated kernels of this library are sensitive to
+// the number of CTAs resident per SM (concurrent store streams against warps in flight); the optimum moves with filter length,
+// element type and node size (profiles/r2_wpd1d_residency_sweep.jsonl), so the first LARGE launch of a shape measures the
+// candidates on the caller's own data (every candidate launch is a complete, correct run of the kernel) and the choice is
+// cached per (kernel, shape).  Small launches, captured streams and WX_B200_AUTOTUNE=0 use the caller's rule instead.
+// ----------------------------------------------------------------------------------------------
+#include <functional>
+struct WxTuneKey { const void *kernel; long a, b, c, d; };
+int wx_tuned_choice(const WxTuneKey &key, int ncand, const int *cand, int fallback, bool big_enough, cudaStream_t s,
+                    const std::function<int(int)> &launch, int *choice);
+
+// ----------------------------------------------------------------------------------------------
 // device helpers
 // ----------------------------------------------------------------------------------------------
 // periodic wrap of an index that may be negative or exceed the period several times

@@ -40,6 +40,27 @@ __device__ __forceinline__ void wx_tma_store_2d(const CUtensorMap *map, int c0, 
                  "r"(c0), "r"(c1), "r"(wx_smem_u32(smem_src))
                  : "memory");
 }
+// the same with an L2 eviction policy (createpolicy): the packet table is written once and never re-read by this kernel, x is read once
+__device__ __forceinline__ unsigned long long wx_policy_evict_first()
+{
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void wx_tma_load_2d_hint(void *smem_dst, const CUtensorMap *map, int c0, int c1, unsigned long long *bar, unsigned long long pol)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;" ::"r"(
+                     wx_smem_u32(smem_dst)),
+                 "l"(reinterpret_cast<unsigned long long>(map)), "r"(c0), "r"(c1), "r"(wx_smem_u32(bar)), "l"(pol)
+                 : "memory");
+}
+__device__ __forceinline__ void wx_tma_store_2d_hint(const CUtensorMap *map, int c0, int c1, const void *smem_src, unsigned long long pol)
+{
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%1, %2}], [%3], %4;" ::"l"(
+                     reinterpret_cast<unsigned long long>(map)),
+                 "r"(c0), "r"(c1), "r"(wx_smem_u32(smem_src)), "l"(pol)
+                 : "memory");
+}
 __device__ __forceinline__ void wx_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void wx_bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void wx_bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }

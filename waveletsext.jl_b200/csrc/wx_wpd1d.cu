@@ -75,9 +75,10 @@ __global__ void __launch_bounds__(256) wpd1d_fused_k(T *__restrict__ y, const T 
 // Tensor maps view x and y as 2-D arrays of 128-byte rows: coordinates {0, row}.
 template <typename T, int F>
 __global__ void __launch_bounds__(512) wpd1d_tma_k(const __grid_constant__ CUtensorMap mapx, const __grid_constant__ CUtensorMap mapy, long n, int L,
-                                                  int d0, long items, int bufelems, int boxrows, Taps<T> tp)
+                                                  int d0, long items, int bufelems, int boxrows, int l2hint, Taps<T> tp)
 {
     constexpr int RE = 128 / (int)sizeof(T);          // elements per 128-byte row
+    const unsigned long long pol = wx_policy_evict_first();
     extern __shared__ unsigned char wx_smem_raw[];
     __shared__ __align__(8) unsigned long long bar;
     // 1024-byte alignment for SWIZZLE_128B, as an offset from the array so that the accesses stay LDS/STS (not generic LD/ST)
@@ -103,14 +104,18 @@ __global__ void __launch_bounds__(512) wpd1d_tma_k(const __grid_constant__ CUten
             wx_bulk_wait_read0();                                      // stores of the previous item have released smem
             wx_mbar_expect_tx(&bar, (unsigned)(n0 * sizeof(T)));
             for (int bx = 0; bx < nbox; ++bx) {
-                if (d0 == 0) wx_tma_load_2d(buf0 + (long)bx * boxrows * RE, &mapx, 0, (int)(k * sigrows + (long)bx * boxrows), &bar);
+                if (d0 == 0 && l2hint) wx_tma_load_2d_hint(buf0 + (long)bx * boxrows * RE, &mapx, 0, (int)(k * sigrows + (long)bx * boxrows), &bar, pol);
+                else if (d0 == 0) wx_tma_load_2d(buf0 + (long)bx * boxrows * RE, &mapx, 0, (int)(k * sigrows + (long)bx * boxrows), &bar);
                 else         wx_tma_load_2d(buf0 + (long)bx * boxrows * RE, &mapy, 0, (int)(yrow0 + (long)d0 * sigrows + (long)bx * boxrows), &bar);
             }
         }
         wx_mbar_wait(&bar, parity);
         parity ^= 1;
         if (d0 == 0 && tid == 0) {                                     // level 0 = x   (DWT.jl:142)
-            for (int bx = 0; bx < nbox; ++bx) wx_tma_store_2d(&mapy, 0, (int)(yrow0 + (long)bx * boxrows), buf0 + (long)bx * boxrows * RE);
+            for (int bx = 0; bx < nbox; ++bx) {
+                if (l2hint) wx_tma_store_2d_hint(&mapy, 0, (int)(yrow0 + (long)bx * boxrows), buf0 + (long)bx * boxrows * RE, pol);
+                else wx_tma_store_2d(&mapy, 0, (int)(yrow0 + (long)bx * boxrows), buf0 + (long)bx * boxrows * RE);
+            }
             wx_bulk_commit();
         }
 
@@ -124,7 +129,10 @@ __global__ void __launch_bounds__(512) wpd1d_tma_k(const __grid_constant__ CUten
             __syncthreads();
             if (tid == 0) {
                 const long row = yrow0 + (long)(d0 + l + 1) * sigrows;
-                for (int bx = 0; bx < nbox; ++bx) wx_tma_store_2d(&mapy, 0, (int)(row + (long)bx * boxrows), b + (long)bx * boxrows * RE);
+                for (int bx = 0; bx < nbox; ++bx) {
+                    if (l2hint) wx_tma_store_2d_hint(&mapy, 0, (int)(row + (long)bx * boxrows), b + (long)bx * boxrows * RE, pol);
+                    else wx_tma_store_2d(&mapy, 0, (int)(row + (long)bx * boxrows), b + (long)bx * boxrows * RE);
+                }
                 wx_bulk_commit();
             }
             T *t = a; a = b; b = t;
@@ -194,26 +202,50 @@ int wpd1d_launch_tma(T *y, const T *x, long n, int L, long N, int d0, const Taps
     long units = n0 / (2 * C::K);
     int threads = (int)((units + 31) / 32 * 32);
     if (threads < 64) threads = 64;
-    // Resident CTAs per SM.  Shared memory allows three 256-thread CTAs; for the 8-tap filters in Float64 TWO are faster -- measured
-    // on 65536 x 4096, L = 12 (same box, same run): db4 5.31 ms with three CTAs, 4.70 ms with two (0.977 of the measured HBM copy
-    // peak), 4.80 ms with two 512-thread CTAs; haar / db2 / db3 do not care (5.2 ms either way), coif4 and sym8 lose with two
-    // (5.0 -> 5.4 ms, 5.3 -> 6.6 ms) and lose more with 512 threads.  Fewer concurrent store streams per SM suit the DRAM better as
-    // long as two CTAs still cover the FP64 work.  Knobs for re-measuring: WX_B200_WPD1D_THREADS (256 / 512), WX_B200_WPD1D_OCC.
+    // Resident CTAs per SM.  The kernel is write-dominated (L+1 rows out per row in) and the best residency is NOT the maximum:
+    // fewer concurrent store streams suit the DRAM better as long as the resident warps still cover the arithmetic.  Measured
+    // (profiles/r2_wpd1d_residency_sweep.jsonl, 8 filters x 2 element types x n in {1024, 4096}): haar F64 n = 4096 runs 4.63 ms
+    // with ONE CTA per SM against 5.25 ms with three; db4 F64 wants 2, coif4 / sym8 3; n = 1024 wants 3-6, Float32 2-8.  The first
+    // large launch of a shape therefore measures the candidates (wx_tuned_choice); small launches use the warp-count rule below.
+    // Knobs for re-measuring: WX_B200_WPD1D_THREADS (256 / 512), WX_B200_WPD1D_OCC, WX_B200_WPD1D_L2HINT, WX_B200_AUTOTUNE=0.
     const char *tenv = getenv("WX_B200_WPD1D_THREADS");             // read per call so that one process can sweep them
     const char *oenv = getenv("WX_B200_WPD1D_OCC");
+    const char *henv = getenv("WX_B200_WPD1D_L2HINT");
+    const int l2hint = henv ? atoi(henv) : 1;
     if (threads > 256) threads = (tenv && atoi(tenv) == 512 && threads >= 512) ? 512 : 256;
     auto kern = wpd1d_tma_k<T, F>;
     WX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int occ = 0;
-    WX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
-    if (occ < 1) return WX_OK;
-    if (oenv && atoi(oenv) >= 1) { if (atoi(oenv) < occ) occ = atoi(oenv); }
-    else if (F == 8 && sizeof(T) == 8 && occ == 3) occ = 2;            // exactly the measured shape: 32 KB nodes, three CTAs by shared memory
+    int occmax = 0;
+    WX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occmax, kern, threads, smem));
+    if (occmax < 1) return WX_OK;
     const long items = N << d0;
-    long blocks = (long)dv.sms * occ;
-    if (blocks > items) blocks = items;
-    kern<<<(unsigned)blocks, threads, smem, s>>>(mx, my, n, L, d0, items, (int)(bufbytes / sizeof(T)), (int)boxrows, t);
-    WX_LAUNCHED();
+    auto launch = [&](int occ) -> int {
+        long blocks = (long)dv.sms * occ;
+        if (blocks > items) blocks = items;
+        kern<<<(unsigned)blocks, threads, smem, s>>>(mx, my, n, L, d0, items, (int)(bufbytes / sizeof(T)), (int)boxrows, l2hint, t);
+        WX_LAUNCHED();
+        return WX_OK;
+    };
+    int occ;
+    if (oenv && atoi(oenv) >= 1) {
+        occ = atoi(oenv) < occmax ? atoi(oenv) : occmax;
+    } else {
+        // rule: resident warps that cover the arithmetic of an F-tap filter (8 + F in Float64, 10 + 1.5 F in Float32)
+        const double want = sizeof(T) == 8 ? 8.0 + F : 10.0 + 1.5 * F;
+        int rule = (int)(want / (threads / 32) + 0.5);
+        if (rule < 1) rule = 1;
+        if (rule > occmax) rule = occmax;
+        int cand[16], nc = 0;
+        for (int c = 1; c <= occmax && c <= 6; ++c) cand[nc++] = c;
+        if (occmax >= 8) cand[nc++] = 8;
+        if (occmax >= 12) cand[nc++] = 12;
+        if (occmax > 6 && occmax != 8 && occmax != 12) cand[nc++] = occmax;
+        const bool big = items >= 4L * dv.sms * occmax && (double)N * (double)n * (L + 2) * sizeof(T) >= 256e6;
+        rc = wx_tuned_choice(WxTuneKey{(const void *)kern, n0, (long)(L - d0), (long)threads, (long)l2hint}, nc, cand, rule, big, s, launch, &occ);
+        if (rc) return rc;
+    }
+    rc = launch(occ);
+    if (rc) return rc;
     *handled = true;
     return WX_OK;
 }
