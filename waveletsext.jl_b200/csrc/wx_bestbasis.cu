@@ -381,7 +381,8 @@ __global__ void __launch_bounds__(kT) lsdb_hist_k(double *counts, const double *
     long k1 = k0 + kchunk; if (k1 > N) k1 = N;
     for (long k = k0; k < k1; ++k) {
         const double xv = (double)X[k * szK + e];
-        const long ki = (long)floor((xv - a) * dinv + 1.5);          // AverageShiftedHistograms bin rule (1-based)
+        const double tq = (xv - a) * dinv + 1.5;                      // AverageShiftedHistograms bin rule (1-based)
+        const long ki = (tq >= 1.0 && tq < (double)npts + 1.0) ? (long)floor(tq) : 0;
         if (ki >= 1 && ki <= npts) atomicAdd(&counts[(ki - 1) * szK + e], 1.0);
     }
 }
@@ -412,12 +413,14 @@ __global__ void __launch_bounds__(kT) lsdb_hist_smem_k(double *counts, const dou
         for (int u = 0; u < U; ++u) r[u] = __ldcs(p + (k + u) * szK);
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const long ki = (long)floor(((double)r[u] - a) * dinv + 1.5);      // AverageShiftedHistograms bin rule (1-based)
+            const double tq = ((double)r[u] - a) * dinv + 1.5;                 // AverageShiftedHistograms bin rule (1-based)
+            const long ki = (tq >= 1.0 && tq < (double)npts + 1.0) ? (long)floor(tq) : 0;
             if (ki >= 1 && ki <= npts) wx_cnt[(int)(ki - 1) * kT + tid] += 1u;
         }
     }
     for (; k < k1; ++k) {
-        const long ki = (long)floor(((double)p[k * szK] - a) * dinv + 1.5);
+        const double tq = ((double)p[k * szK] - a) * dinv + 1.5;
+        const long ki = (tq >= 1.0 && tq < (double)npts + 1.0) ? (long)floor(tq) : 0;
         if (ki >= 1 && ki <= npts) wx_cnt[(int)(ki - 1) * kT + tid] += 1u;
     }
     for (int i = 0; i < npts; ++i) {
@@ -464,9 +467,12 @@ __global__ void __launch_bounds__(kT) lsdb_logpdf_part_k(double *part, const dou
     double acc = 0.0, accl = 0.0;
     for (long k = k0; k < k1; ++k) {
         const double xv = (double)X[k * szK + e];
-        long i = (long)floor((xv - a) * dinv) + 1;                   // searchsortedlast(rng, x), 1-based
+        const double tq = (xv - a) * dinv;
+        // a sample outside the grid (or NaN, or a degenerate grid) has pdf 0; never feed a NaN / huge quotient to the integer
+        // search below (the conversion of NaN is LONG_MIN on the device: the walk would never end)
+        long i = (tq >= 0.0 && tq < (double)npts) ? (long)floor(tq) + 1 : (tq < 0.0 ? 0 : npts);   // searchsortedlast(rng, x), 1-based
         while (i >= 1 && i <= npts && a + (double)(i - 1) * delta > xv) --i;
-        while (i + 1 <= npts && a + (double)i * delta <= xv) ++i;
+        while (i >= 0 && i + 1 <= npts && a + (double)i * delta <= xv) ++i;
         double pdf = 0.0;
         if (i >= 1 && i < npts) {
             const double g0 = a + (double)(i - 1) * delta, g1 = a + (double)i * delta;
@@ -507,10 +513,11 @@ __global__ void __launch_bounds__(kL * kH) lsdb_logpdf_smem_k(double *part, cons
     const T *p = X + e;
     auto pdf_at = [&](double xv) {
         const double t = (xv - a) * dinv;
-        long i = (long)floor(t) + 1;                                   // searchsortedlast(rng, x), 1-based
+        // outside the grid / NaN / degenerate grid: pdf 0 (the device converts NaN to LONG_MIN: the walk below would never end)
+        long i = (t >= 0.0 && t < (double)npts) ? (long)floor(t) + 1 : (t < 0.0 ? 0 : npts);      // searchsortedlast(rng, x), 1-based
         double g0 = fma((double)(i - 1), delta, a);
         while (i >= 1 && i <= npts && g0 > xv) { --i; g0 = fma((double)(i - 1), delta, a); }
-        while (i + 1 <= npts && fma((double)i, delta, a) <= xv) { ++i; g0 = fma((double)(i - 1), delta, a); }
+        while (i >= 0 && i + 1 <= npts && fma((double)i, delta, a) <= xv) { ++i; g0 = fma((double)(i - 1), delta, a); }
         double pdf = 0.0;
         if (i >= 1 && i < npts) {
             const double y0 = wx_dens[(int)(i - 1) * kL + pos], y1 = wx_dens[(int)i * kL + pos];

@@ -34,11 +34,29 @@ struct RwCfg {
 template <int F, int AC, int WHICH>
 struct RwWin { static constexpr int M0 = AC ? -(F / 2) : (WHICH == 0 ? -1 : -(F - 1)); };
 
+// AC = 2: autocorrelation filters with EXACTLY symmetric taps (checked on the host): P = [rev(b), c, b], Q = [-rev(b), c, -b]
+// (acwt/acwt_utils.jl:27-48), so  w1 = c v0 + s,  w2 = c v0 - s  with  s = sum_j b_j (v[+j] + v[-j]):  F + 2 flops per output
+// pair instead of 4F - 2.  Every tree kernel of this file uses the same form for a given filter, so acwpt == acwpd[:, leaves]
+// (test/transforms.jl:153-154) stays bitwise; the result differs from the tap-by-tap order of acdwt_step! by rounding only.
+template <typename T, int F>
+__device__ __forceinline__ T rw_ac_sym_s(const T *win, const Taps<T> &tp)
+{
+    constexpr int M = (F - 1) / 2;
+    T s = tp.g[M + 1] * (win[M + 1] + win[M - 1]);
+#pragma unroll
+    for (int j = 2; j <= M; ++j) s = fma(tp.g[M + j], win[M + j] + win[M - j], s);
+    return s;
+}
+
 template <typename T, int F, int AC, int WHICH>
 __device__ __forceinline__ T rw_dot(const T *win, const Taps<T> &tp)
 {
     T a;
-    if (AC) {
+    if (AC == 2) {
+        constexpr int M = (F - 1) / 2;
+        const T s = rw_ac_sym_s<T, F>(win, tp);
+        a = fma(tp.g[M], win[M], WHICH == 0 ? s : -s);
+    } else if (AC) {
         a = (WHICH == 0 ? tp.g[0] : tp.h[0]) * win[0];
 #pragma unroll
         for (int j = 1; j < F; ++j) a = fma(WHICH == 0 ? tp.g[j] : tp.h[j], win[j], a);
@@ -89,8 +107,15 @@ __device__ __forceinline__ void rw_pass2(const T *__restrict__ src, T *__restric
         for (int m = 0; m < W; ++m) { win[m] = src[idx]; idx = (idx + D) & mask; }
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-            dst0[base + k * D] = rw_dot<T, F, AC, 0>(&win[k], tp);
-            dst1[(base + (k + SH) * D) & mask] = rw_dot<T, F, AC, 1>(&win[k], tp);
+            if (AC == 2) {                               // both children from one symmetric sum (same operations as rw_dot<.., 2, ..>)
+                constexpr int M = (F - 1) / 2;
+                const T sm = rw_ac_sym_s<T, F>(&win[k], tp);
+                dst0[base + k * D] = fma(tp.g[M], win[k + M], sm);
+                dst1[base + k * D] = fma(tp.g[M], win[k + M], -sm);
+            } else {
+                dst0[base + k * D] = rw_dot<T, F, AC, 0>(&win[k], tp);
+                dst1[(base + (k + SH) * D) & mask] = rw_dot<T, F, AC, 1>(&win[k], tp);
+            }
         }
     }
 }
@@ -345,6 +370,23 @@ int rwpd_plan(T *xw, const T *x, long n, int L, int wpt, long N, const Taps<T> &
     return WX_OK;
 }
 
+// the autocorrelation taps (g = P, h = Q) have the exact symmetric structure the AC = 2 kernels assume
+// ... and the fused kernel covers the WHOLE tree (n >= K * 2^(L-1)): a partially fused tree finishes through the tap-by-tap step
+// kernels, and acwpt (leaves only, not fused in that case) must stay bitwise equal to the leaves of acwpd
+template <typename T>
+bool ac_taps_symmetric(const Taps<T> &t, long n, int L)
+{
+    if (t.F < 3 || (t.F & 1) == 0) return false;
+    if (wx_ilog2l(n) - ((t.F <= 16) ? 4 : 3) + 1 < L) return false;
+    static const bool off = getenv("WX_B200_NO_AC_SYM") != nullptr;          // A-B measurements only
+    if (off) return false;
+    const int M = (t.F - 1) / 2;
+    if (t.h[M] != t.g[M]) return false;
+    for (int j = 1; j <= M; ++j)
+        if (t.g[M + j] != t.g[M - j] || t.h[M + j] != -t.g[M + j] || t.h[M - j] != -t.g[M - j]) return false;
+    return true;
+}
+
 }  // namespace
 
 // Runs the leading `*done` levels of the tree (0 = nothing handled; the caller continues with the per-depth path).
@@ -358,7 +400,9 @@ int wx_rwpd1d_fused(int ac, int wpt, T *xw, const T *x, long n, int L, long N, c
     static const bool off = getenv("WX_B200_NO_FUSED_RWPD") != nullptr;    // debugging / A-B measurements only
     if (off) return WX_OK;
 #define WX_RW_CASE(FF, AA) case FF: return rwpd_plan<T, FF, AA>(xw, x, n, L, wpt, N, t, s, done);
-    if (ac) {
+    if (ac && ac_taps_symmetric(t, n, L)) {
+        switch (t.F) { WX_RW_CASE(3, 2) WX_RW_CASE(7, 2) WX_RW_CASE(11, 2) WX_RW_CASE(15, 2) WX_RW_CASE(19, 2) WX_RW_CASE(23, 2) WX_RW_CASE(31, 2) WX_RW_CASE(39, 2) }
+    } else if (ac) {
         switch (t.F) { WX_RW_CASE(3, 1) WX_RW_CASE(7, 1) WX_RW_CASE(11, 1) WX_RW_CASE(15, 1) WX_RW_CASE(19, 1) WX_RW_CASE(23, 1) WX_RW_CASE(31, 1) WX_RW_CASE(39, 1) }
     } else {
         switch (t.F) { WX_RW_CASE(2, 0) WX_RW_CASE(4, 0) WX_RW_CASE(6, 0) WX_RW_CASE(8, 0) WX_RW_CASE(10, 0) WX_RW_CASE(12, 0) WX_RW_CASE(16, 0) WX_RW_CASE(20, 0) }
@@ -379,7 +423,9 @@ int wx_rdwt1d_fused(int ac, T *xw, const T *x, long n, int L, long N, const Taps
     static const bool off = getenv("WX_B200_NO_FUSED_RWPD") != nullptr;
     if (off) return WX_OK;
 #define WX_RC_CASE(FF, AA) case FF: return rdwt_chain_plan<T, FF, AA>(xw, x, n, L, N, t, s, done);
-    if (ac) {
+    if (ac && ac_taps_symmetric(t, n, L)) {
+        switch (t.F) { WX_RC_CASE(3, 2) WX_RC_CASE(7, 2) WX_RC_CASE(11, 2) WX_RC_CASE(15, 2) WX_RC_CASE(19, 2) WX_RC_CASE(23, 2) WX_RC_CASE(31, 2) WX_RC_CASE(39, 2) }
+    } else if (ac) {
         switch (t.F) { WX_RC_CASE(3, 1) WX_RC_CASE(7, 1) WX_RC_CASE(11, 1) WX_RC_CASE(15, 1) WX_RC_CASE(19, 1) WX_RC_CASE(23, 1) WX_RC_CASE(31, 1) WX_RC_CASE(39, 1) }
     } else {
         switch (t.F) { WX_RC_CASE(2, 0) WX_RC_CASE(4, 0) WX_RC_CASE(6, 0) WX_RC_CASE(8, 0) WX_RC_CASE(10, 0) WX_RC_CASE(12, 0) WX_RC_CASE(16, 0) WX_RC_CASE(20, 0) }
