@@ -45,7 +45,7 @@ def test_golden_steps_gpu(wx, cuda):
 
 
 @pytest.mark.parametrize("dt", [np.float64, np.float32])
-@pytest.mark.parametrize("name", ["haar", "db2", "db4", "coif4", "sym8", "db10", "db3", "db7"])
+@pytest.mark.parametrize("name", ["haar", "db2", "db4", "coif4", "sym8", "db10", "db3", "db7", "db9", "db12", "db11"])
 @pytest.mark.parametrize("n,L", [(4096, 12), (1024, 10), (1024, 4), (64, 6), (8, 3), (16, 0), (96, 5), (24, 3)])
 def test_wpdall_parity(wx, O, cuda, dt, name, n, L):
     wt = wx.wavelet(name)
@@ -136,7 +136,7 @@ def random_tree(n, rng, pr=0.7, maxdepth=None):
 
 
 @pytest.mark.parametrize("dt", [np.float64, np.float32])
-@pytest.mark.parametrize("name", ["haar", "db2", "sym8", "db10"])
+@pytest.mark.parametrize("name", ["haar", "db2", "sym8", "db10", "db7", "db9", "db12"])
 @pytest.mark.parametrize("n", [16, 96, 48, 1024])
 def test_wpt_iwpt_trees_filters_and_lengths(wx, O, cuda, dt, name, n):
     """fused all-level tree kernels: every supported filter length, non power-of-two lengths, random trees"""

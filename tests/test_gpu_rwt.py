@@ -47,7 +47,7 @@ def test_golden_steps_swt_acwt(wx, cuda):
 
 
 @pytest.mark.parametrize("dt", [np.float64, np.float32])
-@pytest.mark.parametrize("name", ["haar", "db4", "coif4"])
+@pytest.mark.parametrize("name", ["haar", "db4", "coif4", "db7", "db9", "db12"])
 @pytest.mark.parametrize("n,L", [(8, 3), (64, 4), (2048, 8), (96, 3)])
 def test_swt_family_1d(wx, O, cuda, dt, name, n, L):
     wt = wx.wavelet(name)
@@ -90,7 +90,7 @@ def test_swt_family_1d(wx, O, cuda, dt, name, n, L):
 
 
 @pytest.mark.parametrize("dt", [np.float64, np.float32])
-@pytest.mark.parametrize("name", ["haar", "db4"])
+@pytest.mark.parametrize("name", ["haar", "db4", "db7", "db9"])
 @pytest.mark.parametrize("n,L", [(8, 3), (64, 4), (2048, 8)])
 def test_acwt_family_1d(wx, O, cuda, dt, name, n, L):
     wt = wx.wavelet(name)

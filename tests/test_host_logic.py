@@ -215,10 +215,10 @@ def test_denoising_host_objects(wx):
 def test_wavelet_only_returns_verified_filters(wx):
     """Wavelets.jl's table filters without a verified copy here raise instead of returning a heuristic root choice"""
     import numpy as np
-    for name in ("haar", "db2", "db4", "db7", "db10", "sym4", "sym8", "coif4"):
+    for name in ("haar", "db2", "db4", "db7", "db10", "db12", "db16", "sym4", "sym8", "coif4"):
         q = wx.wavelet(name).taps
         assert wx.filters.check_orthonormal(q) < 1e-12, name
-    for name in ("sym5", "sym6", "sym7", "sym9", "sym10", "coif2", "coif6", "beyl", "vaid", "batt2", "db11"):
+    for name in ("sym5", "sym6", "sym7", "sym9", "sym10", "coif2", "coif6", "beyl", "vaid", "batt2", "db17"):
         with pytest.raises(ValueError):
             wx.wavelet(name)
     # any other filter crosses as data

@@ -257,6 +257,8 @@ static bool shape_ok(const void *a, const void *b, long n, size_t elt, long N, i
         case 6: { constexpr int FF = 6; CALL; } break;   case 8: { constexpr int FF = 8; CALL; } break;         \
         case 10: { constexpr int FF = 10; CALL; } break; case 12: { constexpr int FF = 12; CALL; } break;       \
         case 16: { constexpr int FF = 16; CALL; } break; case 20: { constexpr int FF = 20; CALL; } break;       \
+        case 14: { constexpr int FF = 14; CALL; } break; case 18: { constexpr int FF = 18; CALL; } break;       \
+        case 24: { constexpr int FF = 24; CALL; } break;                                                        \
         default: break;                                                                                         \
     }
 

@@ -401,11 +401,11 @@ int wx_rwpd1d_fused(int ac, int wpt, T *xw, const T *x, long n, int L, long N, c
     if (off) return WX_OK;
 #define WX_RW_CASE(FF, AA) case FF: return rwpd_plan<T, FF, AA>(xw, x, n, L, wpt, N, t, s, done);
     if (ac && ac_taps_symmetric(t, n, L)) {
-        switch (t.F) { WX_RW_CASE(3, 2) WX_RW_CASE(7, 2) WX_RW_CASE(11, 2) WX_RW_CASE(15, 2) WX_RW_CASE(19, 2) WX_RW_CASE(23, 2) WX_RW_CASE(31, 2) WX_RW_CASE(39, 2) }
+        switch (t.F) { WX_RW_CASE(3, 2) WX_RW_CASE(7, 2) WX_RW_CASE(11, 2) WX_RW_CASE(15, 2) WX_RW_CASE(19, 2) WX_RW_CASE(23, 2) WX_RW_CASE(27, 2) WX_RW_CASE(31, 2) WX_RW_CASE(35, 2) WX_RW_CASE(39, 2) }
     } else if (ac) {
-        switch (t.F) { WX_RW_CASE(3, 1) WX_RW_CASE(7, 1) WX_RW_CASE(11, 1) WX_RW_CASE(15, 1) WX_RW_CASE(19, 1) WX_RW_CASE(23, 1) WX_RW_CASE(31, 1) WX_RW_CASE(39, 1) }
+        switch (t.F) { WX_RW_CASE(3, 1) WX_RW_CASE(7, 1) WX_RW_CASE(11, 1) WX_RW_CASE(15, 1) WX_RW_CASE(19, 1) WX_RW_CASE(23, 1) WX_RW_CASE(27, 1) WX_RW_CASE(31, 1) WX_RW_CASE(35, 1) WX_RW_CASE(39, 1) }
     } else {
-        switch (t.F) { WX_RW_CASE(2, 0) WX_RW_CASE(4, 0) WX_RW_CASE(6, 0) WX_RW_CASE(8, 0) WX_RW_CASE(10, 0) WX_RW_CASE(12, 0) WX_RW_CASE(16, 0) WX_RW_CASE(20, 0) }
+        switch (t.F) { WX_RW_CASE(2, 0) WX_RW_CASE(4, 0) WX_RW_CASE(6, 0) WX_RW_CASE(8, 0) WX_RW_CASE(10, 0) WX_RW_CASE(12, 0) WX_RW_CASE(14, 0) WX_RW_CASE(16, 0) WX_RW_CASE(18, 0) WX_RW_CASE(20, 0) WX_RW_CASE(24, 0) }
     }
 #undef WX_RW_CASE
     return WX_OK;
@@ -424,11 +424,11 @@ int wx_rdwt1d_fused(int ac, T *xw, const T *x, long n, int L, long N, const Taps
     if (off) return WX_OK;
 #define WX_RC_CASE(FF, AA) case FF: return rdwt_chain_plan<T, FF, AA>(xw, x, n, L, N, t, s, done);
     if (ac && ac_taps_symmetric(t, n, L)) {
-        switch (t.F) { WX_RC_CASE(3, 2) WX_RC_CASE(7, 2) WX_RC_CASE(11, 2) WX_RC_CASE(15, 2) WX_RC_CASE(19, 2) WX_RC_CASE(23, 2) WX_RC_CASE(31, 2) WX_RC_CASE(39, 2) }
+        switch (t.F) { WX_RC_CASE(3, 2) WX_RC_CASE(7, 2) WX_RC_CASE(11, 2) WX_RC_CASE(15, 2) WX_RC_CASE(19, 2) WX_RC_CASE(23, 2) WX_RC_CASE(27, 2) WX_RC_CASE(31, 2) WX_RC_CASE(35, 2) WX_RC_CASE(39, 2) }
     } else if (ac) {
-        switch (t.F) { WX_RC_CASE(3, 1) WX_RC_CASE(7, 1) WX_RC_CASE(11, 1) WX_RC_CASE(15, 1) WX_RC_CASE(19, 1) WX_RC_CASE(23, 1) WX_RC_CASE(31, 1) WX_RC_CASE(39, 1) }
+        switch (t.F) { WX_RC_CASE(3, 1) WX_RC_CASE(7, 1) WX_RC_CASE(11, 1) WX_RC_CASE(15, 1) WX_RC_CASE(19, 1) WX_RC_CASE(23, 1) WX_RC_CASE(27, 1) WX_RC_CASE(31, 1) WX_RC_CASE(35, 1) WX_RC_CASE(39, 1) }
     } else {
-        switch (t.F) { WX_RC_CASE(2, 0) WX_RC_CASE(4, 0) WX_RC_CASE(6, 0) WX_RC_CASE(8, 0) WX_RC_CASE(10, 0) WX_RC_CASE(12, 0) WX_RC_CASE(16, 0) WX_RC_CASE(20, 0) }
+        switch (t.F) { WX_RC_CASE(2, 0) WX_RC_CASE(4, 0) WX_RC_CASE(6, 0) WX_RC_CASE(8, 0) WX_RC_CASE(10, 0) WX_RC_CASE(12, 0) WX_RC_CASE(14, 0) WX_RC_CASE(16, 0) WX_RC_CASE(18, 0) WX_RC_CASE(20, 0) WX_RC_CASE(24, 0) }
     }
 #undef WX_RC_CASE
     return WX_OK;

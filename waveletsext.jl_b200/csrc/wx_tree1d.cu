@@ -122,7 +122,7 @@ int wx_tree1d_fused_depth(const T *y, const T *x, long n, int nlev, int F)
     WxDev dv;
     if (wx_devinfo(dv)) return -1;
     constexpr int V = WxVec<T>::N;
-    const bool fusedF = (F == 2 || F == 4 || F == 6 || F == 8 || F == 10 || F == 12 || F == 16 || F == 20);
+    const bool fusedF = (F >= 2 && F <= 20 && F % 2 == 0) || F == 24;
     if (!fusedF || nlev < 1 || n >= (1L << 30) || ((((uintptr_t)y) | ((uintptr_t)x)) & 15) != 0) return -1;
     int d0 = 0;
     while (d0 < nlev && (size_t)2 * (((n >> d0) * sizeof(T) + 127) / 128 * 128) > dv.smem_optin) ++d0;
@@ -138,7 +138,7 @@ int wx_tree1d_fused(bool inverse, bool full, T *y, const T *x, long n, long N, i
                     const unsigned char *ddepth, int Kx, int vecgather, const Taps<T> &t, cudaStream_t s)
 {
 #define WX_TR_CASE(FF) case FF: return launch_f<T, FF>(inverse, full, y, x, n, N, d0, nlev, dtree, ntree, ddepth, Kx, vecgather, t, s);
-    switch (t.F) { WX_TR_CASE(2) WX_TR_CASE(4) WX_TR_CASE(6) WX_TR_CASE(8) WX_TR_CASE(10) WX_TR_CASE(12) WX_TR_CASE(16) WX_TR_CASE(20) }
+    switch (t.F) { WX_TR_CASE(2) WX_TR_CASE(4) WX_TR_CASE(6) WX_TR_CASE(8) WX_TR_CASE(10) WX_TR_CASE(12) WX_TR_CASE(14) WX_TR_CASE(16) WX_TR_CASE(18) WX_TR_CASE(20) WX_TR_CASE(24) }
 #undef WX_TR_CASE
     return wx_fail(WX_EUNSUPPORTED, "tree1d fused: filter length %d", t.F);
 }

@@ -211,7 +211,7 @@ int wpd1d_launch_tma(T *y, const T *x, long n, int L, long N, int d0, const Taps
     const char *tenv = getenv("WX_B200_WPD1D_THREADS");             // read per call so that one process can sweep them
     const char *oenv = getenv("WX_B200_WPD1D_OCC");
     const char *henv = getenv("WX_B200_WPD1D_L2HINT");
-    const int l2hint = henv ? atoi(henv) : 1;
+    const int l2hint = henv ? atoi(henv) : 0;       // evict_first hints on the bulk tensor copies: measured, no effect (profiles/r2_wpd1d_ab.jsonl)
     if (threads > 256) threads = (tenv && atoi(tenv) == 512 && threads >= 512) ? 512 : 256;
     auto kern = wpd1d_tma_k<T, F>;
     WX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -264,7 +264,7 @@ int wpd1d_impl(T *y, const T *x, long n, int L, long N, const double *h, const d
 
     constexpr int V = WxVec<T>::N;
     const bool aligned = (((uintptr_t)y | (uintptr_t)x) & 15) == 0;
-    const bool fusedF = (F == 2 || F == 4 || F == 6 || F == 8 || F == 10 || F == 12 || F == 16 || F == 20);
+    const bool fusedF = (F >= 2 && F <= 20 && F % 2 == 0) || F == 24;      // every even length of Wavelets.jl's tables (dbN, symN, coifN, beyl, vaid)
     // smallest start depth whose node fits the ping-pong buffers
     int d0 = 0;
     while (d0 < L && (size_t)2 * (((n >> d0) * sizeof(T) + 127) / 128 * 128) > dv.smem_optin) ++d0;
@@ -289,7 +289,7 @@ int wpd1d_impl(T *y, const T *x, long n, int L, long N, const double *h, const d
         return wpd1d_launch_fused<T, FF>(y, x, n, L, N, d0, t, s);                                  \
     }
     switch (F) {
-        WX_WPD_CASE(2) WX_WPD_CASE(4) WX_WPD_CASE(6) WX_WPD_CASE(8) WX_WPD_CASE(10) WX_WPD_CASE(12) WX_WPD_CASE(16) WX_WPD_CASE(20)
+        WX_WPD_CASE(2) WX_WPD_CASE(4) WX_WPD_CASE(6) WX_WPD_CASE(8) WX_WPD_CASE(10) WX_WPD_CASE(12) WX_WPD_CASE(14) WX_WPD_CASE(16) WX_WPD_CASE(18) WX_WPD_CASE(20) WX_WPD_CASE(24)
     }
 #undef WX_WPD_CASE
     return wx_fail(WX_EUNSUPPORTED, "unreachable");

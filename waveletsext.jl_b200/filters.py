@@ -170,7 +170,7 @@ WT = _WT()
 
 
 def wavelet(name: str) -> OrthoFilter:
-    """``wavelet(WT.db4)`` -> OrthoFilter.  Supported: haar, db1..db10 (spectral factorisation, the construction Wavelets.jl
+    """``wavelet(WT.db4)`` -> OrthoFilter.  Supported: haar, db1..db16 (spectral factorisation, the construction Wavelets.jl
     itself uses for dbN), sym4, sym8 and coif4 (each checked against a recalled copy of the tabulated filter).  Wavelets.jl's
     other table filters (sym5-7, sym9-10, coif2/6/8, batt*, beyl, vaid) have no verified table in this offline image: they
     raise instead of returning taps that may differ from the reference's by a root choice or a time reversal -- pass the taps
@@ -178,13 +178,13 @@ def wavelet(name: str) -> OrthoFilter:
     name = str(name).lower()
     if name in ("haar", "db1"):
         return OrthoFilter(_daubechies(1), "haar")
-    if name.startswith("db") and name[2:].isdigit() and 1 <= int(name[2:]) <= 10:
+    if name.startswith("db") and name[2:].isdigit() and 1 <= int(name[2:]) <= 16:
         return OrthoFilter(_daubechies(int(name[2:])), name)
     if name in ("sym4", "sym8"):
         return OrthoFilter(_symlet(int(name[3:])), name)
     if name == "coif4":
         return OrthoFilter(_coif4(), name)
-    raise ValueError(f"unknown or unverified wavelet class {name!r}: supported names are haar, db1..db10, sym4, sym8, coif4; "
+    raise ValueError(f"unknown or unverified wavelet class {name!r}: supported names are haar, db1..db16, sym4, sym8, coif4; "
                      f"for any other filter pass its qmf taps as data: OrthoFilter(taps, name)")
 
 
