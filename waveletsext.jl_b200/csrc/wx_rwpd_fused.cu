@@ -313,15 +313,29 @@ int rwpd_launch(T *xw, const T *x, long n, long ncols, int dstart, int dend, int
     if (threads > 256) threads = 256;
     auto kern = rwpd_dfs_k<T, F, AC>;
     WX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int occ = 0;
-    WX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
-    if (occ < 1) return wx_fail(WX_EUNSUPPORTED, "rwpd fused kernel does not fit (smem %zu)", smem);
+    int occmax = 0;
+    WX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occmax, kern, threads, smem));
+    if (occmax < 1) return wx_fail(WX_EUNSUPPORTED, "rwpd fused kernel does not fit (smem %zu)", smem);
     const long items = N << dstart;
-    long blocks = (long)dv.sms * occ;
-    if (blocks > items) blocks = items;
-    kern<<<(unsigned)blocks, threads, smem, s>>>(xw, x, (int)n, ncols, dstart, dend, L, wpt, chain, items, t);
-    WX_LAUNCHED();
-    return WX_OK;
+    auto launch = [&](int occ) -> int {
+        long blocks = (long)dv.sms * occ;
+        if (blocks > items) blocks = items;
+        kern<<<(unsigned)blocks, threads, smem, s>>>(xw, x, (int)n, ncols, dstart, dend, L, wpt, chain, items, t);
+        WX_LAUNCHED();
+        return WX_OK;
+    };
+    // resident CTAs per SM: a pure store stream like wpd1d_tma_k (see wx_wpd1d.cu) -- the first large launch of a shape measures
+    // the candidates, small launches take the maximum
+    int cand[8], nc = 0, occ = occmax;
+    for (int c = 1; c <= occmax && c <= 6; ++c) cand[nc++] = c;
+    const char *oenv = getenv("WX_B200_RWPD_OCC");
+    if (oenv && atoi(oenv) >= 1) occ = atoi(oenv) < occmax ? atoi(oenv) : occmax;
+    else {
+        const bool big = items >= 4L * dv.sms * occmax && (double)N * (double)n * (double)(1L << (dend + (wpt ? 0 : 1))) * sizeof(T) >= 256e6;
+        rc = wx_tuned_choice(WxTuneKey{(const void *)kern, n, (long)dstart * 64 + dend, (long)wpt * 2 + chain, (long)threads}, nc, cand, occmax, big, s, launch, &occ);
+        if (rc) return rc;
+    }
+    return launch(occ);
 }
 
 template <typename T, int F, int AC>

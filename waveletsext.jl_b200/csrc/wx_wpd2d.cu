@@ -561,9 +561,29 @@ int wpd2d_haar_run(T *y, const T *x, long m, long n, int L, long N, const Taps<T
     const long tiles_r = m >> lr, tiles = tiles_r * (n >> lc);
     if (tiles * N >= (1L << 31)) return WX_OK;
     auto kern = wpd2d_haar_k<T>;
-    WX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<(unsigned)(tiles * N), kT2, smem, s>>>(y, x, (int)m, (int)n, L, lr, lc, make_div32(tiles), make_div32(tiles_r), t);
-    WX_LAUNCHED();
+    // resident CTAs per SM: one CTA per tile (hardware scheduled), so the residency is capped by asking for more dynamic shared
+    // memory than the two buffers need.  Like the other write-dominated kernels the best residency is measured by the first
+    // large launch of a shape (wx_tuned_choice); small launches take what fits.
+    const int occfit = (int)(dv.smem_optin / (smem + 1024));
+    auto launch = [&](int occ) -> int {
+        size_t ask = smem;
+        if (occ >= 1 && occ < occfit) { ask = (dv.smem_optin / (size_t)occ - 1024) & ~(size_t)127; if (ask < smem) ask = smem; }
+        WX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ask));
+        kern<<<(unsigned)(tiles * N), kT2, ask, s>>>(y, x, (int)m, (int)n, L, lr, lc, make_div32(tiles), make_div32(tiles_r), t);
+        WX_LAUNCHED();
+        return WX_OK;
+    };
+    int cand[8], nc = 0, occ = occfit;
+    for (int c = 1; c <= occfit && c <= 6; ++c) cand[nc++] = c;
+    const char *oenv = getenv("WX_B200_HAAR2D_OCC");
+    if (oenv && atoi(oenv) >= 1) occ = atoi(oenv);
+    else {
+        const bool big = tiles * N >= 8L * dv.sms * (occfit > 0 ? occfit : 1) && (double)m * (double)n * (double)N * (L + 2) * sizeof(T) >= 256e6;
+        rc = wx_tuned_choice(WxTuneKey{(const void *)kern, m, n, (long)L, (long)lr * 64 + lc}, nc, cand, occfit, big, s, launch, &occ);
+        if (rc) return rc;
+    }
+    rc = launch(occ);
+    if (rc) return rc;
     *done = true;
     return WX_OK;
 }
