@@ -359,6 +359,7 @@ static LsdbGrid lsdb_grid(long N)
 
 // per-position grid origin a and step delta from the reduced statistics  (bestbasis_costs.jl:143-147)
 // stats rows: 0 shift c, 1/2 sum(x-c) hi/lo, 3/4 sum((x-c)^2) hi/lo, 5 min, 6 max   (hi = the correctly rounded sum)
+template <bool SAFE = true>
 __device__ __forceinline__ void lsdb_axis(const double *stats, long szK, long e, double Ntot, long npts, double &a, double &delta)
 {
     const double s1 = stats[szK + e], s2 = stats[3 * szK + e], mn = stats[5 * szK + e], mx = stats[6 * szK + e];
@@ -367,6 +368,11 @@ __device__ __forceinline__ void lsdb_axis(const double *stats, long szK, long e,
     const double sg = sqrt(var);
     delta = (mx - mn + sg) / (double)(npts - 1);
     a = mn - 0.5 * sg;
+    // A position that is constant over the batch has delta == 0 (the reference's range `a:0.0:b` throws, bestbasis_costs.jl:146).
+    // The streaming kernels must still terminate on it (0 * inf = NaN converts to LONG_MIN on the device and the grid walk of the
+    // log-pdf pass would never end), so they see a unit step there; lsdb_density_k tests the RAW step, poisons the column's density
+    // with NaN, the cost of every node that contains the position becomes NaN and wx_lsdb_costs turns that into the error.
+    if (SAFE && (!(delta > 0.0) || !isfinite(delta))) delta = 1.0;
 }
 
 template <typename T>
@@ -381,8 +387,7 @@ __global__ void __launch_bounds__(kT) lsdb_hist_k(double *counts, const double *
     long k1 = k0 + kchunk; if (k1 > N) k1 = N;
     for (long k = k0; k < k1; ++k) {
         const double xv = (double)X[k * szK + e];
-        const double tq = (xv - a) * dinv + 1.5;                      // AverageShiftedHistograms bin rule (1-based)
-        const long ki = (tq >= 1.0 && tq < (double)npts + 1.0) ? (long)floor(tq) : 0;
+        const long ki = (long)floor((xv - a) * dinv + 1.5);          // AverageShiftedHistograms bin rule (1-based)
         if (ki >= 1 && ki <= npts) atomicAdd(&counts[(ki - 1) * szK + e], 1.0);
     }
 }
@@ -413,14 +418,12 @@ __global__ void __launch_bounds__(kT) lsdb_hist_smem_k(double *counts, const dou
         for (int u = 0; u < U; ++u) r[u] = __ldcs(p + (k + u) * szK);
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const double tq = ((double)r[u] - a) * dinv + 1.5;                 // AverageShiftedHistograms bin rule (1-based)
-            const long ki = (tq >= 1.0 && tq < (double)npts + 1.0) ? (long)floor(tq) : 0;
+            const long ki = (long)floor(((double)r[u] - a) * dinv + 1.5);      // AverageShiftedHistograms bin rule (1-based)
             if (ki >= 1 && ki <= npts) wx_cnt[(int)(ki - 1) * kT + tid] += 1u;
         }
     }
     for (; k < k1; ++k) {
-        const double tq = ((double)p[k * szK] - a) * dinv + 1.5;
-        const long ki = (tq >= 1.0 && tq < (double)npts + 1.0) ? (long)floor(tq) : 0;
+        const long ki = (long)floor(((double)p[k * szK] - a) * dinv + 1.5);
         if (ki >= 1 && ki <= npts) wx_cnt[(int)(ki - 1) * kT + tid] += 1u;
     }
     for (int i = 0; i < npts; ++i) {
@@ -435,7 +438,7 @@ __global__ void __launch_bounds__(kT) lsdb_density_k(double *dens, const double 
     const long e = (long)blockIdx.x * kT + threadIdx.x;
     if (e >= szK) return;
     double a, delta;
-    lsdb_axis(stats, szK, e, Ntot, npts, a, delta);
+    lsdb_axis<false>(stats, szK, e, Ntot, npts, a, delta);
     double tot = 0.0;
     for (long i = 1; i <= npts; ++i) {
         double y = 0.0;
@@ -467,12 +470,9 @@ __global__ void __launch_bounds__(kT) lsdb_logpdf_part_k(double *part, const dou
     double acc = 0.0, accl = 0.0;
     for (long k = k0; k < k1; ++k) {
         const double xv = (double)X[k * szK + e];
-        const double tq = (xv - a) * dinv;
-        // a sample outside the grid (or NaN, or a degenerate grid) has pdf 0; never feed a NaN / huge quotient to the integer
-        // search below (the conversion of NaN is LONG_MIN on the device: the walk would never end)
-        long i = (tq >= 0.0 && tq < (double)npts) ? (long)floor(tq) + 1 : (tq < 0.0 ? 0 : npts);   // searchsortedlast(rng, x), 1-based
+        long i = (long)floor((xv - a) * dinv) + 1;                   // searchsortedlast(rng, x), 1-based
         while (i >= 1 && i <= npts && a + (double)(i - 1) * delta > xv) --i;
-        while (i >= 0 && i + 1 <= npts && a + (double)i * delta <= xv) ++i;
+        while (i + 1 <= npts && a + (double)i * delta <= xv) ++i;
         double pdf = 0.0;
         if (i >= 1 && i < npts) {
             const double g0 = a + (double)(i - 1) * delta, g1 = a + (double)i * delta;
@@ -482,7 +482,6 @@ __global__ void __launch_bounds__(kT) lsdb_logpdf_part_k(double *part, const dou
         dd_acc(acc, accl, log(pdf));
     }
     dd_norm(acc, accl);
-    if (!(delta > 0.0) || !isfinite(delta)) { acc = NAN; accl = 0.0; }     // zero range step: see lsdb_density_k / wx_lsdb_costs
     double *o = part + ((long)blockIdx.y * 2) * szK + e;
     o[0] = acc; o[szK] = accl;
 }
@@ -513,11 +512,10 @@ __global__ void __launch_bounds__(kL * kH) lsdb_logpdf_smem_k(double *part, cons
     const T *p = X + e;
     auto pdf_at = [&](double xv) {
         const double t = (xv - a) * dinv;
-        // outside the grid / NaN / degenerate grid: pdf 0 (the device converts NaN to LONG_MIN: the walk below would never end)
-        long i = (t >= 0.0 && t < (double)npts) ? (long)floor(t) + 1 : (t < 0.0 ? 0 : npts);      // searchsortedlast(rng, x), 1-based
+        long i = (long)floor(t) + 1;                                   // searchsortedlast(rng, x), 1-based
         double g0 = fma((double)(i - 1), delta, a);
         while (i >= 1 && i <= npts && g0 > xv) { --i; g0 = fma((double)(i - 1), delta, a); }
-        while (i >= 0 && i + 1 <= npts && fma((double)i, delta, a) <= xv) { ++i; g0 = fma((double)(i - 1), delta, a); }
+        while (i + 1 <= npts && fma((double)i, delta, a) <= xv) { ++i; g0 = fma((double)(i - 1), delta, a); }
         double pdf = 0.0;
         if (i >= 1 && i < npts) {
             const double y0 = wx_dens[(int)(i - 1) * kL + pos], y1 = wx_dens[(int)i * kL + pos];
@@ -538,7 +536,6 @@ __global__ void __launch_bounds__(kL * kH) lsdb_logpdf_smem_k(double *part, cons
     }
     for (; k < k1; ++k) dd_acc(acc, accl, log(pdf_at((double)p[k * szK])));
     dd_norm(acc, accl);
-    if (!(delta > 0.0) || !isfinite(delta)) { acc = NAN; accl = 0.0; }     // zero range step: see lsdb_density_k / wx_lsdb_costs
     double *o = part + ((long)(blockIdx.y * kH + kh) * 2) * szK + e;
     o[0] = acc; o[szK] = accl;
 }

@@ -75,7 +75,14 @@ __device__ __forceinline__ void wpd_wide_level(const T *__restrict__ src, T *__r
     const int half = p >> 1;
     const int units = n0 / (2 * K);
     const int lgh = 31 - __clz(half);
-    for (int u = tid; u < units; u += nthreads) {
+    // Lanes -> units.  A unit reads the 4 chunks it owns plus the first chunks of the NEXT unit (the filter's look-ahead) and
+    // stores its detail outputs S/V chunks ahead.  With the 128-byte XOR swizzle, 8 consecutive units are conflict free on
+    // their own chunks but not on the neighbour's (units u+1 .. u+8 straddle two swizzle periods): ncu showed 6 instead of 4
+    // wavefronts on half of the window loads and 7 on the detail stores.  Letting a quarter warp take the EVEN units of a
+    // group of 16 and the next quarter the ODD ones makes both the own and the neighbour's chunks hit 8 distinct bank groups.
+    const bool perm16 = (units & 15) == 0;
+    for (int u0 = tid; u0 < units; u0 += nthreads) {
+        const int u = perm16 ? ((u0 & ~15) | ((u0 & 7) << 1) | ((u0 >> 3) & 1)) : u0;
         const int gi = u * K;
         const int j = POW2 ? (gi >> lgh) : (gi / half);
         const int i = gi - j * half;

@@ -235,6 +235,7 @@ int wpd1d_launch_tma(T *y, const T *x, long n, int L, long N, int d0, const Taps
         int rule = (int)(want / (threads / 32) + 0.5);
         if (rule < 1) rule = 1;
         if (rule > occmax) rule = occmax;
+        if (items <= (long)dv.sms * occmax) rule = occmax;      // a launch of at most one wave is latency bound: everything resident
         int cand[16], nc = 0;
         for (int c = 1; c <= occmax && c <= 6; ++c) cand[nc++] = c;
         if (occmax >= 8) cand[nc++] = 8;
