@@ -47,6 +47,16 @@ def report(name, ms, launches, alg_bytes, units, unit_name, extra=None):
     print(json.dumps(out), flush=True)
 
 
+def fp64_bound(fmas):
+    """time of `fmas` double-precision FMAs at the B200's FP64 pipe rate (64 DFMA per clock per SM, 148 SMs, max SM clock of
+    MEASURED_PEAKS.json): the second roofline of the long filters in Float64"""
+    try:
+        mhz = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["sm_max_mhz"])
+    except Exception:
+        mhz = 1965.0
+    return fmas / (64.0 * 148.0 * mhz * 1e6) * 1e3
+
+
 def cpu_rate(fn, units, budget_s=2.0):
     """units per second of the CPU port: repeat fn() (which processes `units` samples / pixels) for about budget_s seconds"""
     import time
@@ -114,7 +124,11 @@ def main():
                 y = torch.empty((N, L + 1, n), dtype=dt, device=dev)
                 if want(f"wpdall_{tag}_{wname}"):
                     ms, nl = timeit(lambda: wx.dwt._wpd_batch(x, wt, L, y))
-                    report(f"wpdall_{tag}_{wname}", ms, nl, es * n * N * (L + 2), n * N, "GSamples_per_s")
+                    extra = None
+                    if es == 8:          # F FMAs per sample and level for each of the two filters = F*L*n*N in total... per OUTPUT pair 2F, i.e. F per sample
+                        fb = fp64_bound(float(len(wt.taps)) * L * n * N)
+                        extra = {"fp64_pipe_bound_ms": round(fb, 3), "frac_of_fp64_bound": round(fb / ms, 4)}
+                    report(f"wpdall_{tag}_{wname}", ms, nl, es * n * N * (L + 2), n * N, "GSamples_per_s", extra)
                 if want(f"iwptall_{tag}_{wname}"):
                     wx.dwt._wpd_batch(x, wt, L, y)
                     leaves = y[:, L].contiguous()
@@ -123,7 +137,11 @@ def main():
                     tree = wx.maketree(n, L, "full")
                     ms, nl = timeit(lambda: wx.dwt._tree_batch("iwpt", leaves, wt, tree, out))
                     err = float((out - x).abs().max() / x.abs().max())
-                    report(f"iwptall_{tag}_{wname}", ms, nl, 2 * es * n * N, n * N, "GSamples_per_s", {"roundtrip_relerr": err})
+                    extra = {"roundtrip_relerr": err}
+                    if es == 8:
+                        fb = fp64_bound(float(len(wt.taps)) * L * n * N)
+                        extra.update({"fp64_pipe_bound_ms": round(fb, 3), "frac_of_fp64_bound": round(fb / ms, 4)})
+                    report(f"iwptall_{tag}_{wname}", ms, nl, 2 * es * n * N, n * N, "GSamples_per_s", extra)
                     del leaves, out
                 del x
                 torch.cuda.empty_cache()

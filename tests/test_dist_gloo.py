@@ -70,6 +70,13 @@ def _worker(rank, world, port, q):
         g = [torch.empty_like(tot) for _ in range(world)]
         dist.all_gather(g, tot)
         assert torch.equal(g[0], g[1])                       # bitwise identical on every rank
+        # the library's own communicator is bootstrapped over this group: rank 0's NCCL unique id reaches every rank unchanged
+        # (wx_comm_init_rank itself needs a GPU per rank: tests/mgpu_check.py)
+        ident = wx.dist.exchange_unique_id()
+        assert isinstance(ident, bytes) and len(ident) == 128 and any(ident)
+        both = [None] * world
+        dist.all_gather_object(both, ident)
+        assert both[0] == both[1]
         # denoiseall's bestTH: per-signal noise levels of unequal shards, gathered in rank order
         sig = np.arange(lo, hi, dtype=np.float64) * 0.5
         allsig = wx.dist.allgather_host_vector(sig)

@@ -11,7 +11,9 @@ struct WpdCfg {
     static constexpr int V = WxVec<T>::N;                              // elements per 16 B chunk
     // output pairs per window.  K = 4V (thread stride of one 128-byte row, fully conflict-free window loads) was measured in
     // round 1: same speed within noise (the kernel is HBM-bound, 5.21 vs 5.13 ms) at 78 instead of 54 registers -- kept at 2V.
-    static constexpr int K = 2 * V;
+    // Long filters (14+ taps) take 4V: the window re-reads (2S + 2K) / K samples per output pair, 3.0 with K = 2V against 2.0 with
+    // K = 4V for 16 taps -- they are bound by the shared-memory and FP64 pipes together, not by HBM alone.
+    static constexpr int K = (F >= 14 ? 4 : 2) * V;
     static constexpr int S = (((F - 2) / 2) + V - 1) / V * V;          // high-pass look-ahead (multiple of V)
     static constexpr int W = 2 * S + 2 * K;                            // window length (elements)
 };
@@ -80,7 +82,7 @@ __device__ __forceinline__ void wpd_wide_level(const T *__restrict__ src, T *__r
     // their own chunks but not on the neighbour's (units u+1 .. u+8 straddle two swizzle periods): ncu showed 6 instead of 4
     // wavefronts on half of the window loads and 7 on the detail stores.  Letting a quarter warp take the EVEN units of a
     // group of 16 and the next quarter the ODD ones makes both the own and the neighbour's chunks hit 8 distinct bank groups.
-    const bool perm16 = (units & 15) == 0;
+    const bool perm16 = (2 * K / V == 4) && (units & 15) == 0;          // units of 8 chunks are conflict free in lane order
     for (int u0 = tid; u0 < units; u0 += nthreads) {
         const int u = perm16 ? ((u0 & ~15) | ((u0 & 7) << 1) | ((u0 >> 3) & 1)) : u0;
         const int gi = u * K;

@@ -9,7 +9,7 @@ from __future__ import annotations
 import torch
 import torch.distributed as dist
 
-__all__ = ["comm", "destroy_comms", "shard_range", "shard", "is_dist", "rank", "world_size", "allreduce_sum", "allreduce_min", "allreduce_max",
+__all__ = ["comm", "destroy_comms", "exchange_unique_id", "shard_range", "shard", "is_dist", "rank", "world_size", "allreduce_sum", "allreduce_min", "allreduce_max",
            "total_count", "broadcast_from_first", "allgather_parts", "dd_sum_host"]
 
 
@@ -29,17 +29,27 @@ def comm(device, group=None):
     key = (id(group) if group is not None else 0, device.index)
     c = _COMMS.get(key)
     if c is None:
-        ident = [None]
-        if rank(group) == 0:
-            buf = (C.c_ubyte * 128)()
-            _lib.call("wx_comm_unique_id", buf)
-            ident[0] = bytes(buf)
-        dist.broadcast_object_list(ident, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        ident = exchange_unique_id(group)
         h = C.c_void_p()
         with torch.cuda.device(device):
-            _lib.call("wx_comm_init_rank", C.byref(h), ident[0], rank(group), world_size(group))
+            _lib.call("wx_comm_init_rank", C.byref(h), ident, rank(group), world_size(group))
         c = _COMMS[key] = h.value
     return c
+
+
+def exchange_unique_id(group=None) -> bytes:
+    """rank 0 of the group asks libwx_b200 for an NCCL unique id (``wx_comm_unique_id``, 128 bytes) and every rank receives it
+    over the existing process group (any backend).  Collective."""
+    import ctypes as C
+    from . import _lib
+    ident = [None]
+    if rank(group) == 0:
+        buf = (C.c_ubyte * 128)()
+        _lib.call("wx_comm_unique_id", buf)
+        ident[0] = bytes(buf)
+    dist.broadcast_object_list(ident, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    assert isinstance(ident[0], bytes) and len(ident[0]) == 128
+    return ident[0]
 
 
 def destroy_comms() -> None:
