@@ -36,13 +36,13 @@ __host__ __device__ constexpr int wx_ld_odd(int rows) { return rows | 1; }
 // TRC > 0: tile edge known at compile time (tr = tc = TRC): index arithmetic folds to shifts / immediates and the column pass
 // slides a register window down each column (KSEG pairs per thread, lanes across columns).
 // ---------------------------------------------------------------------------------------------------------
-template <typename T, int F, int TRC>
-__global__ void __launch_bounds__(kT2, 3) wpd2d_tile_k(T *__restrict__ y, const T *__restrict__ x, int m, int n, int L, int d, int tr_, int tc_,
+template <typename T, int F, int TRC, int TCC = TRC, int MINB = 3>
+__global__ void __launch_bounds__(kT2, MINB) wpd2d_tile_k(T *__restrict__ y, const T *__restrict__ x, int m, int n, int L, int d, int tr_, int tc_,
                                                       Div32 drowtiles, Div32 dtiles_r, Div32 dtiles_c, Div32 dgx, long ntiles, Taps<T> tp)
 {
-    const int tr = TRC > 0 ? TRC : tr_, tc = TRC > 0 ? TRC : tc_;
+    const int tr = TRC > 0 ? TRC : tr_, tc = TRC > 0 ? TCC : tc_;
     using P2 = typename Pair<T>::type;
-    constexpr int S = (F - 2) / 2, KROW = wx_krow(F);
+    constexpr int S = (F - 2) / 2, KROW = (TRC > 0 && TCC == 16) ? 4 : wx_krow(F);      // narrow tiles: 4 column groups keep all 256 threads busy
     extern __shared__ __align__(16) unsigned char wx_2d_smem[];
     const int PR = 2 * tr + F - 2, PC = 2 * tc + F - 2, R2 = 2 * tr;
     const int LDP = TRC > 0 ? wx_ld_pairs(PR) : PR + 2 * (tr & 1);      // generic shape: odd tiles padded (see host)
@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(kT2, 3) wpd2d_tile_k(T *__restrict__ y, const 
     if (TRC > 0 && TRC % KSEG == 0) {
         // lanes walk the columns (pair loads, conflict free by the choice of LDP); a thread slides one window of
         // 2*KSEG+F-2 samples down KSEG output pairs of its column
-        constexpr int PCc = 2 * TRC + F - 2, NSEG = (TRC > 0 ? TRC : KSEG) / KSEG, W = 2 * KSEG + F - 2;
+        constexpr int PCc = 2 * TCC + F - 2, NSEG = (TRC > 0 ? TRC : KSEG) / KSEG, W = 2 * KSEG + F - 2;
         for (int t = tid; t < PCc * NSEG; t += kT2) {
             const int sg = t / PCc, b = t - sg * PCc, il0 = sg * KSEG;
             const T *src = P + b * LDP + 2 * il0;
@@ -607,9 +607,15 @@ int wpd2d_run_chunk(T *y, const T *x, long m, long n, int L, long N, const Taps<
     const int cap = (env && atoi(env) >= 1 && atoi(env) <= 32) ? atoi(env) : 32;     // the kernel maps one lane per row pair: tr <= 32
     for (int d = 0; d < db; ++d) {
         const long hr = (m >> d) / 2, hc = (n >> d) / 2;
-        const int tr = largest_divisor_le(hr, cap), tc = largest_divisor_le(hc, cap);
+        // Narrow tiles (32 x 16, knob WX_B200_WPD2D_NARROW): 41 KB instead of 76 KB of shared memory and a 64-register build, i.e. up
+        // to five resident CTAs instead of three for the latency-bound tile pass, at the price of a wider relative halo
+        static const char *nenv = getenv("WX_B200_WPD2D_NARROW");
+        const int narrow = nenv ? atoi(nenv) : 0;
+        const int tr = largest_divisor_le(hr, cap);
+        int tc = largest_divisor_le(hc, cap);
+        if (narrow && tr == 32 && tc == 32) tc = 16;
         const int PR = 2 * tr + F - 2, PC = 2 * tc + F - 2;
-        const bool shaped = (tr == 32 && tc == 32);          // the compile-time-shaped instantiation (padded leading dimensions)
+        const bool shaped = (tr == 32 && (tc == 32 || tc == 16));          // the compile-time-shaped instantiations (padded leading dimensions)
         const size_t smem = shaped ? ((size_t)wx_ld_pairs(PR) * PC + (size_t)wx_ld_odd(2 * tr) * PC) * sizeof(T)
                                    : ((size_t)(PR + 2 * (tr & 1)) * PC + (size_t)2 * tr * (PC + 2 * (tc & 1))) * sizeof(T);
         if (smem > dv.smem_optin) return wx_fail(WX_EUNSUPPORTED, "wpd 2-D tile does not fit shared memory");
@@ -623,7 +629,11 @@ int wpd2d_run_chunk(T *y, const T *x, long m, long n, int L, long N, const Taps<
         static const char *penv = getenv("WX_B200_WPD2D_PERSIST");
         const int per_sm = penv ? atoi(penv) : 0;
         const long ctas = per_sm > 0 && ntiles > (long)dv.sms * per_sm ? (long)dv.sms * per_sm : ntiles;
-        if (tr == 32 && tc == 32) {
+        if (tr == 32 && tc == 16) {
+            auto kern = wpd2d_tile_k<T, F, 32, 16, 4>;
+            WX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<(unsigned)ctas, kT2, smem, s>>>(y, d == 0 ? x : nullptr, (int)m, (int)n, L, d, tr, tc, drt, dtr, dtc, dgx, ntiles, t);
+        } else if (tr == 32 && tc == 32) {
             auto kern = wpd2d_tile_k<T, F, 32>;
             WX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             kern<<<(unsigned)ctas, kT2, smem, s>>>(y, d == 0 ? x : nullptr, (int)m, (int)n, L, d, tr, tc, drt, dtr, dtc, dgx, ntiles, t);
