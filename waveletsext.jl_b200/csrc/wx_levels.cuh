@@ -6,14 +6,16 @@
 #pragma once
 #include "wx_common.cuh"
 
-template <typename T, int F>
+template <typename T, int F, int KM = 2>
 struct WpdCfg {
     static constexpr int V = WxVec<T>::N;                              // elements per 16 B chunk
     // output pairs per window.  K = 4V (thread stride of one 128-byte row, fully conflict-free window loads) was measured in
     // round 1: same speed within noise (the kernel is HBM-bound, 5.21 vs 5.13 ms) at 78 instead of 54 registers -- kept at 2V.
-    // Long filters (14+ taps) take 4V: the window re-reads (2S + 2K) / K samples per output pair, 3.0 with K = 2V against 2.0 with
-    // K = 4V for 16 taps -- they are bound by the shared-memory and FP64 pipes together, not by HBM alone.
-    static constexpr int K = (F >= 14 ? 4 : 2) * V;
+    // KM = 4 (chosen by the wpdall launcher for 14+ taps on nodes long enough to keep the CTA busy): the window re-reads
+    // (2S + 2K) / K samples per output pair, 3.0 with K = 2V against 2.0 with K = 4V for 16 taps -- long filters are bound by the
+    // shared-memory and FP64 pipes together, not by HBM alone.  Measured (profiles/r2_k4v_threshold.jsonl): sym8 F64 n = 4096
+    // 5.9 -> 5.4 ms, F32 2.67 -> 2.50 ms; 10-12 taps lose, and so do short nodes (F32 n = 1024: 32 units for a 64-thread CTA).
+    static constexpr int K = KM * V;
     static constexpr int S = (((F - 2) / 2) + V - 1) / V * V;          // high-pass look-ahead (multiple of V)
     static constexpr int W = 2 * S + 2 * K;                            // window length (elements)
 };
@@ -67,11 +69,11 @@ __device__ __forceinline__ int wx_swz_group(int e)
 }
 
 // ---- wide level: node half-length is a multiple of K -------------------------------------------------
-template <typename T, int F, bool POW2, bool GST, bool TREE = false>
+template <typename T, int F, bool POW2, bool GST, bool TREE = false, int KM = 2>
 __device__ __forceinline__ void wpd_wide_level(const T *__restrict__ src, T *__restrict__ dst, T *__restrict__ grow, int n0, int p,
                                                bool last, const Taps<T> &tp, int tid, int nthreads, TreeMask tmk = TreeMask{nullptr, 0})
 {
-    using C = WpdCfg<T, F>;
+    using C = WpdCfg<T, F, KM>;
     using VT = typename WxVec<T>::type;
     constexpr int V = C::V, K = C::K, S = C::S, W = C::W;
     const int half = p >> 1;
@@ -205,17 +207,17 @@ __device__ __forceinline__ void wpd_generic_level(const T *__restrict__ src, T *
 }
 
 // one decomposition level of every node of the staged signal: picks the wide / small / generic path
-template <typename T, int F, bool GST, bool TREE = false>
+template <typename T, int F, bool GST, bool TREE = false, int KM = 2>
 __device__ __forceinline__ void wpd_level(const T *__restrict__ a, T *__restrict__ b, T *__restrict__ grow, int n0, int p, bool last,
                                           const Taps<T> &tp, int tid, int nthreads, TreeMask tmk = TreeMask{nullptr, 0})
 {
-    using C = WpdCfg<T, F>;
+    using C = WpdCfg<T, F, KM>;
     constexpr int V = C::V, K = C::K;
     const int half = p >> 1;
     const bool pow2 = (p & (p - 1)) == 0;
     if (half % K == 0) {
-        if (pow2) wpd_wide_level<T, F, true, GST, TREE>(a, b, grow, n0, p, last, tp, tid, nthreads, tmk);
-        else      wpd_wide_level<T, F, false, GST, TREE>(a, b, grow, n0, p, last, tp, tid, nthreads, tmk);
+        if (pow2) wpd_wide_level<T, F, true, GST, TREE, KM>(a, b, grow, n0, p, last, tp, tid, nthreads, tmk);
+        else      wpd_wide_level<T, F, false, GST, TREE, KM>(a, b, grow, n0, p, last, tp, tid, nthreads, tmk);
     } else if (p == 2 && n0 % (V > 2 ? V : 2) == 0) {
         wpd_small_level<T, F, 2, GST, TREE>(a, b, grow, n0, last, tp, tid, nthreads, tmk);
     } else if (p == 4) {

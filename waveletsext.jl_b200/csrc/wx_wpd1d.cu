@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(256) wpd1d_fused_k(T *__restrict__ y, const T 
 // Buffer reuse: store S_l reads buffer b_l during level l+1; thread 0 waits for it (bulk wait_group.read) right
 // before the barrier that lets level l+2 overwrite that buffer, so the wait is normally already satisfied.
 // Tensor maps view x and y as 2-D arrays of 128-byte rows: coordinates {0, row}.
-template <typename T, int F>
+template <typename T, int F, int KM>
 __global__ void __launch_bounds__(512) wpd1d_tma_k(const __grid_constant__ CUtensorMap mapx, const __grid_constant__ CUtensorMap mapy, long n, int L,
                                                   int d0, long items, int bufelems, int boxrows, int l2hint, Taps<T> tp)
 {
@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(512) wpd1d_tma_k(const __grid_constant__ CUten
         const int nlev = L - d0;
         for (int l = 0; l < nlev; ++l) {
             const int p = n0 >> l;
-            wpd_level<T, F, false>(a, b, nullptr, n0, p, false, tp, tid, nthreads);
+            wpd_level<T, F, false, false, KM>(a, b, nullptr, n0, p, false, tp, tid, nthreads);
             wx_fence_proxy_async();                                    // my smem writes -> visible to the TMA engine
             if (tid == 0) wx_bulk_wait_read0();                        // buffer `a` is no longer being read by an older store
             __syncthreads();
@@ -178,10 +178,10 @@ int wpd1d_launch_fused(T *y, const T *x, long n, int L, long N, int d0, const Ta
 }
 
 
-template <typename T, int F>
+template <typename T, int F, int KM>
 int wpd1d_launch_tma(T *y, const T *x, long n, int L, long N, int d0, const Taps<T> &t, cudaStream_t s, bool *handled)
 {
-    using C = WpdCfg<T, F>;
+    using C = WpdCfg<T, F, KM>;
     *handled = false;
     constexpr long RE = 128 / (long)sizeof(T);
     const long n0 = n >> d0;
@@ -213,7 +213,7 @@ int wpd1d_launch_tma(T *y, const T *x, long n, int L, long N, int d0, const Taps
     const char *henv = getenv("WX_B200_WPD1D_L2HINT");
     const int l2hint = henv ? atoi(henv) : 0;       // evict_first hints on the bulk tensor copies: measured, no effect (profiles/r2_wpd1d_ab.jsonl)
     if (threads > 256) threads = (tenv && atoi(tenv) == 512 && threads >= 512) ? 512 : 256;
-    auto kern = wpd1d_tma_k<T, F>;
+    auto kern = wpd1d_tma_k<T, F, KM>;
     WX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occmax = 0;
     WX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occmax, kern, threads, smem));
@@ -285,7 +285,12 @@ int wpd1d_impl(T *y, const T *x, long n, int L, long N, const double *h, const d
 #define WX_WPD_CASE(FF)                                                                             \
     case FF: {                                                                                      \
         bool handled = false;                                                                       \
-        if (!no_tma) { rc = wpd1d_launch_tma<T, FF>(y, x, n, L, N, d0, t, s, &handled); if (rc) return rc; } \
+        if (!no_tma) {                                                                              \
+            /* 14+ taps on nodes of at least 128 wide units: the wider window (WpdCfg KM = 4) */        \
+            if (FF >= 14 && (n >> d0) / (8 * V) >= 128) rc = wpd1d_launch_tma<T, FF, (FF >= 14 ? 4 : 2)>(y, x, n, L, N, d0, t, s, &handled); \
+            else rc = wpd1d_launch_tma<T, FF, 2>(y, x, n, L, N, d0, t, s, &handled);                  \
+            if (rc) return rc;                                                                      \
+        }                                                                                           \
         if (handled) return WX_OK;                                                                  \
         return wpd1d_launch_fused<T, FF>(y, x, n, L, N, d0, t, s);                                  \
     }
