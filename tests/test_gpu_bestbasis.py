@@ -339,3 +339,22 @@ def test_ldb_2d(wx, O, cuda):
     cref = O.ldb_costs(Dref)
     assert rel(cost, cref) <= 1e-10
     assert np.array_equal(tree, O.tree_select(cref, 16, 16, minmax="max"))
+
+
+def test_getbasiscoefall_per_signal_trees_checks(wx, cuda):
+    """Utils.jl:204-218: every tree valid, n_t == gettreelength, enough decomposition levels -- checked on the device"""
+    wt = wx.wavelet("db2")
+    n, N, L = 64, 9, 3
+    Xw = wx.wpdall(torch.randn((N, n), dtype=torch.float64, device=cuda), wt, L)          # K = 4 levels
+    trees = torch.zeros((N, n - 1), dtype=torch.bool, device=cuda)
+    trees[:, 0] = True; trees[3, 1] = True
+    out = wx.getbasiscoefall(Xw, trees)
+    assert torch.equal(out[0, :32], Xw[0, 1, :32]) and torch.equal(out[3, :16], Xw[3, 2, :16]) and torch.equal(out[3, 32:], Xw[3, 1, 32:])
+    bad = trees.clone(); bad[5, 0] = False; bad[5, 2] = True                               # node 3 split, its parent is not
+    with pytest.raises(AssertionError):
+        wx.getbasiscoefall(Xw, bad)
+    deep = trees.clone(); deep[2, [1, 3, 7]] = True                                        # a split node at depth 3 needs level 4
+    with pytest.raises(ValueError):
+        wx.getbasiscoefall(Xw, deep)
+    with pytest.raises(AssertionError):
+        wx.getbasiscoefall(Xw, trees[:, :-1])                                              # n_t != gettreelength
