@@ -561,29 +561,18 @@ int wpd2d_haar_run(T *y, const T *x, long m, long n, int L, long N, const Taps<T
     const long tiles_r = m >> lr, tiles = tiles_r * (n >> lc);
     if (tiles * N >= (1L << 31)) return WX_OK;
     auto kern = wpd2d_haar_k<T>;
-    // resident CTAs per SM: one CTA per tile (hardware scheduled), so the residency is capped by asking for more dynamic shared
-    // memory than the two buffers need.  Like the other write-dominated kernels the best residency is measured by the first
-    // large launch of a shape (wx_tuned_choice); small launches take what fits.
-    const int occfit = (int)(dv.smem_optin / (smem + 1024));
-    auto launch = [&](int occ) -> int {
-        size_t ask = smem;
+    // Residency: one CTA per tile, hardware scheduled, three per SM by shared memory.  Capping it (by asking for more dynamic shared
+    // memory, knob WX_B200_HAAR2D_OCC) was measured in round 2: 9.39 ms with three, 9.97 with two, 13.3 with one (Float32 5.98 / 6.41 /
+    // 8.60) -- unlike the persistent 1-D kernels this one wants everything resident, so it is not tuned at run time.  (A first
+    // version let wx_tuned_choice try the candidates: the launches with inflated shared memory left every later launch ~7 % slower.)
+    size_t ask = smem;
+    if (const char *oenv = getenv("WX_B200_HAAR2D_OCC")) {
+        const int occ = atoi(oenv), occfit = (int)(dv.smem_optin / (smem + 1024));
         if (occ >= 1 && occ < occfit) { ask = (dv.smem_optin / (size_t)occ - 1024) & ~(size_t)127; if (ask < smem) ask = smem; }
-        WX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ask));
-        kern<<<(unsigned)(tiles * N), kT2, ask, s>>>(y, x, (int)m, (int)n, L, lr, lc, make_div32(tiles), make_div32(tiles_r), t);
-        WX_LAUNCHED();
-        return WX_OK;
-    };
-    int cand[8], nc = 0, occ = occfit;
-    for (int c = 1; c <= occfit && c <= 6; ++c) cand[nc++] = c;
-    const char *oenv = getenv("WX_B200_HAAR2D_OCC");
-    if (oenv && atoi(oenv) >= 1) occ = atoi(oenv);
-    else {
-        const bool big = tiles * N >= 8L * dv.sms * (occfit > 0 ? occfit : 1) && (double)m * (double)n * (double)N * (L + 2) * sizeof(T) >= 256e6;
-        rc = wx_tuned_choice(WxTuneKey{(const void *)kern, m, n, (long)L, (long)lr * 64 + lc}, nc, cand, occfit, big, s, launch, &occ);
-        if (rc) return rc;
     }
-    rc = launch(occ);
-    if (rc) return rc;
+    WX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ask));
+    kern<<<(unsigned)(tiles * N), kT2, ask, s>>>(y, x, (int)m, (int)n, L, lr, lc, make_div32(tiles), make_div32(tiles_r), t);
+    WX_LAUNCHED();
     *done = true;
     return WX_OK;
 }
