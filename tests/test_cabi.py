@@ -81,3 +81,62 @@ def test_compute_fails_loudly_without_gpu(wx):
         _lib.check(rc)
     with pytest.raises((_lib.WxError, RuntimeError, AssertionError)):
         wx.host.wpdall_host(np.zeros((2, 8)), wx.wavelet("haar"), device=0)
+
+
+def test_collective_entry_points_validate_without_a_gpu(wx):
+    """wx_comm.cu: NCCL resolves by dlopen (no link-time dependency), argument errors are reported before any CUDA / NCCL work,
+    and without a device the communicator constructors and the fused best-basis drivers fail loudly"""
+    import subprocess, shutil
+    import torch
+    from waveletsext_b200 import _lib
+    L = _lib.lib()
+    protos = _lib.parse_header()
+    for nm in ("wx_nccl_version", "wx_comm_unique_id", "wx_comm_init_rank", "wx_comm_init_all", "wx_comm_info", "wx_comm_destroy",
+               "wx_group_start", "wx_group_end", "wx_allreduce", "wx_allgather", "wx_broadcast", "wx_tree_costs_jbb_f64",
+               "wx_tree_costs_jbb_f32", "wx_tree_costs_lsdb_f64", "wx_tree_costs_lsdb_f32", "wx_bestbasistree_f64", "wx_bestbasistree_f32",
+               "wx_bestbasistree_multi_f64", "wx_bestbasistree_multi_f32", "wx_wpd_bestbasis_host_f64", "wx_wpd_bestbasis_host_f32"):
+        assert nm in protos, nm
+    # no DT_NEEDED on NCCL: a single-GPU host never needs it
+    readelf = shutil.which("readelf")
+    if readelf:
+        needed = subprocess.run([readelf, "-d", _lib.LIBPATH], capture_output=True, text=True).stdout
+        assert "nccl" not in needed.lower()
+    v = C.c_int(0)
+    assert L.wx_nccl_version(C.byref(v)) == 0 and v.value >= 21800                       # the libnccl.so.2 torch mapped
+    ident = (C.c_ubyte * 128)()
+    assert L.wx_comm_unique_id(ident) == 0 and any(bytes(ident))
+    h = C.c_void_p()
+    assert L.wx_comm_init_rank(C.byref(h), ident, 2, 2) == _lib.WX_EINVAL and "rank" in _lib.last_error()
+    assert L.wx_comm_init_rank(None, ident, 0, 1) == _lib.WX_EINVAL
+    assert L.wx_allreduce(None, None, 4, 0, 0, None) == _lib.WX_EINVAL
+    assert L.wx_allgather(None, None, None, 4, 0, None) == _lib.WX_EINVAL
+    assert L.wx_broadcast(None, None, 4, 0, 0, None) == _lib.WX_EINVAL
+    assert L.wx_comm_destroy(None) == 0
+    assert L.wx_comm_info(None, None, None, None, None) == _lib.WX_EINVAL
+    tree = np.zeros(63, np.uint8)
+    # argument checks of the fused drivers come before any device work
+    rc = L.wx_bestbasistree_f64(None, 2, tree.ctypes.data, 63, None, None, 0, 64, 7, 0, 0, 0, C.c_double(2.0), None)
+    assert rc == _lib.WX_EINVAL and "method" in _lib.last_error()
+    rc = L.wx_bestbasistree_f64(None, 0, tree.ctypes.data, 62, None, None, 0, 64, 7, 0, 0, 0, C.c_double(2.0), None)
+    assert rc == _lib.WX_EINVAL and "tree buffer" in _lib.last_error()
+    rc = L.wx_bestbasistree_f64(None, 0, None, 63, None, None, 0, 64, 7, 0, 0, 0, C.c_double(2.0), None)
+    assert rc == _lib.WX_EINVAL
+    rc = L.wx_bestbasistree_multi_f64(None, 2, 0, tree.ctypes.data, 63, None, None, None, 0, 64, 7, 0, 0, C.c_double(2.0))
+    assert rc == _lib.WX_EINVAL
+    coef = np.zeros((2, 64)); x = np.zeros((2, 64)); hh = np.ones(2); gg = np.ones(2)
+    rc = L.wx_wpd_bestbasis_host_f64(None, coef.ctypes.data, tree.ctypes.data, 63, x.ctypes.data, 64, 9, 2, hh.ctypes.data, gg.ctypes.data, 2, 0, 0,
+                                      C.c_double(2.0), 0)
+    assert rc == _lib.WX_EINVAL and "maxtransformlevels" in _lib.last_error()
+    rc = L.wx_wpd_bestbasis_host_f64(None, coef.ctypes.data, tree.ctypes.data, 60, x.ctypes.data, 64, 3, 2, hh.ctypes.data, gg.ctypes.data, 2, 0, 0,
+                                      C.c_double(2.0), 0)
+    assert rc == _lib.WX_EINVAL and "tree buffer" in _lib.last_error()
+    if not torch.cuda.is_available():
+        X = np.zeros((4, 7, 64))
+        costs = np.zeros(127)
+        assert L.wx_tree_costs_jbb_f64(None, costs.ctypes.data, X.ctypes.data, 0, 64, 7, 4, 0, 0, C.c_double(2.0), None) == _lib.WX_ECUDA
+        assert L.wx_comm_init_rank(C.byref(h), ident, 0, 1) == _lib.WX_ECUDA
+        comms = (C.c_void_p * 1)()
+        assert L.wx_comm_init_all(comms, 1, None) == _lib.WX_ECUDA
+        rc = L.wx_wpd_bestbasis_host_f64(None, coef.ctypes.data, tree.ctypes.data, 63, x.ctypes.data, 64, 3, 2, hh.ctypes.data, gg.ctypes.data, 2, 0, 0,
+                                          C.c_double(2.0), 0)
+        assert rc == _lib.WX_ECUDA
