@@ -358,3 +358,29 @@ def test_getbasiscoefall_per_signal_trees_checks(wx, cuda):
         wx.getbasiscoefall(Xw, deep)
     with pytest.raises(AssertionError):
         wx.getbasiscoefall(Xw, trees[:, :-1])                                              # n_t != gettreelength
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+@pytest.mark.parametrize("n,L", [(1024, 10), (2048, 11), (4096, 6), (1024, 3)])
+def test_bb_costs_power_of_two_kernel(wx, O, cuda, dt, n, L):
+    """the specialised kernel for decimated tables with n = 2^a >= 1024 (four coefficients per thread, segmented shuffle sums) against
+    the oracle and against the generic kernel's answer for the same table (a zero signal and a one-hot signal included)"""
+    wt = wx.wavelet("db4")
+    N = 6
+    X = signals(n, N, n + L).astype(dt)
+    X[1] = 0.0
+    X[2] = 0.0; X[2, 5] = 3.0
+    Xw = wx.wpdall(dev(X, cuda), wt, L)
+    Xh = Xw.cpu().numpy()
+    for cost, method in (("shannon", wx.BB()), ("logenergy", wx.BB(wx.LogEnergyEntropyCost(), False))):
+        costs, _, _ = wx.bestbasis._bb_costs_batch(Xw, method)
+        c = costs.cpu().numpy()
+        for k in range(N):
+            ref = O.tree_costs_bb(Xh[k], False, cost).astype(np.float64)
+            fin = np.isfinite(ref)
+            assert np.array_equal(np.isfinite(c[k]), fin)
+            den = np.abs(ref[fin]).max() if fin.any() and np.abs(ref[fin]).max() > 0 else 1.0
+            assert np.abs(c[k][fin] - ref[fin]).max() <= (1e-12 if dt == np.float64 else 2e-5) * den, (cost, k)
+        trees = wx.bestbasistreeall(Xw, method)
+        for k in (0, 3):
+            assert wx.isvalidtree(X[k], trees[k].cpu().numpy())

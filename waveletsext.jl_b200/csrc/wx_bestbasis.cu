@@ -905,6 +905,111 @@ __global__ void __launch_bounds__(kT) bb_costs_1d_k(double *costs, const T *X, l
     }
 }
 
+// The same for the common shape -- decimated table, n a power of two >= 1024 -- with the control flow stripped: the generic kernel
+// above spends 112 thread instructions per coefficient (ncu: 78 % of the issue slots, 7 % of them DFMA; 64-bit index arithmetic and
+// per-level set-up around four coefficients of work).  Here a thread owns four consecutive coefficients of a 1024-element chunk
+// (one 128-bit / two 128-bit loads), all four lie in one node whenever the node has >= 4 coefficients, and the node sums are
+// segmented shuffle reductions over the p/4 threads of a node (shared memory only for nodes wider than a warp's 128 coefficients).
+template <typename T> struct BbLoad4;
+template <> struct BbLoad4<double> {
+    __device__ static __forceinline__ void ld(const double *p, double *v)
+    {
+        const double2 a = __ldcs(reinterpret_cast<const double2 *>(p)), b = __ldcs(reinterpret_cast<const double2 *>(p) + 1);
+        v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+    }
+};
+template <> struct BbLoad4<float> {
+    __device__ static __forceinline__ void ld(const float *p, double *v)
+    {
+        const float4 a = __ldcs(reinterpret_cast<const float4 *>(p));
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+    }
+};
+
+template <typename T>
+__global__ void __launch_bounds__(kT) bb_costs_1d_pow2_k(double *costs, const T *X, int n, int lgn, int K, long nn, int kind)
+{
+    __shared__ double wsum[kT / 32];
+    __shared__ double s_inv;
+    const long k = blockIdx.x;
+    const T *Xk = X + k * (long)n * K;
+    double *ck = costs + k * nn;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nchunk = n >> 10;
+    double v[4];
+    // nrm = norm(X[:,1])
+    double a = 0.0;
+    for (int c = 0; c < nchunk; ++c) {
+        BbLoad4<T>::ld(Xk + c * 1024 + tid * 4, v);
+        a = fma(v[0], v[0], a); a = fma(v[1], v[1], a); a = fma(v[2], v[2], a); a = fma(v[3], v[3], a);
+    }
+    a = group_sum(a, 32);
+    if (lane == 0) wsum[warp] = a;
+    __syncthreads();
+    if (tid == 0) {
+        double t = 0.0;
+        for (int w = 0; w < kT / 32; ++w) t += wsum[w];
+        double nrm = sqrt(t);
+        if (sizeof(T) == 4) nrm = (double)(float)nrm;
+        s_inv = nrm > 0.0 ? 1.0 / nrm : 0.0;                 // nrm == 0: every cost is 0 (bestbasis_costs.jl:119)
+    }
+    __syncthreads();
+    const double inv = s_inv;
+    for (int l = 0; l < K; ++l) {
+        const int lgp = lgn - l;                              // node length 2^lgp
+        const T *lev = Xk + (long)l * n;
+        double *cl = ck + ((1L << l) - 1);
+        if (lgp >= 10) {
+            // a node is one or more whole chunks: accumulate per thread over the node's chunks, then one block reduction
+            const int cpn = 1 << (lgp - 10);
+            for (int j = 0; j < (1 << l); ++j) {
+                double acc = 0.0;
+                for (int c = 0; c < cpn; ++c) {
+                    BbLoad4<T>::ld(lev + (j * cpn + c) * 1024 + tid * 4, v);
+                    acc += (bb_term(v[0], inv, kind) + bb_term(v[1], inv, kind)) + (bb_term(v[2], inv, kind) + bb_term(v[3], inv, kind));
+                }
+                acc = group_sum(acc, 32);
+                if (lane == 0) wsum[warp] = acc;
+                __syncthreads();
+                if (tid == 0) {
+                    double t = 0.0;
+                    for (int w = 0; w < kT / 32; ++w) t += wsum[w];
+                    cl[j] = t;
+                }
+                __syncthreads();
+            }
+            continue;
+        }
+        for (int c = 0; c < nchunk; ++c) {
+            const int e0 = c * 1024 + tid * 4;
+            BbLoad4<T>::ld(lev + e0, v);
+            const double t0 = bb_term(v[0], inv, kind), t1 = bb_term(v[1], inv, kind), t2 = bb_term(v[2], inv, kind), t3 = bb_term(v[3], inv, kind);
+            if (lgp >= 2) {
+                const int gsz = 1 << (lgp - 2);               // threads per node: 1 .. 128
+                double acc = (t0 + t1) + (t2 + t3);
+                if (gsz <= 32) {
+                    acc = group_sum(acc, gsz);
+                    if ((tid & (gsz - 1)) == 0) cl[e0 >> lgp] = acc;
+                } else {
+                    acc = group_sum(acc, 32);
+                    if (lane == 0) wsum[warp] = acc;
+                    __syncthreads();
+                    if ((tid & (gsz - 1)) == 0) {
+                        double t = 0.0;
+                        for (int w = 0; w < gsz / 32; ++w) t += wsum[warp + w];
+                        cl[e0 >> lgp] = t;
+                    }
+                    __syncthreads();
+                }
+            } else if (lgp == 1) {
+                cl[e0 >> 1] = t0 + t1; cl[(e0 >> 1) + 1] = t2 + t3;
+            } else {
+                cl[e0] = t0; cl[e0 + 1] = t1; cl[e0 + 2] = t2; cl[e0 + 3] = t3;
+            }
+        }
+    }
+}
+
 // any geometry (2-D quad trees, redundant 2-D): one warp per (signal, node) through node_elem.  pernode: the 2-D non-redundant
 // branch of the reference normalises every node by its own norm (bestbasis_tree.jl:252 passes no nrm) -- kept as written.
 template <typename T>
@@ -1148,7 +1253,11 @@ static int bb_costs_impl(double *costs, const T *X, long m, long n, int K, long 
     const long nn = count_nodes(m, K, redundant);
     if (m == 0) {
         WX_REQUIRE(N < (1L << 31), "too many signals for one launch");
-        bb_costs_1d_k<T><<<(unsigned)N, kT, 0, s>>>(costs, X, n, K, nn, redundant, kind);
+        static const bool generic = getenv("WX_B200_BB_GENERIC") != nullptr;          // A-B measurements only
+        if (!generic && !redundant && wx_ispow2(n) && n >= 1024 && n < (1L << 30) && K <= wx_ilog2l(n) + 1 && (((uintptr_t)X) & 15) == 0)
+            bb_costs_1d_pow2_k<T><<<(unsigned)N, kT, 0, s>>>(costs, X, (int)n, wx_ilog2l(n), K, nn, kind);
+        else
+            bb_costs_1d_k<T><<<(unsigned)N, kT, 0, s>>>(costs, X, n, K, nn, redundant, kind);
     } else {
         NodeGeom g{m, n, K, redundant};
         const long sz = m * n;
