@@ -238,10 +238,12 @@ __device__ __forceinline__ void wpd_level(const T *__restrict__ a, T *__restrict
 //   v[2t]   = sum_r g[F-1-2r] w1[t-r] + h[2r+1] w2[t+r]
 //   v[2t+1] = sum_r g[F-2-2r] w1[t-r] + h[2r]   w2[t+r]          (indices mod p/2, r = 0..R-1 in the reference's order)
 // =====================================================================================================
-template <typename T, int F>
+template <typename T, int F, int KM = 4>
 struct IwptCfg {
     static constexpr int V = WxVec<T>::N;
-    static constexpr int K = 4 * V;                                    // output pairs per thread (reads at a 4-chunk stride: conflict free)
+    // output pairs per thread.  KM = 4 (reads at a 4-chunk stride) is the default; the launcher takes KM = 2 for nodes too short to
+    // give a CTA 64 units of 4V pairs (Float32 n = 1024: iwptall 0.78 -> 0.57 ms, profiles/r2_iwpt_km_ab.jsonl)
+    static constexpr int K = KM * V;
     static constexpr int R = F / 2;
     static constexpr int S = ((R - 1) + V - 1) / V * V;                // w1 look-behind (multiple of V)
     static constexpr int W = K + S;                                    // window length of each child
@@ -267,11 +269,11 @@ __device__ __forceinline__ void iwpt_pair(const T *a, const T *b, const Taps<T> 
     od = o;
 }
 
-template <typename T, int F, bool POW2, bool TREE>
+template <typename T, int F, bool POW2, bool TREE, int KM = 4>
 __device__ __forceinline__ void iwpt_wide_level(const T *__restrict__ src, T *__restrict__ dst, int n0, int p, const Taps<T> &tp, int tid,
                                                 int nthreads, TreeMask tmk)
 {
-    using C = IwptCfg<T, F>;
+    using C = IwptCfg<T, F, KM>;
     using VT = typename WxVec<T>::type;
     constexpr int V = C::V, K = C::K, S = C::S, W = C::W;
     constexpr int GA = (S + K - 1) / K;                 // aligned groups of K elements behind t0 touched by the w1 window
@@ -452,17 +454,17 @@ __device__ __forceinline__ void iwpt_generic_level(const T *__restrict__ src, T 
     }
 }
 
-template <typename T, int F, bool TREE>
+template <typename T, int F, bool TREE, int KM = 4>
 __device__ __forceinline__ void iwpt_level(const T *__restrict__ a, T *__restrict__ b, int n0, int p, const Taps<T> &tp, int tid, int nthreads,
                                            TreeMask tmk)
 {
-    using C = IwptCfg<T, F>;
+    using C = IwptCfg<T, F, KM>;
     constexpr int V = C::V, K = C::K;
     const int half = p >> 1;
     const bool pow2 = (p & (p - 1)) == 0;
     if (half % K == 0) {
-        if (pow2) iwpt_wide_level<T, F, true, TREE>(a, b, n0, p, tp, tid, nthreads, tmk);
-        else      iwpt_wide_level<T, F, false, TREE>(a, b, n0, p, tp, tid, nthreads, tmk);
+        if (pow2) iwpt_wide_level<T, F, true, TREE, KM>(a, b, n0, p, tp, tid, nthreads, tmk);
+        else      iwpt_wide_level<T, F, false, TREE, KM>(a, b, n0, p, tp, tid, nthreads, tmk);
     } else if (p == 2 && n0 % (V > 2 ? V : 2) == 0) {
         iwpt_small_level<T, F, 2, TREE>(a, b, n0, tp, tid, nthreads, tmk);
     } else if (p == 4) {

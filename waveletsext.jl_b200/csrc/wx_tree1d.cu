@@ -9,12 +9,16 @@
 #include "wx_steps.cuh"
 #include "wx_levels.cuh"
 
+#ifndef WX_TREE_MAXT
+#define WX_TREE_MAXT 256          // threads per CTA of the fused tree kernels (A-B builds: 512 with WX_IWPT_KM=2)
+#endif
+
 namespace {
 
 // item = (signal k, node j0 of depth d0).  Levels d0..nlev-1 of that node are processed (forward: top down, inverse:
 // bottom up).  depth != nullptr: x is a packet table (n, Kx, N) and position e is read from level depth[e].
-template <typename T, int F, bool INV, bool TREE>
-__global__ void __launch_bounds__(256) tree1d_fused_k(T *__restrict__ y, const T *__restrict__ x, long n, int d0, int nlev, long items, int bufelems,
+template <typename T, int F, bool INV, bool TREE, int KM>
+__global__ void __launch_bounds__(WX_TREE_MAXT) tree1d_fused_k(T *__restrict__ y, const T *__restrict__ x, long n, int d0, int nlev, long items, int bufelems,
                                                      const unsigned char *__restrict__ tree, long ntree, const unsigned char *__restrict__ depth,
                                                      int Kx, int vecgather, Taps<T> tp)
 {
@@ -62,7 +66,7 @@ __global__ void __launch_bounds__(256) tree1d_fused_k(T *__restrict__ y, const T
             const int d = d0 + l;
             const long first = ((1L << d) - 1) + (j0 << l);               // 0-based heap position of the node's first depth-d descendant
             TreeMask tm{TREE ? tree + first : nullptr, ntree - first};
-            if (INV) iwpt_level<T, F, TREE>(a, b, n0, n0 >> l, tp, tid, nthreads, tm);
+            if (INV) iwpt_level<T, F, TREE, KM>(a, b, n0, n0 >> l, tp, tid, nthreads, tm);
             else     wpd_level<T, F, false, TREE>(a, b, nullptr, n0, n0 >> l, false, tp, tid, nthreads, tm);
             __syncthreads();
             T *t = a; a = b; b = t;
@@ -75,20 +79,20 @@ __global__ void __launch_bounds__(256) tree1d_fused_k(T *__restrict__ y, const T
     }
 }
 
-template <typename T, int F, bool INV, bool TREE>
-int launch(T *y, const T *x, long n, long N, int d0, int nlev, const unsigned char *dtree, long ntree, const unsigned char *ddepth, int Kx,
-           int vecgather, const Taps<T> &t, cudaStream_t s)
+template <typename T, int F, bool INV, bool TREE, int KM>
+int launch_km(T *y, const T *x, long n, long N, int d0, int nlev, const unsigned char *dtree, long ntree, const unsigned char *ddepth, int Kx,
+              int vecgather, const Taps<T> &t, cudaStream_t s)
 {
     WxDev dv; int rc = wx_devinfo(dv); if (rc) return rc;
     constexpr int V = WxVec<T>::N;
     const long n0 = n >> d0;
     const long bufbytes = ((n0 * (long)sizeof(T) + 127) / 128) * 128;
     const size_t smem = (size_t)2 * bufbytes;
-    long units = n0 / (8 * V);
+    long units = n0 / (2 * (INV ? IwptCfg<T, F, KM>::K : WpdCfg<T, F>::K));
     int threads = (int)((units + 31) / 32 * 32);
     if (threads < 64) threads = 64;
-    if (threads > 256) threads = 256;
-    auto kern = tree1d_fused_k<T, F, INV, TREE>;
+    if (threads > WX_TREE_MAXT) threads = WX_TREE_MAXT;
+    auto kern = tree1d_fused_k<T, F, INV, TREE, KM>;
     WX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
     WX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
@@ -99,6 +103,16 @@ int launch(T *y, const T *x, long n, long N, int d0, int nlev, const unsigned ch
     kern<<<(unsigned)blocks, threads, smem, s>>>(y, x, n, d0, nlev, items, (int)(bufbytes / sizeof(T)), dtree, ntree, ddepth, Kx, vecgather, t);
     WX_LAUNCHED();
     return WX_OK;
+}
+
+// inverse: 4V output pairs per thread unless the node is too short to give a CTA 64 such units (then 2V); forward: WpdCfg's 2V
+template <typename T, int F, bool INV, bool TREE>
+int launch(T *y, const T *x, long n, long N, int d0, int nlev, const unsigned char *dtree, long ntree, const unsigned char *ddepth, int Kx,
+           int vecgather, const Taps<T> &t, cudaStream_t s)
+{
+    constexpr int V = WxVec<T>::N;
+    if (INV && (n >> d0) / (8 * V) < 64) return launch_km<T, F, INV, TREE, 2>(y, x, n, N, d0, nlev, dtree, ntree, ddepth, Kx, vecgather, t, s);
+    return launch_km<T, F, INV, TREE, 4>(y, x, n, N, d0, nlev, dtree, ntree, ddepth, Kx, vecgather, t, s);
 }
 
 template <typename T, int F>
