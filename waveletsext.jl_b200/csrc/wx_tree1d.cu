@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(WX_TREE_MAXT) tree1d_fused_k(T *__restrict__ y
             const long first = ((1L << d) - 1) + (j0 << l);               // 0-based heap position of the node's first depth-d descendant
             TreeMask tm{TREE ? tree + first : nullptr, ntree - first};
             if (INV) iwpt_level<T, F, TREE, KM>(a, b, n0, n0 >> l, tp, tid, nthreads, tm);
-            else     wpd_level<T, F, false, TREE>(a, b, nullptr, n0, n0 >> l, false, tp, tid, nthreads, tm);
+            else     wpd_level<T, F, false, TREE, KM>(a, b, nullptr, n0, n0 >> l, false, tp, tid, nthreads, tm);
             __syncthreads();
             T *t = a; a = b; b = t;
         }
@@ -88,7 +88,7 @@ int launch_km(T *y, const T *x, long n, long N, int d0, int nlev, const unsigned
     const long n0 = n >> d0;
     const long bufbytes = ((n0 * (long)sizeof(T) + 127) / 128) * 128;
     const size_t smem = (size_t)2 * bufbytes;
-    long units = n0 / (2 * (INV ? IwptCfg<T, F, KM>::K : WpdCfg<T, F>::K));
+    long units = n0 / (2 * (INV ? IwptCfg<T, F, KM>::K : WpdCfg<T, F, KM>::K));
     int threads = (int)((units + 31) / 32 * 32);
     if (threads < 64) threads = 64;
     if (threads > WX_TREE_MAXT) threads = WX_TREE_MAXT;
@@ -105,13 +105,15 @@ int launch_km(T *y, const T *x, long n, long N, int d0, int nlev, const unsigned
     return WX_OK;
 }
 
-// inverse: 4V output pairs per thread unless the node is too short to give a CTA 64 such units (then 2V); forward: WpdCfg's 2V
+// 4V output pairs per thread unless the node is too short to give a CTA 64 such units (then 2V).  (The by-tree kernels are bound by
+// the shared-memory / FP pipes, not by HBM like wpdall, so the wider window pays for every filter length.)
 template <typename T, int F, bool INV, bool TREE>
 int launch(T *y, const T *x, long n, long N, int d0, int nlev, const unsigned char *dtree, long ntree, const unsigned char *ddepth, int Kx,
            int vecgather, const Taps<T> &t, cudaStream_t s)
 {
     constexpr int V = WxVec<T>::N;
-    if (INV && (n >> d0) / (8 * V) < 64) return launch_km<T, F, INV, TREE, 2>(y, x, n, N, d0, nlev, dtree, ntree, ddepth, Kx, vecgather, t, s);
+    static const bool fwd2 = getenv("WX_B200_WPT_KM2") != nullptr;          // A-B measurements only
+    if ((n >> d0) / (8 * V) < 64 || (!INV && fwd2)) return launch_km<T, F, INV, TREE, 2>(y, x, n, N, d0, nlev, dtree, ntree, ddepth, Kx, vecgather, t, s);
     return launch_km<T, F, INV, TREE, 4>(y, x, n, N, d0, nlev, dtree, ntree, ddepth, Kx, vecgather, t, s);
 }
 
