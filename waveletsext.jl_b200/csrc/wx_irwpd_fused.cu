@@ -19,7 +19,10 @@ namespace {
 
 template <typename T, int F>
 struct IrCfg {
-    static constexpr int LGK = (F <= 16) ? 4 : 3;
+#ifndef WX_IR_LGK
+#define WX_IR_LGK 4
+#endif
+    static constexpr int LGK = (F <= 16) ? WX_IR_LGK : 3;
     static constexpr int K = 1 << LGK;
 };
 
