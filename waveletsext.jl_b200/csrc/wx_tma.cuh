@@ -63,6 +63,7 @@ __device__ __forceinline__ void wx_tma_store_2d_hint(const CUtensorMap *map, int
 }
 __device__ __forceinline__ void wx_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void wx_bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void wx_bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void wx_bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // host: tensor map over `rows` rows of 128 bytes starting at `base`, box = boxrows x 128 B, SWIZZLE_128B.

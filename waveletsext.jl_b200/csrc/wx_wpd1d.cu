@@ -73,7 +73,9 @@ __global__ void __launch_bounds__(256) wpd1d_fused_k(T *__restrict__ y, const T 
 // Buffer reuse: store S_l reads buffer b_l during level l+1; thread 0 waits for it (bulk wait_group.read) right
 // before the barrier that lets level l+2 overwrite that buffer, so the wait is normally already satisfied.
 // Tensor maps view x and y as 2-D arrays of 128-byte rows: coordinates {0, row}.
-template <typename T, int F, int KM>
+// PF (three buffers): the next item's node is prefetched into the buffer the current item does not use, so the load latency of an
+// item is hidden behind the previous item's levels instead of being exposed at the top of every iteration.
+template <typename T, int F, int KM, bool PF>
 __global__ void __launch_bounds__(512) wpd1d_tma_k(const __grid_constant__ CUtensorMap mapx, const __grid_constant__ CUtensorMap mapy, long n, int L,
                                                   int d0, long items, int bufelems, int boxrows, int l2hint, Taps<T> tp)
 {
@@ -82,12 +84,14 @@ __global__ void __launch_bounds__(512) wpd1d_tma_k(const __grid_constant__ CUten
     extern __shared__ unsigned char wx_smem_raw[];
     __shared__ __align__(8) unsigned long long bar;
     // 1024-byte alignment for SWIZZLE_128B, as an offset from the array so that the accesses stay LDS/STS (not generic LD/ST)
-    T *buf0 = reinterpret_cast<T *>(wx_smem_raw + ((1024u - (wx_smem_u32(wx_smem_raw) & 1023u)) & 1023u));
-    T *buf1 = buf0 + bufelems;
+    T *X = reinterpret_cast<T *>(wx_smem_raw + ((1024u - (wx_smem_u32(wx_smem_raw) & 1023u)) & 1023u));   // holds the item's node
+    T *P = X + bufelems;                                                                                  // first level's output
+    T *N = PF ? P + bufelems : nullptr;                                                                   // landing buffer of the NEXT item
     const int n0 = (int)(n >> d0);
     const int tid = threadIdx.x, nthreads = blockDim.x;
     const int noderows = n0 / RE, nbox = noderows / boxrows;
     const long sigrows = n / RE;
+    const int nlev = L - d0;
 
     if (tid == 0) {
         wx_mbar_init(&bar, 1);
@@ -96,31 +100,49 @@ __global__ void __launch_bounds__(512) wpd1d_tma_k(const __grid_constant__ CUten
     __syncthreads();
     unsigned parity = 0;
 
+    // node of `item` -> dst (one thread)
+    auto load_item = [&](long item, T *dst) {
+        const long k = item >> d0;
+        const long j0 = item & ((1L << d0) - 1);
+        const long yrow0 = k * sigrows * (L + 1) + j0 * noderows;
+        wx_mbar_expect_tx(&bar, (unsigned)(n0 * sizeof(T)));
+        for (int bx = 0; bx < nbox; ++bx) {
+            if (d0 == 0 && l2hint) wx_tma_load_2d_hint(dst + (long)bx * boxrows * RE, &mapx, 0, (int)(k * sigrows + (long)bx * boxrows), &bar, pol);
+            else if (d0 == 0) wx_tma_load_2d(dst + (long)bx * boxrows * RE, &mapx, 0, (int)(k * sigrows + (long)bx * boxrows), &bar);
+            else         wx_tma_load_2d(dst + (long)bx * boxrows * RE, &mapy, 0, (int)(yrow0 + (long)d0 * sigrows + (long)bx * boxrows), &bar);
+        }
+    };
+    auto store_row = [&](long row, const T *src) {
+        for (int bx = 0; bx < nbox; ++bx) {
+            if (l2hint) wx_tma_store_2d_hint(&mapy, 0, (int)(row + (long)bx * boxrows), src + (long)bx * boxrows * RE, pol);
+            else wx_tma_store_2d(&mapy, 0, (int)(row + (long)bx * boxrows), src + (long)bx * boxrows * RE);
+        }
+        wx_bulk_commit();
+    };
+
+    if (PF && tid == 0 && (long)blockIdx.x < items) load_item(blockIdx.x, X);
     for (long item = blockIdx.x; item < items; item += gridDim.x) {
         const long k = item >> d0;
         const long j0 = item & ((1L << d0) - 1);
         const long yrow0 = k * sigrows * (L + 1) + j0 * noderows;      // row of level 0, this node
-        if (tid == 0) {
-            wx_bulk_wait_read0();                                      // stores of the previous item have released smem
-            wx_mbar_expect_tx(&bar, (unsigned)(n0 * sizeof(T)));
-            for (int bx = 0; bx < nbox; ++bx) {
-                if (d0 == 0 && l2hint) wx_tma_load_2d_hint(buf0 + (long)bx * boxrows * RE, &mapx, 0, (int)(k * sigrows + (long)bx * boxrows), &bar, pol);
-                else if (d0 == 0) wx_tma_load_2d(buf0 + (long)bx * boxrows * RE, &mapx, 0, (int)(k * sigrows + (long)bx * boxrows), &bar);
-                else         wx_tma_load_2d(buf0 + (long)bx * boxrows * RE, &mapy, 0, (int)(yrow0 + (long)d0 * sigrows + (long)bx * boxrows), &bar);
+        if (PF) {
+            // level 1 writes P, which fed the SECOND most recent store of the previous item (the most recent one reads the buffer that
+            // is now N and is waited for before the prefetch below): leave one group pending
+            if (tid == 0) wx_bulk_wait_read1();
+            wx_mbar_wait(&bar, parity);                                // this item's node, prefetched during the previous item
+            parity ^= 1;
+            __syncthreads();                                           // thread 0's wait holds for everybody
+        } else {
+            if (tid == 0) {
+                wx_bulk_wait_read0();                                  // stores of the previous item have released smem
+                load_item(item, X);
             }
+            wx_mbar_wait(&bar, parity);
+            parity ^= 1;
         }
-        wx_mbar_wait(&bar, parity);
-        parity ^= 1;
-        if (d0 == 0 && tid == 0) {                                     // level 0 = x   (DWT.jl:142)
-            for (int bx = 0; bx < nbox; ++bx) {
-                if (l2hint) wx_tma_store_2d_hint(&mapy, 0, (int)(yrow0 + (long)bx * boxrows), buf0 + (long)bx * boxrows * RE, pol);
-                else wx_tma_store_2d(&mapy, 0, (int)(yrow0 + (long)bx * boxrows), buf0 + (long)bx * boxrows * RE);
-            }
-            wx_bulk_commit();
-        }
+        if (d0 == 0 && tid == 0) store_row(yrow0, X);                  // level 0 = x   (DWT.jl:142)
 
-        T *a = buf0, *b = buf1;
-        const int nlev = L - d0;
+        T *a = X, *b = P;
         for (int l = 0; l < nlev; ++l) {
             const int p = n0 >> l;
             wpd_level<T, F, false, false, KM>(a, b, nullptr, n0, p, false, tp, tid, nthreads);
@@ -128,14 +150,17 @@ __global__ void __launch_bounds__(512) wpd1d_tma_k(const __grid_constant__ CUten
             if (tid == 0) wx_bulk_wait_read0();                        // buffer `a` is no longer being read by an older store
             __syncthreads();
             if (tid == 0) {
-                const long row = yrow0 + (long)(d0 + l + 1) * sigrows;
-                for (int bx = 0; bx < nbox; ++bx) {
-                    if (l2hint) wx_tma_store_2d_hint(&mapy, 0, (int)(row + (long)bx * boxrows), b + (long)bx * boxrows * RE, pol);
-                    else wx_tma_store_2d(&mapy, 0, (int)(row + (long)bx * boxrows), b + (long)bx * boxrows * RE);
-                }
-                wx_bulk_commit();
+                store_row(yrow0 + (long)(d0 + l + 1) * sigrows, b);
+                // every older store has finished reading shared memory (wait above): N is free, fetch the next item's node
+                if (PF && l == 0 && item + gridDim.x < items) load_item(item + gridDim.x, N);
             }
             T *t = a; a = b; b = t;
+        }
+        if (PF) {
+            // rotate: the prefetched buffer becomes X; the buffer of the last level's output (its store is the most recent group)
+            // becomes the next landing buffer, the other one the next P
+            T *Fb = (nlev & 1) ? P : X, *Gb = (nlev & 1) ? X : P;
+            X = N; P = Gb; N = Fb;
         }
     }
     if (tid == 0) wx_bulk_wait_all();
@@ -178,8 +203,8 @@ int wpd1d_launch_fused(T *y, const T *x, long n, int L, long N, int d0, const Ta
 }
 
 
-template <typename T, int F, int KM>
-int wpd1d_launch_tma(T *y, const T *x, long n, int L, long N, int d0, const Taps<T> &t, cudaStream_t s, bool *handled)
+template <typename T, int F, int KM, bool PF>
+int wpd1d_launch_tma_pf(T *y, const T *x, long n, int L, long N, int d0, const Taps<T> &t, cudaStream_t s, bool *handled)
 {
     using C = WpdCfg<T, F, KM>;
     *handled = false;
@@ -197,7 +222,7 @@ int wpd1d_launch_tma(T *y, const T *x, long n, int L, long N, int d0, const Taps
     if (wx_make_rowmap(&my, (const void *)y, sizeof(T), yrows, boxrows) != WX_OK) return WX_OK;
     WxDev dv; int rc = wx_devinfo(dv); if (rc) return rc;
     const long bufbytes = ((n0 * (long)sizeof(T) + 1023) / 1024) * 1024;
-    const size_t smem = (size_t)2 * bufbytes + 1024;
+    const size_t smem = (size_t)(PF ? 3 : 2) * bufbytes + 1024;
     if (smem > dv.smem_optin) return WX_OK;
     long units = n0 / (2 * C::K);
     int threads = (int)((units + 31) / 32 * 32);
@@ -213,7 +238,7 @@ int wpd1d_launch_tma(T *y, const T *x, long n, int L, long N, int d0, const Taps
     const char *henv = getenv("WX_B200_WPD1D_L2HINT");
     const int l2hint = henv ? atoi(henv) : 0;       // evict_first hints on the bulk tensor copies: measured, no effect (profiles/r2_wpd1d_ab.jsonl)
     if (threads > 256) threads = (tenv && atoi(tenv) == 512 && threads >= 512) ? 512 : 256;
-    auto kern = wpd1d_tma_k<T, F, KM>;
+    auto kern = wpd1d_tma_k<T, F, KM, PF>;
     WX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occmax = 0;
     WX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occmax, kern, threads, smem));
@@ -249,6 +274,18 @@ int wpd1d_launch_tma(T *y, const T *x, long n, int L, long N, int d0, const Taps
     if (rc) return rc;
     *handled = true;
     return WX_OK;
+}
+
+// three buffers (prefetch of the next node) when they fit, else two
+template <typename T, int F, int KM>
+int wpd1d_launch_tma(T *y, const T *x, long n, int L, long N, int d0, const Taps<T> &t, cudaStream_t s, bool *handled)
+{
+    static const bool nopf = getenv("WX_B200_WPD1D_NO_PREFETCH") != nullptr;      // A-B measurements only
+    if (!nopf) {
+        int rc = wpd1d_launch_tma_pf<T, F, KM, true>(y, x, n, L, N, d0, t, s, handled);
+        if (rc || *handled) return rc;
+    }
+    return wpd1d_launch_tma_pf<T, F, KM, false>(y, x, n, L, N, d0, t, s, handled);
 }
 
 template <typename T>
