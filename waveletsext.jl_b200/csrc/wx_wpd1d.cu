@@ -203,8 +203,8 @@ int wpd1d_launch_fused(T *y, const T *x, long n, int L, long N, int d0, const Ta
 }
 
 
-template <typename T, int F, int KM, bool PF>
-int wpd1d_launch_tma_pf(T *y, const T *x, long n, int L, long N, int d0, const Taps<T> &t, cudaStream_t s, bool *handled)
+template <typename T, int F, int KM>
+int wpd1d_launch_tma(T *y, const T *x, long n, int L, long N, int d0, const Taps<T> &t, cudaStream_t s, bool *handled)
 {
     using C = WpdCfg<T, F, KM>;
     *handled = false;
@@ -222,70 +222,74 @@ int wpd1d_launch_tma_pf(T *y, const T *x, long n, int L, long N, int d0, const T
     if (wx_make_rowmap(&my, (const void *)y, sizeof(T), yrows, boxrows) != WX_OK) return WX_OK;
     WxDev dv; int rc = wx_devinfo(dv); if (rc) return rc;
     const long bufbytes = ((n0 * (long)sizeof(T) + 1023) / 1024) * 1024;
-    const size_t smem = (size_t)(PF ? 3 : 2) * bufbytes + 1024;
-    if (smem > dv.smem_optin) return WX_OK;
+    const size_t smem2 = (size_t)2 * bufbytes + 1024, smem3 = (size_t)3 * bufbytes + 1024;
+    if (smem2 > dv.smem_optin) return WX_OK;
     long units = n0 / (2 * C::K);
     int threads = (int)((units + 31) / 32 * 32);
     if (threads < 64) threads = 64;
-    // Resident CTAs per SM.  The kernel is write-dominated (L+1 rows out per row in) and the best residency is NOT the maximum:
-    // fewer concurrent store streams suit the DRAM better as long as the resident warps still cover the arithmetic.  Measured
-    // (profiles/r2_wpd1d_residency_sweep.jsonl, 8 filters x 2 element types x n in {1024, 4096}): haar F64 n = 4096 runs 4.63 ms
-    // with ONE CTA per SM against 5.25 ms with three; db4 F64 wants 2, coif4 / sym8 3; n = 1024 wants 3-6, Float32 2-8.  The first
-    // large launch of a shape therefore measures the candidates (wx_tuned_choice); small launches use the warp-count rule below.
-    // Knobs for re-measuring: WX_B200_WPD1D_THREADS (256 / 512), WX_B200_WPD1D_OCC, WX_B200_WPD1D_L2HINT, WX_B200_AUTOTUNE=0.
+    // Resident CTAs per SM and the prefetch buffer.  The kernel is write-dominated (L+1 rows out per row in) and the best residency
+    // is NOT the maximum: fewer concurrent store streams suit the DRAM better as long as the resident warps still cover the
+    // arithmetic.  Measured (profiles/r2_wpd1d_residency_sweep.jsonl, 8 filters x 2 element types x n in {1024, 4096}): haar F64
+    // n = 4096 runs 4.63 ms with ONE CTA per SM against 5.25 ms with three; db4 F64 wants 2, coif4 / sym8 3; n = 1024 wants 3-6,
+    // Float32 2-8.  The three-buffer variant (next node prefetched during the current item) helps the long filters (sym8 F64
+    // 5.79 -> 5.36 ms) and hurts db4 / db5 F64 (4.81 -> 5.24 ms, profiles/r2_wpd1d_prefetch_ab.jsonl).  The first large launch of a
+    // shape therefore measures the (prefetch, residency) candidates (wx_tuned_choice); small launches use the warp-count rule.
+    // Knobs: WX_B200_WPD1D_THREADS (256 / 512), WX_B200_WPD1D_OCC, WX_B200_WPD1D_NO_PREFETCH, WX_B200_WPD1D_L2HINT, WX_B200_AUTOTUNE=0.
     const char *tenv = getenv("WX_B200_WPD1D_THREADS");             // read per call so that one process can sweep them
     const char *oenv = getenv("WX_B200_WPD1D_OCC");
     const char *henv = getenv("WX_B200_WPD1D_L2HINT");
+    const char *penv = getenv("WX_B200_WPD1D_NO_PREFETCH");
     const int l2hint = henv ? atoi(henv) : 0;       // evict_first hints on the bulk tensor copies: measured, no effect (profiles/r2_wpd1d_ab.jsonl)
     if (threads > 256) threads = (tenv && atoi(tenv) == 512 && threads >= 512) ? 512 : 256;
-    auto kern = wpd1d_tma_k<T, F, KM, PF>;
-    WX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int occmax = 0;
-    WX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occmax, kern, threads, smem));
-    if (occmax < 1) return WX_OK;
+    auto kern2 = wpd1d_tma_k<T, F, KM, false>;
+    auto kern3 = wpd1d_tma_k<T, F, KM, true>;
+    WX_CUDA(cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    int occmax2 = 0, occmax3 = 0;
+    WX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occmax2, kern2, threads, smem2));
+    if (occmax2 < 1) return WX_OK;
+    if (!penv && smem3 <= dv.smem_optin) {
+        WX_CUDA(cudaFuncSetAttribute(kern3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+        WX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occmax3, kern3, threads, smem3));
+    }
     const long items = N << d0;
-    auto launch = [&](int occ) -> int {
+    // candidate code = residency + 100 * prefetch
+    auto launch = [&](int code) -> int {
+        const int occ = code % 100;
         long blocks = (long)dv.sms * occ;
         if (blocks > items) blocks = items;
-        kern<<<(unsigned)blocks, threads, smem, s>>>(mx, my, n, L, d0, items, (int)(bufbytes / sizeof(T)), (int)boxrows, l2hint, t);
+        if (code >= 100) kern3<<<(unsigned)blocks, threads, smem3, s>>>(mx, my, n, L, d0, items, (int)(bufbytes / sizeof(T)), (int)boxrows, l2hint, t);
+        else             kern2<<<(unsigned)blocks, threads, smem2, s>>>(mx, my, n, L, d0, items, (int)(bufbytes / sizeof(T)), (int)boxrows, l2hint, t);
         WX_LAUNCHED();
         return WX_OK;
     };
-    int occ;
+    int code;
     if (oenv && atoi(oenv) >= 1) {
-        occ = atoi(oenv) < occmax ? atoi(oenv) : occmax;
+        code = atoi(oenv) % 100 < occmax2 ? atoi(oenv) % 100 : occmax2;
+        if (atoi(oenv) >= 100 && occmax3 >= 1) code = 100 + (atoi(oenv) % 100 < occmax3 ? atoi(oenv) % 100 : occmax3);
     } else {
-        // rule: resident warps that cover the arithmetic of an F-tap filter (8 + F in Float64, 10 + 1.5 F in Float32)
+        // rule: two buffers, resident warps that cover the arithmetic of an F-tap filter (8 + F in Float64, 10 + 1.5 F in Float32)
         const double want = sizeof(T) == 8 ? 8.0 + F : 10.0 + 1.5 * F;
         int rule = (int)(want / (threads / 32) + 0.5);
         if (rule < 1) rule = 1;
-        if (rule > occmax) rule = occmax;
-        if (items <= (long)dv.sms * occmax) rule = occmax;      // a launch of at most one wave is latency bound: everything resident
-        int cand[16], nc = 0;
-        for (int c = 1; c <= occmax && c <= 6; ++c) cand[nc++] = c;
-        if (occmax >= 8) cand[nc++] = 8;
-        if (occmax >= 12) cand[nc++] = 12;
-        if (occmax > 6 && occmax != 8 && occmax != 12) cand[nc++] = occmax;
-        const bool big = items >= 4L * dv.sms * occmax && (double)N * (double)n * (L + 2) * sizeof(T) >= 256e6;
-        rc = wx_tuned_choice(WxTuneKey{(const void *)kern, n0, (long)(L - d0), (long)threads, (long)l2hint}, nc, cand, rule, big, s, launch, &occ);
+        if (rule > occmax2) rule = occmax2;
+        if (items <= (long)dv.sms * occmax2) rule = occmax2;    // a launch of at most one wave is latency bound: everything resident
+        int cand[40], nc = 0;
+        for (int pf = 0; pf < 2; ++pf) {
+            const int om = pf ? occmax3 : occmax2;
+            for (int c = 1; c <= om && c <= 6; ++c) cand[nc++] = c + 100 * pf;
+            if (om >= 8) cand[nc++] = 8 + 100 * pf;
+            if (om >= 12) cand[nc++] = 12 + 100 * pf;
+            if (om > 6 && om != 8 && om != 12) cand[nc++] = om + 100 * pf;
+        }
+        const bool big = items >= 4L * dv.sms * occmax2 && (double)N * (double)n * (L + 2) * sizeof(T) >= 256e6;
+        rc = wx_tuned_choice(WxTuneKey{(const void *)kern2, n0, (long)(L - d0), (long)threads, (long)l2hint + 2 * (penv ? 1 : 0)}, nc, cand, rule, big, s,
+                             launch, &code);
         if (rc) return rc;
     }
-    rc = launch(occ);
+    rc = launch(code);
     if (rc) return rc;
     *handled = true;
     return WX_OK;
-}
-
-// three buffers (prefetch of the next node) when they fit, else two
-template <typename T, int F, int KM>
-int wpd1d_launch_tma(T *y, const T *x, long n, int L, long N, int d0, const Taps<T> &t, cudaStream_t s, bool *handled)
-{
-    static const bool nopf = getenv("WX_B200_WPD1D_NO_PREFETCH") != nullptr;      // A-B measurements only
-    if (!nopf) {
-        int rc = wpd1d_launch_tma_pf<T, F, KM, true>(y, x, n, L, N, d0, t, s, handled);
-        if (rc || *handled) return rc;
-    }
-    return wpd1d_launch_tma_pf<T, F, KM, false>(y, x, n, L, N, d0, t, s, handled);
 }
 
 template <typename T>
