@@ -55,6 +55,8 @@ int wx_pool_alloc(void **p, size_t bytes, cudaStream_t s)
 // ---- residency tuning (see wx_common.cuh) ----------------------------------------------------------------
 #include <map>
 #include <tuple>
+#include <vector>
+#include <algorithm>
 static std::mutex wx_tune_mutex;
 static std::map<std::tuple<const void *, int, long, long, long, long>, int> wx_tune_cache;
 
@@ -74,28 +76,51 @@ int wx_tuned_choice(const WxTuneKey &key, int ncand, const int *cand, int fallba
     if (!big_enough || ncand < 2 || (env && atoi(env) == 0)) return WX_OK;
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     if (cudaStreamIsCapturing(s, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) { cudaGetLastError(); return WX_OK; }
-    cudaEvent_t ev[3];
+    cudaEvent_t ev[4];
     for (auto &e : ev) WX_CUDA(cudaEventCreate(&e));
-    float best = 0.f, tfall = -1.f;
     int rc = WX_OK, bestc = fallback;
-    for (int i = 0; i < ncand && rc == WX_OK; ++i) {
-        rc = launch(cand[i]);                                             // warm-up of this residency (also pages the code in)
-        if (rc) break;
+    float best = 0.f;
+    // time `reps` back-to-back launches of one candidate after a warm-up launch; the minimum counts
+    auto measure = [&](int c, int reps, float *tmin) -> int {
+        int r = launch(c);                                                // warm-up of this candidate (also pages the code in)
+        if (r) return r;
         cudaEventRecord(ev[0], s);
-        rc = launch(cand[i]); if (rc) break;
-        cudaEventRecord(ev[1], s);
-        rc = launch(cand[i]); if (rc) break;
-        cudaEventRecord(ev[2], s);
-        if (cudaEventSynchronize(ev[2]) != cudaSuccess) { rc = wx_fail(WX_ECUDA, "autotune: %s", cudaGetErrorString(cudaGetLastError())); break; }
-        float t1 = 0.f, t2 = 0.f;
-        cudaEventElapsedTime(&t1, ev[0], ev[1]);
-        cudaEventElapsedTime(&t2, ev[1], ev[2]);
-        const float t = t1 < t2 ? t1 : t2;
-        if (i == 0 || t < best) { best = t; bestc = cand[i]; }
-        if (cand[i] == fallback) tfall = t;
+        for (int i = 0; i < reps; ++i) {
+            r = launch(c);
+            if (r) return r;
+            cudaEventRecord(ev[i + 1], s);
+        }
+        if (cudaEventSynchronize(ev[reps]) != cudaSuccess) return wx_fail(WX_ECUDA, "autotune: %s", cudaGetErrorString(cudaGetLastError()));
+        *tmin = 1e30f;
+        for (int i = 0; i < reps; ++i) { float t = 0.f; cudaEventElapsedTime(&t, ev[i], ev[i + 1]); if (t < *tmin) *tmin = t; }
+        return WX_OK;
+    };
+    // pass 1: every candidate, two timed launches; pass 2: the three fastest and the caller's rule again, three timed launches each
+    // (launch-to-launch noise is a few per cent and the candidates are often that close)
+    std::vector<std::pair<float, int>> first;
+    for (int i = 0; i < ncand && rc == WX_OK; ++i) {
+        float t = 0.f;
+        rc = measure(cand[i], 2, &t);
+        if (!rc) first.push_back({t, cand[i]});
     }
-    // launch-to-launch noise is a few per cent: leave the caller's rule unless a candidate beats it clearly
-    if (tfall > 0.f && best > 0.97f * tfall) { bestc = fallback; best = tfall; }
+    float tfall = -1.f;
+    if (!rc) {
+        std::sort(first.begin(), first.end());
+        std::vector<int> finalists;
+        for (size_t i = 0; i < first.size() && finalists.size() < 3; ++i) finalists.push_back(first[i].second);
+        bool has_fall = false;
+        for (int c : finalists) has_fall |= (c == fallback);
+        for (int i = 0; i < ncand && !has_fall; ++i) if (cand[i] == fallback) { finalists.push_back(fallback); has_fall = true; }
+        for (size_t i = 0; i < finalists.size() && rc == WX_OK; ++i) {
+            float t = 0.f;
+            rc = measure(finalists[i], 3, &t);
+            if (rc) break;
+            if (i == 0 || t < best) { best = t; bestc = finalists[i]; }
+            if (finalists[i] == fallback) tfall = t;
+        }
+    }
+    // leave the caller's rule unless a candidate beats it clearly
+    if (!rc && tfall > 0.f && best > 0.97f * tfall) { bestc = fallback; best = tfall; }
     for (auto &e : ev) cudaEventDestroy(e);
     if (rc) return rc;
     {
