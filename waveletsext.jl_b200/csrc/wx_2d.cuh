@@ -98,3 +98,16 @@ __device__ __forceinline__ void dwt_dots2(const T *w, const Taps<T> &tp, T &lo0,
     lo0 = a0; lo1 = a1; hi0 = b0; hi1 = b1;
 }
 
+// heap index of quad node (depth d, block row jr, block col jc): children 4i-2 (TL) 4i-1 (TR) 4i (BL) 4i+1 (BR)
+__device__ __forceinline__ long quad_index2(int d, int jr, int jc)
+{
+    long idx = 1;
+    for (int b = d - 1; b >= 0; --b) idx = 4 * idx - 2 + 2 * ((jr >> b) & 1) + ((jc >> b) & 1);
+    return idx;
+}
+__device__ __forceinline__ bool split2(const unsigned char *tree, long ntree, int d, int jr, int jc)
+{
+    if (tree == nullptr) return true;
+    const long i = quad_index2(d, jr, jc);
+    return i <= ntree && tree[i - 1];
+}

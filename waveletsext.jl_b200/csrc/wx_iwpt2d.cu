@@ -37,20 +37,6 @@ __device__ __forceinline__ void idwt_pair(const T *a, const T *b, const Taps<T> 
     ev = e; od = o;
 }
 
-// heap index of quad node (depth d, block row jr, block col jc): children 4i-2 (TL) 4i-1 (TR) 4i (BL) 4i+1 (BR)
-__device__ __forceinline__ long quad_index2(int d, int jr, int jc)
-{
-    long idx = 1;
-    for (int b = d - 1; b >= 0; --b) idx = 4 * idx - 2 + 2 * ((jr >> b) & 1) + ((jc >> b) & 1);
-    return idx;
-}
-__device__ __forceinline__ bool split2(const unsigned char *tree, long ntree, int d, int jr, int jc)
-{
-    if (tree == nullptr) return true;
-    const long i = quad_index2(d, jr, jc);
-    return i <= ntree && tree[i - 1];
-}
-
 // ---------------------------------------------------------------------------------------------------------
 // one level, tiles with halo: node (jr, jc) of depth d in `dst` from its four quadrants in `src`
 // ---------------------------------------------------------------------------------------------------------

@@ -20,6 +20,9 @@ template <typename T>
 int wx_iwpt2d_fused(T *y, const T *xw, T *scratch, long m, long n, int nlev, long N, const unsigned char *dtree, long ntree, const Taps<T> &t,
                     cudaStream_t s, bool *handled);
 template <typename T> int wx_wpd2d_fused(T *y, const T *x, long m, long n, int L, long N, const Taps<T> &t, cudaStream_t s, bool *handled);
+template <typename T>
+int wx_wpt2d_fused(T *y, const T *x, T *scratch, long m, long n, int nlev, long N, const unsigned char *dtree, long ntree, const Taps<T> &t,
+                   cudaStream_t s, bool *handled);
 
 template <typename T>
 int wx_gather_multi(T *out, const T *Xw, long m, long n, int K, long N, const unsigned char *trees, long ntree, cudaStream_t s);
@@ -357,8 +360,9 @@ int tree2d(bool inverse, T *y, const T *x, long m, long n, long N, const unsigne
     }
     DevTree dt; rc = dt.upload(tree, ntree, s); if (rc) return rc;
     const long Nc = chunk_images(m, n, sizeof(T), N);
-    if (inverse && y != x) {
-        // fused inverse (wx_iwpt2d.cu): whole-node kernel for the deep levels, one halo-tile launch per coarse level
+    if (y != x) {
+        // fused kernels (inverse: wx_iwpt2d.cu, forward: wx_wpd2d.cu in tree mode): one halo-tile launch per level whose nodes exceed
+        // shared memory, the whole-node kernel for all deeper levels
         bool full = true;
         { const long nfull = ((1L << (2 * nlev)) - 1) / 3; full = ntree >= nfull; for (long i = 0; full && i < nfull; ++i) full = tree[i] != 0; }
         T *scr; rc = wx_scratch(&scr, (size_t)img * Nc, s); if (rc) return rc;
@@ -366,8 +370,9 @@ int tree2d(bool inverse, T *y, const T *x, long m, long n, long N, const unsigne
         for (long k0 = 0; k0 < N && !rc && all; k0 += Nc) {
             const long nk = (N - k0 < Nc) ? N - k0 : Nc;
             bool handled = false;
-            rc = wx_iwpt2d_fused<T>(y + k0 * img, x + k0 * img, scr, m, n, nlev, nk, full ? nullptr : dt.d, ntree, t, s, &handled);
-            if (!handled) all = false;                   // decided from the shape: the same for every chunk, nothing was launched
+            if (inverse) rc = wx_iwpt2d_fused<T>(y + k0 * img, x + k0 * img, scr, m, n, nlev, nk, full ? nullptr : dt.d, ntree, t, s, &handled);
+            else rc = wx_wpt2d_fused<T>(y + k0 * img, x + k0 * img, scr, m, n, nlev, nk, full ? nullptr : dt.d, ntree, t, s, &handled);
+            if (!handled) all = false;                   // decided from the shape: the same for every chunk; y is recomputed below
         }
         int rcf = wx_scratch_free(scr, s);
         if (rc || rcf) return rc ? rc : rcf;

@@ -30,14 +30,25 @@ constexpr int KSEG = 4;       // column pass of the compile-time-shaped kernels:
 __host__ __device__ constexpr int wx_ld_pairs(int rows) { return ((rows / 2) % 2 == 0) ? rows + 2 : rows; }
 __host__ __device__ constexpr int wx_ld_odd(int rows) { return rows | 1; }
 
+// Where a launch reads its parents and writes its children.  Packet table (wpd): par = x or a level slice of y, out = the next level
+// slice, copy = level 0 of y on the first launch.  By quad tree (wpt, TREE = true): par / out are whole images that ping-pong between the
+// launches, nodes the tree does not split pass through unchanged, and the whole-node kernel stores only what it holds after its last level.
+template <typename T>
+struct Io2D {
+    const T *par; long pstride;              // parents of image k: par + k * pstride
+    T *out; long ostride;                    // children of image k: out + k * ostride (whole-node kernel, table mode: + (l + 1) * img per level)
+    T *copy; long cstride;                   // y[:,:,1] = x target (DWT.jl:176) or nullptr
+    const unsigned char *tree; long ntree;   // TREE: quad tree on the device, nullptr = every node of these levels splits
+};
+
 // ---------------------------------------------------------------------------------------------------------
 // one level, tiles with halo.  Shared memory: P (parent patch, PR rows x PC cols, column-major) and Tm (column-pass output,
 // 2tr rows x PC cols: rows [0,tr) scaling, [tr,2tr) detail).
 // TRC > 0: tile edge known at compile time (tr = tc = TRC): index arithmetic folds to shifts / immediates and the column pass
 // slides a register window down each column (KSEG pairs per thread, lanes across columns).
 // ---------------------------------------------------------------------------------------------------------
-template <typename T, int F, int TRC, int TCC = TRC, int MINB = 3>
-__global__ void __launch_bounds__(kT2, MINB) wpd2d_tile_k(T *__restrict__ y, const T *__restrict__ x, int m, int n, int L, int d, int tr_, int tc_,
+template <typename T, int F, int TRC, int TCC = TRC, int MINB = 3, bool TREE = false>
+__global__ void __launch_bounds__(kT2, MINB) wpd2d_tile_k(Io2D<T> io, int m, int n, int d, int tr_, int tc_,
                                                       Div32 drowtiles, Div32 dtiles_r, Div32 dtiles_c, Div32 dgx, long ntiles, Taps<T> tp)
 {
     const int tr = TRC > 0 ? TRC : tr_, tc = TRC > 0 ? TCC : tc_;
@@ -51,24 +62,25 @@ __global__ void __launch_bounds__(kT2, MINB) wpd2d_tile_k(T *__restrict__ y, con
     T *Tm = P + LDP * PC;
     const int tid = threadIdx.x;
     const int mp = m >> d, np = n >> d, hr = mp / 2, hc = np / 2;
-    const long img = (long)m * n;
-    const bool from_x = (d == 0 && x != nullptr);
+    const bool from_x = io.copy != nullptr;
     const int lane = tid & 31, warp = tid >> 5;
 
     // tile id -> (bx, by) in the order the hardware would schedule a (gx, gy) grid: bx = image * (row tiles of all nodes) fastest,
     // by = column tiles of all nodes; neighbouring CTAs walk down the rows (their halos meet in L2)
-    struct Tile { long k; int nr0, nc0, i0, k0; };
+    struct Tile { long k; int nr0, nc0, i0, k0; bool split; };
     auto decode = [&](long id) {
         const unsigned by = div32((unsigned)id, dgx), bx = (unsigned)id - by * dgx.d;
         const unsigned k = div32(bx, drowtiles), rt = bx - k * drowtiles.d;
         const int jr = (int)div32(rt, dtiles_r), ti = (int)(rt - (unsigned)jr * dtiles_r.d);
         const int jc = (int)div32(by, dtiles_c), tk = (int)(by - (unsigned)jc * dtiles_c.d);
         Tile t; t.k = k; t.nr0 = jr * mp; t.nc0 = jc * np; t.i0 = ti * tr; t.k0 = tk * tc;
+        t.split = !TREE || split2(io.tree, io.ntree, d, jr, jc);
         return t;
     };
     // parent patch of a tile (periodic inside the node) into P, two rows per asynchronous copy; a warp per column
     auto prefetch = [&](const Tile &t) {
-        const T *par = (from_x ? (x + t.k * img) : (y + t.k * img * (L + 1) + (long)d * img)) + (long)t.nc0 * m + t.nr0;
+        if (TREE && !t.split) return;
+        const T *par = io.par + t.k * io.pstride + (long)t.nc0 * m + t.nr0;
         const int PR2 = PR / 2;
         int rr = 2 * t.i0 + 2 * lane; while (rr >= mp) rr -= mp;
         for (int b = warp; b < PC; b += kT2 / 32) {
@@ -92,11 +104,21 @@ __global__ void __launch_bounds__(kT2, MINB) wpd2d_tile_k(T *__restrict__ y, con
     prefetch(cur);
     for (; id < ntiles; id += gridDim.x) {
     const int nr0 = cur.nr0, nc0 = cur.nc0, i0 = cur.i0, k0 = cur.k0;
-    T *yk = y + cur.k * img * (L + 1);
+    const long cur_k = cur.k;
     cp_async_wait_all();
     __syncthreads();                                      // patch complete; every thread is past the previous tile's row pass (Tm free)
+    if (TREE && !cur.split) {                             // leaf of the tree: this tile's share of the node passes through
+        const long org = (long)(nc0 + 2 * k0) * m + nr0 + 2 * i0;
+        const T *sp = io.par + cur.k * io.pstride + org;
+        T *dp = io.out + cur.k * io.ostride + org;
+        if (dp != sp)
+            for (Walk2 w(tid, tr); w.hi < 2 * tc; w.next())
+                *reinterpret_cast<P2 *>(dp + (long)w.hi * m + 2 * w.lo) = *reinterpret_cast<const P2 *>(sp + (long)w.hi * m + 2 * w.lo);
+        if (id + gridDim.x < ntiles) { cur = decode(id + gridDim.x); prefetch(cur); }
+        continue;
+    }
     if (from_x && lane < tr) {                            // y[:,:,1] = x   DWT.jl:176 : the core of the patch (tr <= 32 pairs per column)
-        T *y0 = yk + (long)(nc0 + 2 * k0) * m + nr0 + 2 * i0 + 2 * lane;
+        T *y0 = io.copy + cur.k * io.cstride + (long)(nc0 + 2 * k0) * m + nr0 + 2 * i0 + 2 * lane;
         for (int b = warp; b < 2 * tc; b += kT2 / 32)
             *reinterpret_cast<P2 *>(y0 + b * m) = *reinterpret_cast<const P2 *>(P + b * LDP + 2 * lane);
     }
@@ -170,7 +192,7 @@ __global__ void __launch_bounds__(kT2, MINB) wpd2d_tile_k(T *__restrict__ y, con
     // P is dead from here on: the next tile's patch streams in while this tile's row pass runs
     if (id + gridDim.x < ntiles) { cur = decode(id + gridDim.x); prefetch(cur); }
     // ---- row pass + store: (2tr rows) x (tc output pairs) ----
-    T *ynext = yk + (long)(d + 1) * img + (long)nc0 * m + nr0;
+    T *ynext = io.out + cur_k * io.ostride + (long)nc0 * m + nr0;
     if ((kT2 % R2) == 0 && (tc % KROW) == 0) {
         // a thread owns one row r and KROW consecutive output columns: one window of 2*KROW+F-2 samples slides along the row
         const int r = tid % R2;
@@ -261,8 +283,14 @@ __device__ __forceinline__ void load_window_pairs(T *win, const T *src, int star
 // One level of the whole-node kernel with EVERYTHING known at compile time: block edge BE, current node edge MPL (both powers
 // of two, MPL/2 a multiple of KSEG and KROW).  Node / offset splits are shifts, periodic wraps are masks (any number of wraps,
 // so filters longer than the node need no special case), and the integer work per output drops to a few instructions.
-template <typename T, int F, int BE, int MPL>
-__device__ __forceinline__ void wpd2d_block_level_ct(T *__restrict__ A, T *__restrict__ Tm, const Taps<T> &tp, int tid)
+// node (ir, ic) of depth l inside a block whose first node of that depth is (jrb, jcb): does the tree split it?
+struct Split2 {
+    const unsigned char *tree; long ntree; int l, jrb, jcb;
+    __device__ __forceinline__ bool operator()(int ir, int ic) const { return tree == nullptr || split2(tree, ntree, l, jrb + ir, jcb + ic); }
+};
+
+template <typename T, int F, int BE, int MPL, bool TREE>
+__device__ __forceinline__ void wpd2d_block_level_ct(T *__restrict__ A, T *__restrict__ Tm, const Taps<T> &tp, int tid, const Split2 &sp)
 {
     using P2 = typename Pair<T>::type;
     constexpr int S = (F - 2) / 2, LDA = wx_ld_pairs(BE), LDT = wx_ld_odd(BE), KROW = wx_krow(F);
@@ -271,6 +299,7 @@ __device__ __forceinline__ void wpd2d_block_level_ct(T *__restrict__ A, T *__res
     for (int t = tid; t < (BE / 2 / KSEG) * BE; t += kT2) {
         const int sg = t / BE, c = t % BE, ig0 = sg * KSEG;
         const int r0 = (ig0 / HR) * MPL, il0 = ig0 % HR;
+        if (TREE && !sp(ig0 / HR, c / MPL)) continue;
         const T *src = A + c * LDA + r0;
         T win[WS];
 #pragma unroll
@@ -293,6 +322,7 @@ __device__ __forceinline__ void wpd2d_block_level_ct(T *__restrict__ A, T *__res
         const int r = tid % BE;
         for (int g = tid / BE; g < BE / (2 * KROW); g += kT2 / BE) {
             const int kg0 = KROW * g, c0 = (kg0 / HR) * MPL, kl0 = kg0 % HR;
+            if (TREE && !sp(r / MPL, kg0 / HR)) continue;
             const T *src = Tm + c0 * LDT + r;
             T win[WR];
 #pragma unroll
@@ -311,9 +341,8 @@ __device__ __forceinline__ void wpd2d_block_level_ct(T *__restrict__ A, T *__res
 }
 
 // BE > 0: square block of edge BE known at compile time (padded leading dimensions, sliding-window column pass)
-template <typename T, int F, int BE>
-__global__ void __launch_bounds__(kT2, 3) wpd2d_block_k(T *__restrict__ y, const T *__restrict__ x, int m, int n, int L, int db, int dend,
-                                                       Taps<T> tp)
+template <typename T, int F, int BE, bool TREE = false>
+__global__ void __launch_bounds__(kT2, 3) wpd2d_block_k(Io2D<T> io, int m, int n, int db, int dend, Taps<T> tp)
 {
     using P2 = typename Pair<T>::type;
     constexpr int S = (F - 2) / 2, KROW = wx_krow(F);
@@ -327,10 +356,10 @@ __global__ void __launch_bounds__(kT2, 3) wpd2d_block_k(T *__restrict__ y, const
     const unsigned k = blockIdx.x >> db;
     const int jr = (int)(blockIdx.x & ((1u << db) - 1)), jc = (int)blockIdx.y;
     const long img = (long)m * n;
-    T *yk = y + (long)k * img * (L + 1);
-    const bool from_x = (db == 0 && x != nullptr);
+    T *yk = io.out + (long)k * io.ostride;
+    const bool from_x = io.copy != nullptr;
     const long org = (long)(jc * BC) * m + jr * BR;       // block origin in the image
-    const T *par = (from_x ? (x + (long)k * img) : (yk + (long)db * img)) + org;
+    const T *par = io.par + (long)k * io.pstride + org;
     const int BR2 = BR / 2;
     const int lane = tid & 31, warp = tid >> 5;
     // global <-> shared copies of the block: lanes walk the row pairs of a column when a column is at most one warp wide
@@ -342,19 +371,22 @@ __global__ void __launch_bounds__(kT2, 3) wpd2d_block_k(T *__restrict__ y, const
     cp_async_wait_all();
     __syncthreads();
     if (from_x) {                                         // y[:,:,1] = x   DWT.jl:176
-        T *y0 = yk + org;
+        T *y0 = io.copy + (long)k * io.cstride + org;
         if (colwarp) { for (int b = cb0; b < BC; b += cbs) *reinterpret_cast<P2 *>(y0 + b * m + ca) = *reinterpret_cast<const P2 *>(A + b * LDA + ca); }
         else { for (Walk2 w(tid, BR2); w.hi < BC; w.next()) *reinterpret_cast<P2 *>(y0 + w.hi * m + 2 * w.lo) = *reinterpret_cast<const P2 *>(A + w.hi * LDA + 2 * w.lo); }
     }
     for (int l = db; l < dend; ++l) {
         const int mpl = m >> l, npl = n >> l, hr = mpl / 2, hc = npl / 2;
+        const Split2 sp{TREE ? io.tree : nullptr, io.ntree, l, jr << (l - db), jc << (l - db)};
         if (BE == 64 && kT2 % 64 == 0 && mpl == npl && mpl >= 16) {
             // compile-time-shaped levels (node edge 64, 32, 16): both passes with constant geometry
-            if (mpl == 64) wpd2d_block_level_ct<T, F, (BE > 0 ? BE : 64), 64>(A, Tm, tp, tid);
-            else if (mpl == 32) wpd2d_block_level_ct<T, F, (BE > 0 ? BE : 64), 32>(A, Tm, tp, tid);
-            else wpd2d_block_level_ct<T, F, (BE > 0 ? BE : 64), 16>(A, Tm, tp, tid);
-            T *ynext = yk + (long)(l + 1) * img + org;
-            for (int b = cb0; b < BC; b += cbs) *reinterpret_cast<P2 *>(ynext + b * m + ca) = *reinterpret_cast<const P2 *>(A + b * LDA + ca);
+            if (mpl == 64) wpd2d_block_level_ct<T, F, (BE > 0 ? BE : 64), 64, TREE>(A, Tm, tp, tid, sp);
+            else if (mpl == 32) wpd2d_block_level_ct<T, F, (BE > 0 ? BE : 64), 32, TREE>(A, Tm, tp, tid, sp);
+            else wpd2d_block_level_ct<T, F, (BE > 0 ? BE : 64), 16, TREE>(A, Tm, tp, tid, sp);
+            if (!TREE) {
+                T *ynext = yk + (long)(l + 1) * img + org;
+                for (int b = cb0; b < BC; b += cbs) *reinterpret_cast<P2 *>(ynext + b * m + ca) = *reinterpret_cast<const P2 *>(A + b * LDA + ca);
+            }
             continue;
         }
         // ---- column pass A -> Tm, per node: scaling rows on top, detail rows below (shift resolved here) ----
@@ -365,6 +397,7 @@ __global__ void __launch_bounds__(kT2, 3) wpd2d_block_k(T *__restrict__ y, const
             for (int t = tid; t < (BR2 / KSEG) * BC; t += kT2) {
                 const int sg = t / BC, c = t - sg * BC, ig0 = sg * KSEG;
                 const int jn = dq.div(ig0), il0 = ig0 - jn * hr, r0 = jn * mpl;
+                if (TREE && !sp(jn, c / npl)) continue;
                 T win[WS];
                 load_window_pairs<T, WS>(win, A + c * LDA + r0, 2 * il0, mpl);
                 T *dst = Tm + c * LDT + r0;
@@ -384,16 +417,19 @@ __global__ void __launch_bounds__(kT2, 3) wpd2d_block_k(T *__restrict__ y, const
                 const int b = w.hi;
                 T lo[2], hi[2];
                 int il[2], r0[2];
+                bool on[2];
 #pragma unroll
                 for (int t = 0; t < 2; ++t) {
                     const int ig = w.lo + t * (BR2 / 2), jn = dq.div(ig);
                     il[t] = ig - jn * hr; r0[t] = jn * mpl;
+                    on[t] = !TREE || sp(jn, b / npl);
                     T win[F];
                     load_window_pairs<T, F>(win, A + b * LDA + r0[t], 2 * il[t], mpl);
                     dwt_dots<T, F>(win, tp, lo[t], hi[t]);
                 }
 #pragma unroll
                 for (int t = 0; t < 2; ++t) {
+                    if (!on[t]) continue;
                     T *dst = Tm + b * LDT + r0[t];
                     dst[il[t]] = lo[t];
                     int ih = il[t] + S; if (ih >= hr) ih %= hr;
@@ -404,6 +440,7 @@ __global__ void __launch_bounds__(kT2, 3) wpd2d_block_k(T *__restrict__ y, const
             const FastDiv dq(hr);
             for (Walk2 w(tid, BR2); w.hi < BC; w.next()) {
                 const int b = w.hi, jn = dq.div(w.lo), il = w.lo - jn * hr, r0 = jn * mpl;
+                if (TREE && !sp(jn, b / npl)) continue;
                 T win[F];
                 load_window_pairs<T, F>(win, A + b * LDA + r0, 2 * il, mpl);
                 T lo, hi;
@@ -420,6 +457,7 @@ __global__ void __launch_bounds__(kT2, 3) wpd2d_block_k(T *__restrict__ y, const
             const int r = tid % BR;
             for (int g = tid / BR; g < BC / (2 * KROW); g += kT2 / BR) {
                 const int kg0 = KROW * g, jn = kg0 / hc, kl0 = kg0 - jn * hc, c0 = jn * npl;
+                if (TREE && !sp(r / mpl, jn)) continue;
                 T win[2 * KROW + F - 2];
                 const T *src = Tm + c0 * LDT + r;
 #pragma unroll
@@ -439,6 +477,7 @@ __global__ void __launch_bounds__(kT2, 3) wpd2d_block_k(T *__restrict__ y, const
             const FastDiv dq(hc / 2);
             for (Walk2 w(tid, BR); w.hi < BC / 4; w.next()) {
                 const int r = w.lo, jn = dq.div(w.hi), kl = 2 * (w.hi - jn * (hc / 2)), c0 = jn * npl;
+                if (TREE && !sp(r / mpl, jn)) continue;
                 T win[F + 2];
                 load_window<T, F + 2>(win, Tm + c0 * LDT + r, 2 * kl, npl, LDT);
                 T lo0, hi0, lo1, hi1;
@@ -454,6 +493,7 @@ __global__ void __launch_bounds__(kT2, 3) wpd2d_block_k(T *__restrict__ y, const
             const FastDiv dq(hc);
             for (Walk2 w(tid, BR); w.hi < BC / 2; w.next()) {
                 const int r = w.lo, jn = dq.div(w.hi), kl = w.hi - jn * hc, c0 = jn * npl;
+                if (TREE && !sp(r / mpl, jn)) continue;
                 T win[F];
                 load_window<T, F>(win, Tm + c0 * LDT + r, 2 * kl, npl, LDT);
                 T lo, hi;
@@ -465,10 +505,16 @@ __global__ void __launch_bounds__(kT2, 3) wpd2d_block_k(T *__restrict__ y, const
         }
         __syncthreads();
         // ---- level l+1 slice ----
+        if (TREE) continue;
         T *ynext = yk + (long)(l + 1) * img + org;
         if (colwarp) { for (int b = cb0; b < BC; b += cbs) *reinterpret_cast<P2 *>(ynext + b * m + ca) = *reinterpret_cast<const P2 *>(A + b * LDA + ca); }
         else { for (Walk2 w(tid, BR2); w.hi < BC; w.next()) *reinterpret_cast<P2 *>(ynext + w.hi * m + 2 * w.lo) = *reinterpret_cast<const P2 *>(A + w.hi * LDA + 2 * w.lo); }
         // the next column pass only reads A (complete after the barrier above) and writes Tm (free): no barrier needed here
+    }
+    if (TREE) {                                           // by tree: only the coefficients of the last level leave
+        T *yo = yk + org;
+        if (colwarp) { for (int b = cb0; b < BC; b += cbs) *reinterpret_cast<P2 *>(yo + b * m + ca) = *reinterpret_cast<const P2 *>(A + b * LDA + ca); }
+        else { for (Walk2 w(tid, BR2); w.hi < BC; w.next()) *reinterpret_cast<P2 *>(yo + w.hi * m + 2 * w.lo) = *reinterpret_cast<const P2 *>(A + w.hi * LDA + 2 * w.lo); }
     }
 }
 
@@ -584,14 +630,34 @@ static int largest_divisor_le(long v, int cap)
     return best;
 }
 
-template <typename T, int F>
-int wpd2d_run_chunk(T *y, const T *x, long m, long n, int L, long N, const Taps<T> &t, cudaStream_t s)
+// TREE = false: y = packet table (m,n,L+1,N).  TREE = true: y = coefficient images (m,n,N) along the quad tree of depth L (dtree on the
+// device, nullptr = complete), scratch = N more images; the launches ping-pong between y and scratch so that the last one writes y.
+template <typename T, int F, bool TREE>
+int wpd2d_run_chunk(T *y, const T *x, T *scratch, long m, long n, int L, long N, const unsigned char *dtree, long ntree, const Taps<T> &t,
+                    cudaStream_t s)
 {
     WxDev dv; int rc = wx_devinfo(dv); if (rc) return rc;
     // depth from which a whole node fits the block kernel's two buffers (64 KB keeps three CTAs per SM)
     const size_t budget = 65536;
+    const long img = m * n;
     int db = 0;
     while (db < L && (size_t)2 * (m >> db) * (n >> db) * sizeof(T) > budget) ++db;
+    int left = db + (db < L ? 1 : 0);                          // launches to go (TREE: ping-pong parity)
+    const T *cur = x;
+    auto level_io = [&](int d) {
+        Io2D<T> io;
+        if (TREE) {
+            T *dst = (left % 2 == 1) ? y : scratch;
+            io.par = cur; io.pstride = img; io.out = dst; io.ostride = img; io.copy = nullptr; io.cstride = 0; io.tree = dtree; io.ntree = ntree;
+            cur = dst;
+        } else {
+            io.par = d == 0 ? x : y + (long)d * img; io.pstride = d == 0 ? img : img * (L + 1);
+            io.out = y + (long)(d + 1) * img; io.ostride = img * (L + 1);
+            io.copy = d == 0 ? y : nullptr; io.cstride = img * (L + 1); io.tree = nullptr; io.ntree = 0;
+        }
+        --left;
+        return io;
+    };
     static const char *env = getenv("WX_B200_WPD2D_TILE");      // measurement knob: tile edge of the halo kernel
     const int cap = (env && atoi(env) >= 1 && atoi(env) <= 32) ? atoi(env) : 32;     // the kernel maps one lane per row pair: tr <= 32
     for (int d = 0; d < db; ++d) {
@@ -599,7 +665,7 @@ int wpd2d_run_chunk(T *y, const T *x, long m, long n, int L, long N, const Taps<
         // Narrow tiles (32 x 16, knob WX_B200_WPD2D_NARROW): 41 KB instead of 76 KB of shared memory and a 64-register build, i.e. up
         // to five resident CTAs instead of three for the latency-bound tile pass, at the price of a wider relative halo
         static const char *nenv = getenv("WX_B200_WPD2D_NARROW");
-        const int narrow = nenv ? atoi(nenv) : 0;
+        const int narrow = (nenv && !TREE) ? atoi(nenv) : 0;
         const int tr = largest_divisor_le(hr, cap);
         int tc = largest_divisor_le(hc, cap);
         if (narrow && tr == 32 && tc == 32) tc = 16;
@@ -618,18 +684,19 @@ int wpd2d_run_chunk(T *y, const T *x, long m, long n, int L, long N, const Taps<
         static const char *penv = getenv("WX_B200_WPD2D_PERSIST");
         const int per_sm = penv ? atoi(penv) : 0;
         const long ctas = per_sm > 0 && ntiles > (long)dv.sms * per_sm ? (long)dv.sms * per_sm : ntiles;
-        if (tr == 32 && tc == 16) {
-            auto kern = wpd2d_tile_k<T, F, 32, 16, 4>;
+        const Io2D<T> io = level_io(d);
+        if (tr == 32 && tc == 16 && !TREE) {
+            auto kern = wpd2d_tile_k<T, F, 32, 16, 4, false>;
             WX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            kern<<<(unsigned)ctas, kT2, smem, s>>>(y, d == 0 ? x : nullptr, (int)m, (int)n, L, d, tr, tc, drt, dtr, dtc, dgx, ntiles, t);
+            kern<<<(unsigned)ctas, kT2, smem, s>>>(io, (int)m, (int)n, d, tr, tc, drt, dtr, dtc, dgx, ntiles, t);
         } else if (tr == 32 && tc == 32) {
-            auto kern = wpd2d_tile_k<T, F, 32>;
+            auto kern = wpd2d_tile_k<T, F, 32, 32, 3, TREE>;
             WX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            kern<<<(unsigned)ctas, kT2, smem, s>>>(y, d == 0 ? x : nullptr, (int)m, (int)n, L, d, tr, tc, drt, dtr, dtc, dgx, ntiles, t);
+            kern<<<(unsigned)ctas, kT2, smem, s>>>(io, (int)m, (int)n, d, tr, tc, drt, dtr, dtc, dgx, ntiles, t);
         } else {
-            auto kern = wpd2d_tile_k<T, F, 0>;
+            auto kern = wpd2d_tile_k<T, F, 0, 0, 3, TREE>;
             WX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            kern<<<(unsigned)ctas, kT2, smem, s>>>(y, d == 0 ? x : nullptr, (int)m, (int)n, L, d, tr, tc, drt, dtr, dtc, dgx, ntiles, t);
+            kern<<<(unsigned)ctas, kT2, smem, s>>>(io, (int)m, (int)n, d, tr, tc, drt, dtr, dtc, dgx, ntiles, t);
         }
         WX_LAUNCHED();
     }
@@ -638,14 +705,16 @@ int wpd2d_run_chunk(T *y, const T *x, long m, long n, int L, long N, const Taps<
         const size_t smem = shaped ? (size_t)(wx_ld_pairs(64) + wx_ld_odd(64)) * 64 * sizeof(T) : (size_t)2 * (m >> db) * (n >> db) * sizeof(T);
         const long gx = (1L << db) * N, gy = 1L << db;
         if (gx >= (1L << 31) || gy > 65535) return wx_fail(WX_EUNSUPPORTED, "wpd 2-D: too many blocks for one launch");
-        if ((m >> db) == 64 && (n >> db) == 64) {
-            auto kern = wpd2d_block_k<T, F, 64>;
+        Io2D<T> io = level_io(db);
+        if (!TREE) { io.out = y; }                            // the whole-node kernel adds (l + 1) * img per level itself
+        if (shaped) {
+            auto kern = wpd2d_block_k<T, F, 64, TREE>;
             WX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            kern<<<dim3((unsigned)gx, (unsigned)gy), kT2, smem, s>>>(y, db == 0 ? x : nullptr, (int)m, (int)n, L, db, L, t);
+            kern<<<dim3((unsigned)gx, (unsigned)gy), kT2, smem, s>>>(io, (int)m, (int)n, db, L, t);
         } else {
-            auto kern = wpd2d_block_k<T, F, 0>;
+            auto kern = wpd2d_block_k<T, F, 0, TREE>;
             WX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            kern<<<dim3((unsigned)gx, (unsigned)gy), kT2, smem, s>>>(y, db == 0 ? x : nullptr, (int)m, (int)n, L, db, L, t);
+            kern<<<dim3((unsigned)gx, (unsigned)gy), kT2, smem, s>>>(io, (int)m, (int)n, db, L, t);
         }
         WX_LAUNCHED();
     }
@@ -666,7 +735,7 @@ int wpd2d_run(T *y, const T *x, long m, long n, int L, long N, const Taps<T> &t,
     const long img = m * n;
     for (long k0 = 0; k0 < N; k0 += chunk) {
         const long nk = (N - k0 < chunk) ? N - k0 : chunk;
-        int rc = wpd2d_run_chunk<T, F>(y + k0 * img * (L + 1), x + k0 * img, m, n, L, nk, t, s);
+        int rc = wpd2d_run_chunk<T, F, false>(y + k0 * img * (L + 1), x + k0 * img, nullptr, m, n, L, nk, nullptr, 0, t, s);
         if (rc) return rc;
     }
     return WX_OK;
@@ -702,3 +771,29 @@ int wx_wpd2d_fused(T *y, const T *x, long m, long n, int L, long N, const Taps<T
 }
 template int wx_wpd2d_fused<double>(double *, const double *, long, long, int, long, const Taps<double> &, cudaStream_t, bool *);
 template int wx_wpd2d_fused<float>(float *, const float *, long, long, int, long, const Taps<float> &, cudaStream_t, bool *);
+
+// x(m,n,N) -> y(m,n,N) along the quad tree of depth nlev (wpt! 2-D DWT.jl:500-548); dtree = device copy of the tree or nullptr for a
+// complete one; scratch: N images.  One halo-tile launch per level whose nodes exceed shared memory, then the whole-node kernel for all
+// deeper levels: min(nlev, db) + 1 round trips through HBM instead of the packet table + leaf gather.
+template <typename T>
+int wx_wpt2d_fused(T *y, const T *x, T *scratch, long m, long n, int nlev, long N, const unsigned char *dtree, long ntree, const Taps<T> &t,
+                   cudaStream_t s, bool *handled)
+{
+    *handled = false;
+    static const bool off = getenv("WX_B200_NO_FUSED_WPD2D") != nullptr || getenv("WX_B200_WPT2D_TABLE") != nullptr;
+    if (off || nlev < 1 || nlev > 30 || N < 1 || m * n >= (1L << 31) || y == x) return WX_OK;
+    if (((((uintptr_t)y) | ((uintptr_t)x) | ((uintptr_t)scratch)) & 15) != 0) return WX_OK;
+    if ((m >> (nlev - 1)) % 2 != 0 || (n >> (nlev - 1)) % 2 != 0) return WX_OK;
+    int rc;
+#define WX_2D_CASE(FF) case FF: rc = wpd2d_run_chunk<T, FF, true>(y, x, scratch, m, n, nlev, N, dtree, ntree, t, s); break;
+    switch (t.F) {
+        WX_2D_CASE(2) WX_2D_CASE(4) WX_2D_CASE(6) WX_2D_CASE(8) WX_2D_CASE(10) WX_2D_CASE(12) WX_2D_CASE(16) WX_2D_CASE(20)
+        default: return WX_OK;
+    }
+#undef WX_2D_CASE
+    if (rc == WX_EUNSUPPORTED) return WX_OK;          // y is recomputed from x by the caller's other paths
+    if (rc == WX_OK) *handled = true;
+    return rc;
+}
+template int wx_wpt2d_fused<double>(double *, const double *, double *, long, long, int, long, const unsigned char *, long, const Taps<double> &, cudaStream_t, bool *);
+template int wx_wpt2d_fused<float>(float *, const float *, float *, long, long, int, long, const unsigned char *, long, const Taps<float> &, cudaStream_t, bool *);
