@@ -331,6 +331,7 @@ def main():
     ms_per_step = maxr(total_ms) / a.steps
     value = n * N * world / (ms_per_step * 1e-3) / 1e9
     y_head = y[:4].clone()
+    y_tail = y[N - 4:N].clone()
 
     # ---- e2e: wpdall through the host-buffer C-ABI call (pinned host arrays, copies inside the timed region) ----------------
     orig_aff = os.sched_getaffinity(0)
@@ -393,12 +394,14 @@ def main():
             for _ in range(a.e2e_steps):
                 wx.host.wpdall_host(xh_np, wt, L, out=yh_np, device=local)          # synchronous call
             el = maxr(time.perf_counter() - t0)
-            ok = bool(torch.equal(yh[:4].to(dev), y_head))
+            ok = bool(torch.equal(yh[:4].to(dev), y_head)) and (Ne != N or bool(torch.equal(yh[Ne - 4:Ne].to(dev), y_tail)))
+            host_l0 = os.environ.get("WX_B200_HOST_LEVEL0", "1")[:1] != "0"         # wx_host.cu: level 0 (= x) is filled from the host copy of x
             e2e = {"value": a.e2e_steps * Ne * n * world / el / 1e9, "unit": "GSamples/s", "h2d_bytes_per_step": Ne * n * esz,
-                   "d2h_bytes_per_step": Ne * (L + 1) * n * esz, "steps": a.e2e_steps, "signals_per_step": Ne,
+                   "d2h_bytes_per_step": Ne * (L if host_l0 else L + 1) * n * esz, "steps": a.e2e_steps, "signals_per_step": Ne,
                    "matches_device_path": ok, "timer": "host wall clock around the synchronous C-ABI call (wx_wpdall_host), max over ranks",
                    "numa": numa, "pcie_probe": probe,
-                   "bound": "PCIe / host DRAM: the packet table is 13x the input, so every step pulls (L+1)*n*N*8 bytes back to the host"}
+                   "level0": "rows y[:,0,:] = x are written by host threads from the caller's x while levels 1..L cross PCIe" if host_l0 else "whole table over PCIe",
+                   "bound": "PCIe / host DRAM: the packet table is 13x the input, so every step pulls L*n*N*8 bytes back to the host"}
             del xh, yh, xh_np, yh_np
 
     # ---- e2e_pipeline: x (host) -> wpdall -> bestbasistree(JBB) -> getbasiscoefall -> coefficients (host), one C-ABI call ---

@@ -3,10 +3,23 @@
 // (H2D -> fused kernel -> D2H), so copies in both directions overlap the kernel of the neighbouring chunks.
 // Reference: wpdall dwt/dwt_all.jl:260-282 (x and y are host arrays there).
 #include "wx_common.cuh"
+#include <cstdlib>
+#include <cstring>
+#include <thread>
+#include <vector>
 
 namespace {
 
 constexpr int kSlots = 3;
+
+// Level 0 of the packet table is a bit copy of x (y[:,1,k] = x[:,k], DWT.jl:141) and x already lives in host memory: a few host
+// threads fill those rows straight from x while the DMA engine brings back levels 1..L only, so the PCIe-bound call moves
+// L/(L+1) of the table instead of all of it.
+template <typename T>
+void level0_rows(T *y, const T *x, long n, int L, long k0, long k1)
+{
+    for (long k = k0; k < k1; ++k) std::memcpy(y + (size_t)k * (L + 1) * n, x + (size_t)k * n, (size_t)n * sizeof(T));
+}
 
 template <typename T>
 int wpdall_host(T *y, const T *x, long n, int L, long N, const double *h, const double *g, int F, long chunk,
@@ -46,6 +59,21 @@ int wpdall_host(T *y, const T *x, long n, int L, long N, const double *h, const 
             return wx_fail(e == cudaErrorMemoryAllocation ? WX_ENOMEM : WX_ECUDA, "wpdall_host setup: %s", cudaGetErrorString(e));
         }
     }
+    // level 0 on the host (see level0_rows); WX_B200_HOST_LEVEL0=0 sends the whole table over PCIe instead (A-B measurements)
+    static const char *l0env = getenv("WX_B200_HOST_LEVEL0");
+    const bool host_l0 = !(l0env && l0env[0] == '0') && (const void *)y != (const void *)x;
+    std::vector<std::thread> workers;
+    if (host_l0) {
+        unsigned hc = std::thread::hardware_concurrency();
+        long nw = (size_t)N * in_b >= ((size_t)64 << 20) ? (hc >= 8 ? 4 : (hc >= 2 ? 2 : 1)) : 1;
+        if (nw > N) nw = N;
+        try {
+            for (long w = 0; w < nw; ++w) workers.emplace_back(level0_rows<T>, y, x, n, L, N * w / nw, N * (w + 1) / nw);
+        } catch (...) {                                       // no thread could be started: the rest is copied here at the end
+        }
+        if (workers.empty()) level0_rows<T>(y, x, n, L, 0, N);
+        else if ((long)workers.size() < nw) level0_rows<T>(y, x, n, L, N * (long)workers.size() / nw, N);
+    }
     for (long c = 0; c < nchunks && rc == WX_OK; ++c) {
         const int sl = (int)(c % slots);
         const long k0 = c * chunk, nk = (N - k0 < chunk) ? N - k0 : chunk;
@@ -53,13 +81,15 @@ int wpdall_host(T *y, const T *x, long n, int L, long N, const double *h, const 
         if (e != cudaSuccess) { rc = wx_fail(WX_ECUDA, "H2D: %s", cudaGetErrorString(e)); break; }
         rc = kern(dy[sl], dx[sl], n, L, nk, h, g, F, (void *)st[sl]);
         if (rc) break;
-        e = cudaMemcpyAsync(y + k0 * n * (L + 1), dy[sl], out_b * (size_t)nk, cudaMemcpyDeviceToHost, st[sl]);
+        if (!host_l0) e = cudaMemcpyAsync(y + k0 * n * (L + 1), dy[sl], out_b * (size_t)nk, cudaMemcpyDeviceToHost, st[sl]);
+        else if (L > 0) e = cudaMemcpy2DAsync(y + k0 * n * (L + 1) + n, out_b, dy[sl] + n, out_b, in_b * (size_t)L, (size_t)nk, cudaMemcpyDeviceToHost, st[sl]);
         if (e != cudaSuccess) { rc = wx_fail(WX_ECUDA, "D2H: %s", cudaGetErrorString(e)); break; }
     }
     for (int i = 0; i < slots && rc == WX_OK; ++i) {
         cudaError_t e = cudaStreamSynchronize(st[i]);
         if (e != cudaSuccess) rc = wx_fail(WX_ECUDA, "sync: %s", cudaGetErrorString(e));
     }
+    for (auto &w : workers) w.join();
     cleanup();
     return rc;
 }

@@ -24,6 +24,12 @@ namespace {
 // window stays in registers (F = 16 / 20 spilled 1.7 - 2.3 KB per thread with 8)
 __host__ __device__ constexpr int wx_krow(int F) { return F >= 12 ? 4 : 8; }
 constexpr int KSEG = 4;       // column pass of the compile-time-shaped kernels: output pairs per thread (window slides down the column)
+// Whole-node kernel, WIDE variant (long filters in Float64): windows of 8 output pairs in both passes -- (16 + F - 2) / 16 loads per input
+// instead of (8 + F - 2) / 8 -- under a two-CTA launch bound (128 registers), because the 80 registers of three resident CTAs spill them
+// (ptxas: 256 - 784 B for 10 - 20 taps).
+template <int F, bool WIDE> struct BlkCfg {
+    static constexpr int KS = WIDE ? 8 : KSEG, KR = WIDE ? 8 : wx_krow(F), MINB = WIDE ? 2 : 3;
+};
 
 // leading dimensions of the shared-memory arrays.  Column pass: lanes walk COLUMNS and read element pairs, conflict free when
 // (ld / 2) is odd; its outputs are single elements written by lanes that walk columns, conflict free when ld is odd.
@@ -289,11 +295,11 @@ struct Split2 {
     __device__ __forceinline__ bool operator()(int ir, int ic) const { return tree == nullptr || split2(tree, ntree, l, jrb + ir, jcb + ic); }
 };
 
-template <typename T, int F, int BE, int MPL, bool TREE>
+template <typename T, int F, int BE, int MPL, bool TREE, bool WIDE>
 __device__ __forceinline__ void wpd2d_block_level_ct(T *__restrict__ A, T *__restrict__ Tm, const Taps<T> &tp, int tid, const Split2 &sp)
 {
     using P2 = typename Pair<T>::type;
-    constexpr int S = (F - 2) / 2, LDA = wx_ld_pairs(BE), LDT = wx_ld_odd(BE), KROW = wx_krow(F);
+    constexpr int S = (F - 2) / 2, LDA = wx_ld_pairs(BE), LDT = wx_ld_odd(BE), KROW = BlkCfg<F, WIDE>::KR, KSEG = BlkCfg<F, WIDE>::KS;
     constexpr int HR = MPL / 2, WS = 2 * KSEG + F - 2, WR = 2 * KROW + F - 2;
     // ---- column pass A -> Tm ----
     for (int t = tid; t < (BE / 2 / KSEG) * BE; t += kT2) {
@@ -341,8 +347,8 @@ __device__ __forceinline__ void wpd2d_block_level_ct(T *__restrict__ A, T *__res
 }
 
 // BE > 0: square block of edge BE known at compile time (padded leading dimensions, sliding-window column pass)
-template <typename T, int F, int BE, bool TREE = false>
-__global__ void __launch_bounds__(kT2, 3) wpd2d_block_k(Io2D<T> io, int m, int n, int db, int dend, Taps<T> tp)
+template <typename T, int F, int BE, bool TREE = false, bool WIDE = false>
+__global__ void __launch_bounds__(kT2, (BlkCfg<F, WIDE>::MINB)) wpd2d_block_k(Io2D<T> io, int m, int n, int db, int dend, Taps<T> tp)
 {
     using P2 = typename Pair<T>::type;
     constexpr int S = (F - 2) / 2, KROW = wx_krow(F);
@@ -380,9 +386,9 @@ __global__ void __launch_bounds__(kT2, 3) wpd2d_block_k(Io2D<T> io, int m, int n
         const Split2 sp{TREE ? io.tree : nullptr, io.ntree, l, jr << (l - db), jc << (l - db)};
         if (BE == 64 && kT2 % 64 == 0 && mpl == npl && mpl >= 16) {
             // compile-time-shaped levels (node edge 64, 32, 16): both passes with constant geometry
-            if (mpl == 64) wpd2d_block_level_ct<T, F, (BE > 0 ? BE : 64), 64, TREE>(A, Tm, tp, tid, sp);
-            else if (mpl == 32) wpd2d_block_level_ct<T, F, (BE > 0 ? BE : 64), 32, TREE>(A, Tm, tp, tid, sp);
-            else wpd2d_block_level_ct<T, F, (BE > 0 ? BE : 64), 16, TREE>(A, Tm, tp, tid, sp);
+            if (mpl == 64) wpd2d_block_level_ct<T, F, (BE > 0 ? BE : 64), 64, TREE, WIDE>(A, Tm, tp, tid, sp);
+            else if (mpl == 32) wpd2d_block_level_ct<T, F, (BE > 0 ? BE : 64), 32, TREE, WIDE>(A, Tm, tp, tid, sp);
+            else wpd2d_block_level_ct<T, F, (BE > 0 ? BE : 64), 16, TREE, WIDE>(A, Tm, tp, tid, sp);
             if (!TREE) {
                 T *ynext = yk + (long)(l + 1) * img + org;
                 for (int b = cb0; b < BC; b += cbs) *reinterpret_cast<P2 *>(ynext + b * m + ca) = *reinterpret_cast<const P2 *>(A + b * LDA + ca);
@@ -707,7 +713,15 @@ int wpd2d_run_chunk(T *y, const T *x, T *scratch, long m, long n, int L, long N,
         if (gx >= (1L << 31) || gy > 65535) return wx_fail(WX_EUNSUPPORTED, "wpd 2-D: too many blocks for one launch");
         Io2D<T> io = level_io(db);
         if (!TREE) { io.out = y; }                            // the whole-node kernel adds (l + 1) * img per level itself
-        if (shaped) {
+        // measured (profiles/r2_wpd2d_blkwide_ab.jsonl, 1024 x 512^2): Float64 10 / 12 / 16 / 20 taps 5.12 / 5.74 / 7.13 / 8.91 -> 4.89 / 4.96 / 5.83 / 7.40 ms,
+        // Float32 12 / 16 / 20 taps 3.11 / 3.69 / 4.32 -> 3.06 / 3.41 / 4.12 ms, Float32 10 taps loses (2.86 -> 2.94 ms)
+        static const char *wenv = getenv("WX_B200_WPD2D_BLKWIDE");        // A-B knob: 0 = never, 1 = every filter from 10 taps, unset = the rule
+        const bool wide = F >= 10 && (wenv ? atoi(wenv) != 0 : (sizeof(T) == 8 || F >= 12));
+        if (shaped && wide) {
+            auto kern = wpd2d_block_k<T, F, 64, TREE, (F >= 10)>;
+            WX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<dim3((unsigned)gx, (unsigned)gy), kT2, smem, s>>>(io, (int)m, (int)n, db, L, t);
+        } else if (shaped) {
             auto kern = wpd2d_block_k<T, F, 64, TREE>;
             WX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             kern<<<dim3((unsigned)gx, (unsigned)gy), kT2, smem, s>>>(io, (int)m, (int)n, db, L, t);
