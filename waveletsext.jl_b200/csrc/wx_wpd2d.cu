@@ -53,13 +53,14 @@ struct Io2D {
 // TRC > 0: tile edge known at compile time (tr = tc = TRC): index arithmetic folds to shifts / immediates and the column pass
 // slides a register window down each column (KSEG pairs per thread, lanes across columns).
 // ---------------------------------------------------------------------------------------------------------
-template <typename T, int F, int TRC, int TCC = TRC, int MINB = 3, bool TREE = false>
+template <typename T, int F, int TRC, int TCC = TRC, int MINB = 3, bool TREE = false, int KRW = 0>
 __global__ void __launch_bounds__(kT2, MINB) wpd2d_tile_k(Io2D<T> io, int m, int n, int d, int tr_, int tc_,
                                                       Div32 drowtiles, Div32 dtiles_r, Div32 dtiles_c, Div32 dgx, long ntiles, Taps<T> tp)
 {
     const int tr = TRC > 0 ? TRC : tr_, tc = TRC > 0 ? TCC : tc_;
     using P2 = typename Pair<T>::type;
-    constexpr int S = (F - 2) / 2, KROW = (TRC > 0 && TCC == 16) ? 4 : wx_krow(F);      // narrow tiles: 4 column groups keep all 256 threads busy
+    // narrow tiles: 4 column groups keep all 256 threads busy; KRW = 8: long filters with the 8-pair row window (two-CTA launch bound)
+    constexpr int S = (F - 2) / 2, KROW = KRW > 0 ? KRW : ((TRC > 0 && TCC == 16) ? 4 : wx_krow(F));
     extern __shared__ __align__(16) unsigned char wx_2d_smem[];
     const int PR = 2 * tr + F - 2, PC = 2 * tc + F - 2, R2 = 2 * tr;
     const int LDP = TRC > 0 ? wx_ld_pairs(PR) : PR + 2 * (tr & 1);      // generic shape: odd tiles padded (see host)
@@ -691,8 +692,15 @@ int wpd2d_run_chunk(T *y, const T *x, T *scratch, long m, long n, int L, long N,
         const int per_sm = penv ? atoi(penv) : 0;
         const long ctas = per_sm > 0 && ntiles > (long)dv.sms * per_sm ? (long)dv.sms * per_sm : ntiles;
         const Io2D<T> io = level_io(d);
+        static const char *twenv = getenv("WX_B200_WPD2D_TILEWIDE");      // A-B knob
+        // 8-pair row window under a two-CTA bound: only 20 taps in Float64 gain (7.44 -> 6.77 ms per 1024 images; Float32 loses 10-17 %)
+        const bool wide_tile = F >= 12 && (twenv ? atoi(twenv) != 0 : (sizeof(T) == 8 && F >= 20));
         if (tr == 32 && tc == 16 && !TREE) {
             auto kern = wpd2d_tile_k<T, F, 32, 16, 4, false>;
+            WX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<(unsigned)ctas, kT2, smem, s>>>(io, (int)m, (int)n, d, tr, tc, drt, dtr, dtc, dgx, ntiles, t);
+        } else if (tr == 32 && tc == 32 && wide_tile) {
+            auto kern = wpd2d_tile_k<T, F, 32, 32, 2, TREE, (F >= 12 ? 8 : 0)>;
             WX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             kern<<<(unsigned)ctas, kT2, smem, s>>>(io, (int)m, (int)n, d, tr, tc, drt, dtr, dtc, dgx, ntiles, t);
         } else if (tr == 32 && tc == 32) {
