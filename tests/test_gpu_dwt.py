@@ -350,6 +350,15 @@ def test_wpdall_host_pipeline(wx, O, cuda):
     wx.host.trim_scratch(0)
     assert np.array_equal(wx.host.wpdall_host(x, wt, 9, chunk=300), yd)
     wx.host.trim_scratch(1 << 20)
+    # level 0 is filled on the host from x while levels 1..L cross PCIe: L = 0 (nothing to bring back), Float32, and a batch large
+    # enough for the two-thread fill (>= 64 MB of x)
+    assert np.array_equal(wx.host.wpdall_host(x[:10], wt, 0), x[:10, None, :])
+    xf = x.astype(np.float32)
+    assert np.array_equal(wx.host.wpdall_host(xf, wt, 4, chunk=333), wx.wpdall(dev(xf, cuda), wt, 4).cpu().numpy())
+    xb = np.random.default_rng(10).standard_normal((8200, 1024))
+    yb = wx.host.wpdall_host(xb, wt, 2)
+    assert np.array_equal(yb[:, 0], xb)
+    assert np.array_equal(yb, wx.wpdall(dev(xb, cuda), wt, 2).cpu().numpy())
 
 
 @pytest.mark.parametrize("dt", [np.float64, np.float32])
