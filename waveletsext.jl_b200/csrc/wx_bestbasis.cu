@@ -184,12 +184,17 @@ __device__ const double2 wx_log_tab[128] = {
     {0x1.0182436517a37p-1, 0x1.5fe1edad18919p-1}, {0x1.0080402010080p-1, 0x1.61e3efda46467p-1},
 };
 
-__device__ __forceinline__ double wx_log_fast(double x)
+// zero, subnormal, negative, infinite, NaN: not for the table path
+__device__ __forceinline__ bool wx_log_special(double x)
+{
+    const int ex = (int)(__double_as_longlong(x) >> 52);
+    return ex <= 0 || ex >= 0x7ff;
+}
+// the table path itself, straight-line (callers that batch several arguments test wx_log_special once for all of them)
+__device__ __forceinline__ double wx_log_core(double x)
 {
     const long long b = __double_as_longlong(x);
     const int ex = (int)(b >> 52);
-    if (ex <= 0 || ex >= 0x7ff) return log(x);
-    if (x == 1.0) return 0.0;                                 // exactly, like log (the table path would give 1.7e-18)
     const int i = (int)(b >> 45) & 127;
     const double m = __longlong_as_double((b & 0x000fffffffffffffLL) | 0x3ff0000000000000LL);
     const double2 t = __ldg(&wx_log_tab[i]);
@@ -200,8 +205,11 @@ __device__ __forceinline__ double wx_log_fast(double x)
     p = fma(r, p, -0.5);
     p = fma(r * r, p, r);                                   // log1p(r)
     const double e = (double)(ex - 1023);
-    return fma(e, 0x1.62e42fee00000p-1, (t.y + p) + e * 0x1.a39ef35793c76p-33);
+    const double res = fma(e, 0x1.62e42fee00000p-1, (t.y + p) + e * 0x1.a39ef35793c76p-33);
+    return x == 1.0 ? 0.0 : res;                              // exactly, like log (the table path would give 1.7e-18)
 }
+__device__ __noinline__ double wx_log_slow(double x) { return log(x); }
+__device__ __forceinline__ double wx_log_fast(double x) { return wx_log_special(x) ? wx_log_slow(x) : wx_log_core(x); }
 
 // ---- double-double accumulation (error-free transformations) ------------------------------------------------
 // The LSDB grid (origin, step) of a position is a function of the batch statistics, and every sample is binned on it: a
@@ -837,6 +845,24 @@ __device__ __forceinline__ double bb_term(double x, double inv_nrm, int kind)
     return kind == 0 ? -s * ls : -ls;
 }
 
+// four terms at once: one test for "any argument off the table path" (s = 0 included), then straight-line code -- the per-term
+// branches cost more issue slots than the arithmetic (ncu: 78 thread instructions per coefficient, 20 % of them FP64)
+template <int KIND>
+__device__ __forceinline__ void bb_terms4(const double *v, double inv_nrm, double *t)
+{
+    double s[4];
+    bool sp = false;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const double q = v[i] * inv_nrm; s[i] = q * q; sp |= wx_log_special(s[i]); }
+    if (!sp) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { const double ls = wx_log_core(s[i]); t[i] = KIND == 0 ? -s[i] * ls : -ls; }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) t[i] = bb_term(v[i], inv_nrm, KIND);
+    }
+}
+
 // sum over the G = blockDim-aligned power-of-two group of lanes that share a node (G <= 32: segmented xor shuffles;
 // G > 32: whole warps, combined through shared memory by the caller)
 __device__ __forceinline__ double group_sum(double v, int G)
@@ -926,8 +952,47 @@ template <> struct BbLoad4<float> {
     }
 };
 
-template <typename T>
-__global__ void __launch_bounds__(kT) bb_costs_1d_pow2_k(double *costs, const T *X, int n, int lgn, int K, long nn, int kind)
+// one level whose nodes have 2^LGP < 1024 coefficients: a thread's four coefficients share a node when LGP >= 2 and the node sum is
+// a segmented shuffle reduction over the 2^(LGP-2) threads of the node (LGP = 8, 9: whole warps, combined through shared memory)
+template <typename T, int KIND, int LGP>
+__device__ __forceinline__ void bb_level_small(const T *__restrict__ lev, double *__restrict__ cl, int nchunk, int tid, double inv, double *wsum)
+{
+    const int lane = tid & 31, warp = tid >> 5;
+    double v[4], t4[4];
+    for (int c = 0; c < nchunk; ++c) {
+        const int e0 = c * 1024 + tid * 4;
+        BbLoad4<T>::ld(lev + e0, v);
+        bb_terms4<KIND>(v, inv, t4);
+        if constexpr (LGP >= 2) {
+            constexpr int gsz = 1 << (LGP - 2);               // threads per node: 1 .. 128
+            double acc = (t4[0] + t4[1]) + (t4[2] + t4[3]);
+            if constexpr (gsz <= 32) {
+#pragma unroll
+                for (int o = gsz / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                if ((tid & (gsz - 1)) == 0) cl[e0 >> LGP] = acc;
+            } else {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                if (lane == 0) wsum[warp] = acc;
+                __syncthreads();
+                if ((tid & (gsz - 1)) == 0) {
+                    double t = 0.0;
+#pragma unroll
+                    for (int w = 0; w < gsz / 32; ++w) t += wsum[warp + w];
+                    cl[e0 >> LGP] = t;
+                }
+                __syncthreads();
+            }
+        } else if constexpr (LGP == 1) {
+            cl[e0 >> 1] = t4[0] + t4[1]; cl[(e0 >> 1) + 1] = t4[2] + t4[3];
+        } else {
+            cl[e0] = t4[0]; cl[e0 + 1] = t4[1]; cl[e0 + 2] = t4[2]; cl[e0 + 3] = t4[3];
+        }
+    }
+}
+
+template <typename T, int KIND>
+__global__ void __launch_bounds__(kT) bb_costs_1d_pow2_k(double *costs, const T *X, int n, int lgn, int K, long nn)
 {
     __shared__ double wsum[kT / 32];
     __shared__ double s_inv;
@@ -966,7 +1031,9 @@ __global__ void __launch_bounds__(kT) bb_costs_1d_pow2_k(double *costs, const T 
                 double acc = 0.0;
                 for (int c = 0; c < cpn; ++c) {
                     BbLoad4<T>::ld(lev + (j * cpn + c) * 1024 + tid * 4, v);
-                    acc += (bb_term(v[0], inv, kind) + bb_term(v[1], inv, kind)) + (bb_term(v[2], inv, kind) + bb_term(v[3], inv, kind));
+                    double t4[4];
+                    bb_terms4<KIND>(v, inv, t4);
+                    acc += (t4[0] + t4[1]) + (t4[2] + t4[3]);
                 }
                 acc = group_sum(acc, 32);
                 if (lane == 0) wsum[warp] = acc;
@@ -980,32 +1047,17 @@ __global__ void __launch_bounds__(kT) bb_costs_1d_pow2_k(double *costs, const T 
             }
             continue;
         }
-        for (int c = 0; c < nchunk; ++c) {
-            const int e0 = c * 1024 + tid * 4;
-            BbLoad4<T>::ld(lev + e0, v);
-            const double t0 = bb_term(v[0], inv, kind), t1 = bb_term(v[1], inv, kind), t2 = bb_term(v[2], inv, kind), t3 = bb_term(v[3], inv, kind);
-            if (lgp >= 2) {
-                const int gsz = 1 << (lgp - 2);               // threads per node: 1 .. 128
-                double acc = (t0 + t1) + (t2 + t3);
-                if (gsz <= 32) {
-                    acc = group_sum(acc, gsz);
-                    if ((tid & (gsz - 1)) == 0) cl[e0 >> lgp] = acc;
-                } else {
-                    acc = group_sum(acc, 32);
-                    if (lane == 0) wsum[warp] = acc;
-                    __syncthreads();
-                    if ((tid & (gsz - 1)) == 0) {
-                        double t = 0.0;
-                        for (int w = 0; w < gsz / 32; ++w) t += wsum[warp + w];
-                        cl[e0 >> lgp] = t;
-                    }
-                    __syncthreads();
-                }
-            } else if (lgp == 1) {
-                cl[e0 >> 1] = t0 + t1; cl[(e0 >> 1) + 1] = t2 + t3;
-            } else {
-                cl[e0] = t0; cl[e0 + 1] = t1; cl[e0 + 2] = t2; cl[e0 + 3] = t3;
-            }
+        switch (lgp) {                                       // node length known at compile time inside each case: no per-step tests
+            case 0: bb_level_small<T, KIND, 0>(lev, cl, nchunk, tid, inv, wsum); break;
+            case 1: bb_level_small<T, KIND, 1>(lev, cl, nchunk, tid, inv, wsum); break;
+            case 2: bb_level_small<T, KIND, 2>(lev, cl, nchunk, tid, inv, wsum); break;
+            case 3: bb_level_small<T, KIND, 3>(lev, cl, nchunk, tid, inv, wsum); break;
+            case 4: bb_level_small<T, KIND, 4>(lev, cl, nchunk, tid, inv, wsum); break;
+            case 5: bb_level_small<T, KIND, 5>(lev, cl, nchunk, tid, inv, wsum); break;
+            case 6: bb_level_small<T, KIND, 6>(lev, cl, nchunk, tid, inv, wsum); break;
+            case 7: bb_level_small<T, KIND, 7>(lev, cl, nchunk, tid, inv, wsum); break;
+            case 8: bb_level_small<T, KIND, 8>(lev, cl, nchunk, tid, inv, wsum); break;
+            default: bb_level_small<T, KIND, 9>(lev, cl, nchunk, tid, inv, wsum); break;
         }
     }
 }
@@ -1254,10 +1306,12 @@ static int bb_costs_impl(double *costs, const T *X, long m, long n, int K, long 
     if (m == 0) {
         WX_REQUIRE(N < (1L << 31), "too many signals for one launch");
         static const bool generic = getenv("WX_B200_BB_GENERIC") != nullptr;          // A-B measurements only
-        if (!generic && !redundant && wx_ispow2(n) && n >= 1024 && n < (1L << 30) && K <= wx_ilog2l(n) + 1 && (((uintptr_t)X) & 15) == 0)
-            bb_costs_1d_pow2_k<T><<<(unsigned)N, kT, 0, s>>>(costs, X, (int)n, wx_ilog2l(n), K, nn, kind);
-        else
+        if (!generic && !redundant && wx_ispow2(n) && n >= 1024 && n < (1L << 30) && K <= wx_ilog2l(n) + 1 && (((uintptr_t)X) & 15) == 0) {
+            if (kind == 0) bb_costs_1d_pow2_k<T, 0><<<(unsigned)N, kT, 0, s>>>(costs, X, (int)n, wx_ilog2l(n), K, nn);
+            else bb_costs_1d_pow2_k<T, 1><<<(unsigned)N, kT, 0, s>>>(costs, X, (int)n, wx_ilog2l(n), K, nn);
+        } else {
             bb_costs_1d_k<T><<<(unsigned)N, kT, 0, s>>>(costs, X, n, K, nn, redundant, kind);
+        }
     } else {
         NodeGeom g{m, n, K, redundant};
         const long sz = m * n;
