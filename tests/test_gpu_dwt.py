@@ -290,6 +290,25 @@ def test_wpd2d_large_images(wx, O, cuda, dt, name, m, n, L):
 
 
 @pytest.mark.parametrize("dt", [np.float64, np.float32])
+@pytest.mark.parametrize("name", ["db3", "db5", "coif4"])
+def test_wpd2d_more_filter_lengths(wx, O, cuda, dt, name):
+    """6, 10 and 12 taps through the halo-tile / whole-node kernels (10 and 12 taps take the 8-pair windows of the whole-node kernel),
+    table and by-tree forms, against the oracle"""
+    wt = wx.wavelet(name)
+    h, g = pair(wx, wt)
+    m, n, L = 256, 128, 4
+    x = np.random.default_rng(77).standard_normal((2, n, m)).astype(dt)
+    y = wx.wpdall(dev(x, cuda), wt, L)
+    ref = np.stack([O.wpd(x[k], h, g, L) for k in range(2)])
+    assert relerr(y.cpu().numpy(), ref) <= TOL[dt]
+    rt = 1e-10 if dt == np.float64 else 3e-4
+    for tree in (wx.maketree(m, n, L, "full"), wx.maketree(m, n, L, "dwt")):
+        yt = wx.wptall(dev(x, cuda), wt, tree)
+        assert relerr(yt.cpu().numpy(), np.stack([O.wpt(x[k], tree, h, g) for k in range(2)])) <= TOL[dt]
+        assert relerr(wx.iwptall(yt, wt, tree).cpu().numpy(), x) <= rt
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
 def test_wpt2d_trees(wx, O, cuda, dt):
     wt = wx.wavelet("db4")
     h, g = pair(wx, wt)

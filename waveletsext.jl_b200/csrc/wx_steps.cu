@@ -219,6 +219,39 @@ __global__ void __launch_bounds__(kThreads) isdwt_shift_k(View<T> v, View<const 
     pv[j * v.es] = isdwt_elem<T, FF>(p1, w1.es, p2, w2.es, n, d, sw, t, tp, add2out != 0, init);
 }
 
+// the same step with the filter length known at compile time (even F), 32-bit indices and the parity of t resolved once: the element
+// routine above spends ~280 instructions per output on run-time tap indices and 64-bit wraps.  Same terms in the same order.
+template <typename T, int FF>
+__global__ void __launch_bounds__(kThreads) isdwt_shift_fast_k(View<T> v, View<const T> w1, View<const T> w2, int n, int D, int sv, int sw,
+                                                                int add2out, Geo geo, Taps<T> tp)
+{
+    constexpr int F = FF > 0 ? FF : 2, R = F / 2;
+    long t0, b0, b1, b2;
+    if (!decomp(geo, t0, b0, b1, b2)) return;
+    const T *p1 = w1.p + voff(w1, b0, b1, b2);
+    const T *p2 = w2.p + voff(w2, b0, b1, b2);
+    T *pv = v.p + voff(v, b0, b1, b2);
+    const int t = (int)t0 + 1, m = sv + 1 + (int)t0 * D;               // 1-based
+    int j = ((sw == sv) ? m - D - 1 : m - 1) % n; if (j < 0) j += n;   // 0-based write position
+    const bool odd = (t & 1) != 0;
+    const int sc = 2 * D;
+    int k1 = ((t - 1) >> 1) * sc + sw, k2 = k1;                        // 0-based
+    // term r: t odd -> g[F-1-2r], h[2r+1]; t even -> g[F-2-2r], h[2r]
+    T gr = odd ? tp.g[F - 1] : tp.g[F - 2], hr = odd ? tp.h[1] : tp.h[0];
+    T acc;
+    if (add2out) acc = fma(hr, p2[(long)k2 * w2.es], fma(gr, p1[(long)k1 * w1.es], pv[(long)j * v.es]));
+    else         acc = fma(gr, p1[(long)k1 * w1.es], hr * p2[(long)k2 * w2.es]);
+#pragma unroll
+    for (int r = 1; r < R; ++r) {
+        k1 -= sc; if (k1 < 0) k1 += n;
+        k2 += sc; if (k2 >= n) k2 -= n;
+        gr = odd ? tp.g[F - 1 - 2 * r] : tp.g[F - 2 - 2 * r];
+        hr = odd ? tp.h[2 * r + 1] : tp.h[2 * r];
+        acc += fma(gr, p1[(long)k1 * w1.es], hr * p2[(long)k2 * w2.es]);
+    }
+    pv[(long)j * v.es] = acc;
+}
+
 // a10 isdwt_step! average based: one thread per output position (requires n % 2^(d+1) == 0)
 template <typename T, int FF>
 __global__ void __launch_bounds__(kThreads) isdwt_avg_k(View<T> v, View<const T> w1, View<const T> w2, long n, int d, Geo geo, Taps<T> tp)
@@ -345,7 +378,14 @@ int wx_launch_isdwt_shift(View<T> v, View<const T> w1, View<const T> w2, long n,
     long total = cnt * btot(b);
     if (total <= 0) return WX_OK;
     const Geo geo = make_geo(cnt, b);
-    WX_DISPATCH_F(t.F, (isdwt_shift_k<T, FF><<<grid_for(total), kThreads, 0, s>>>(v, w1, w2, n, d, sv, sw, add2out, geo, t)))
+    static const bool literal = getenv("WX_B200_ISDWT_SHIFT_LITERAL") != nullptr;     // A-B measurements
+    bool known = false;
+    WX_DISPATCH_F(t.F, (known = FF > 0 && FF % 2 == 0))
+    if (!literal && known && n < (1L << 30) && (1L << d) < n) {                      // one conditional wrap per step needs 2^(d+1) <= n (checked above)
+        WX_DISPATCH_F(t.F, (isdwt_shift_fast_k<T, FF><<<grid_for(total), kThreads, 0, s>>>(v, w1, w2, (int)n, (int)(1L << d), (int)sv, (int)sw, add2out, geo, t)))
+    } else {
+        WX_DISPATCH_F(t.F, (isdwt_shift_k<T, FF><<<grid_for(total), kThreads, 0, s>>>(v, w1, w2, n, d, sv, sw, add2out, geo, t)))
+    }
     WX_LAUNCHED();
     return WX_OK;
 }
