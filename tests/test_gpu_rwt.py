@@ -152,6 +152,13 @@ def test_redundant_2d(wx, O, cuda, dt, ac):
         assert relerr(wx.iacwpdall(outs["wpd"], wt, tree).cpu().numpy(), x) <= rt
         want = np.stack([O.iacwpd(ref["wpd"][i], tree) for i in range(N)])
         assert relerr(wx.iacwpdall(outs["wpd"], tree).cpu().numpy(), want) <= TOL[dt] * 20
+        # complete trees take the one-pass pairwise sum over the slices (quad tree of depth L = binary tree of depth 2L): against the oracle,
+        # on the reference's own tables, for the wpt layout, the full wpd tree and a complete tree of depth 2 inside the depth-3 table
+        want = np.stack([O.iacwpt(ref["wpt"][i]) for i in range(N)])
+        assert relerr(wx.iacwptall(dev(ref["wpt"], cuda)).cpu().numpy(), want) <= TOL[dt] * 20
+        for tr in (wx.maketree(nr, nc, L, "full"), wx.maketree(nr, nc, 2, "full")):
+            want = np.stack([O.iacwpd(ref["wpd"][i], tr) for i in range(N)])
+            assert relerr(wx.iacwpdall(dev(ref["wpd"], cuda), tr).cpu().numpy(), want) <= TOL[dt] * 20
     else:
         h, g = pair(wx, wt)
         for s in (None, 3):

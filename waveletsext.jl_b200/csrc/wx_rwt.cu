@@ -343,6 +343,22 @@ int irwt_2d(int imode, int mode, T *x, const T *xw, long m, long n, long nsl, in
     auto SV = [&](int d) { return imode == 1 ? sd[(size_t)d] : 0L; };
     auto SW = [&](int d) { return imode == 1 ? sd[(size_t)d + 1] : 0L; };
     if (imode == 1) WX_CUDA(cudaMemsetAsync(x, 0, (size_t)img * N * sizeof(T), s));
+    // Autocorrelation inverses are position-wise sums (iacdwt_step! 2-D acwt/acwt_one_level.jl:288-322: rows (w1+w2)/sqrt2, (w3+w4)/sqrt2, then
+    // columns): the four children of a quad node are four consecutive quarter-ranges of slices, so the quad-tree reduction of depth L IS the
+    // binary pairwise reduction of depth 2L over the slices in their natural order -- one pass over the table instead of three launches
+    // and 9 image sizes per depth.
+    if (imode == 2 && mode == WX_MODE_WPT && 2 * L < 32) return wx_iac_tree_sum<T>(x, xw, img, nsl, 0, 2 * L, N, s);
+    if (imode == 2 && mode == WX_MODE_WPD) {
+        long last = 0;
+        for (long i = ntree; i >= 1; --i) if (tree[i - 1]) { last = i; break; }
+        if (last > 0) {
+            const int Lt = wx_quaddepthl(last) + 1;                                  // depth of the leaves if the tree is complete
+            const long inner = (pow4(Lt) - 1) / 3;                                   // nodes above depth Lt
+            bool full = last == inner && 2 * Lt < 32 && inner + pow4(Lt) <= nsl;
+            for (long i = 1; full && i <= last; ++i) full = tree[i - 1] != 0;
+            if (full) return wx_iac_tree_sum<T>(x, xw, img, nsl, inner, 2 * Lt, N, s);
+        }
+    }
     if (mode == WX_MODE_DWT) {
         // isdwt! 2-D SWT.jl:296-308, 345-356 ; iacdwt! 2-D ACWT.jl:317-327
         T *tmp, *temp;
