@@ -22,7 +22,7 @@ for name, fwd, inv, nsl in (("isdwtall2d", lambda: wx.sdwtall(x, wt, L), lambda 
                             ("isdwtall2d_shift", lambda: wx.sdwtall(x, wt, L), lambda y: wx.isdwtall(y, wt, 5), 3 * L + 1),
                             ("iswptall2d", lambda: wx.swptall(x, wt, L), lambda y: wx.iswptall(y, wt), 4 ** L),
                             ("iswptall2d_shift", lambda: wx.swptall(x, wt, L), lambda y: wx.iswptall(y, wt, 5), 4 ** L),
-                            ("iswpdall2d", lambda: wx.swpdall(x, wt, L), lambda y: wx.iswpdall(y, wt), 4 ** L),
+                            ("iswpdall2d", lambda: wx.swpdall(x, wt, L), lambda y: wx.iswpdall(y, wt, L), 4 ** L),
                             ("iacwptall2d", lambda: wx.acwptall(x, wt, L), lambda y: wx.iacwptall(y, wt), 4 ** L)):
     try:
         y = fwd()
