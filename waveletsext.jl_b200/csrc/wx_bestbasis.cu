@@ -1419,16 +1419,30 @@ __global__ void __launch_bounds__(kT) gather_multi_1d_k(T *out, const T *Xw, lon
     }
     if (bad) atomicOr(flag, bad);
     const T *Xk = Xw + k * (long)K * n;
-    for (long e = threadIdx.x; e < n; e += kT) {
-        int d = 0;
-        long idx = 1;
-        while (idx <= ntree && wx_gt[idx - 1] && d < K - 1) {
-            const long p = n >> (d + 1), j = idx - (1L << d);
+    // leaf depth of position e: walk the staged tree (32-bit indices: ntree = n - 1 < 2^31)
+    const int nt = (int)ntree, ni = (int)n;
+    auto leaf_depth = [&](int e) {
+        int d = 0, idx = 1;
+        while (idx <= nt && wx_gt[idx - 1] && d < K - 1) {
+            const int p = ni >> (d + 1), j = idx - (1 << d);
             idx = 2 * idx + ((e - j * 2 * p) >= p ? 1 : 0);
             ++d;
         }
-        out[k * n + e] = Xk[(long)d * n + e];
+        return d;
+    };
+    // four positions per thread and iteration: the four walks first, then the four gathers in flight together
+    int e = threadIdx.x;
+    for (; e + 3 * kT < ni; e += 4 * kT) {
+        int d[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) d[q] = leaf_depth(e + q * kT);
+        T v[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v[q] = Xk[(long)d[q] * n + e + q * kT];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) out[k * n + e + q * kT] = v[q];
     }
+    for (; e < ni; e += kT) out[k * n + e] = Xk[(long)leaf_depth(e) * n + e];
 }
 
 // the checks of getbasiscoefall(Xw, tree::BitArray{2}) Utils.jl:204-218 on the device: every tree valid (a split node's parent is
