@@ -502,7 +502,7 @@ __global__ void __launch_bounds__(kT) lsdb_hist_smem_k(double *counts, const dou
                                                         int npts)
 {
     extern __shared__ unsigned int wx_cnt[];
-    constexpr int U = 8;
+    constexpr int U = 16;
     const int tid = threadIdx.x;
     const long e = (long)blockIdx.x * kT + tid;
     for (int i = 0; i < npts; ++i) wx_cnt[i * kT + tid] = 0;
