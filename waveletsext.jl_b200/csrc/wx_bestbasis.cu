@@ -497,11 +497,14 @@ __global__ void __launch_bounds__(kT) lsdb_hist_k(double *counts, const double *
 // shared-memory variant: a thread owns one position and keeps its npts bin counters in shared memory (column tid of a
 // (npts, kT) table: conflict free, no atomics needed), U signals in flight; the per-CTA counts are then added to the global
 // table with one atomicAdd per non-empty bin (integer-valued doubles: exact and order independent).
-template <typename T>
+// CT: counter type.  16-bit counters (a slice of at most 65535 signals per CTA) halve the shared memory, so six CTAs instead of three are
+// resident: the pass is latency bound on its loads (ncu: long_scoreboard 8.2 stall cycles per issue at 24 warps).
+template <typename T, typename CT>
 __global__ void __launch_bounds__(kT) lsdb_hist_smem_k(double *counts, const double *stats, const T *X, long szK, long N, long kchunk, double Ntot,
                                                         int npts)
 {
-    extern __shared__ unsigned int wx_cnt[];
+    extern __shared__ unsigned int wx_cnt_raw[];
+    CT *wx_cnt = reinterpret_cast<CT *>(wx_cnt_raw);
     constexpr int U = 16;
     const int tid = threadIdx.x;
     const long e = (long)blockIdx.x * kT + tid;
@@ -521,15 +524,15 @@ __global__ void __launch_bounds__(kT) lsdb_hist_smem_k(double *counts, const dou
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const long ki = (long)floor(((double)r[u] - a) * dinv + 1.5);      // AverageShiftedHistograms bin rule (1-based)
-            if (ki >= 1 && ki <= npts) wx_cnt[(int)(ki - 1) * kT + tid] += 1u;
+            if (ki >= 1 && ki <= npts) wx_cnt[(int)(ki - 1) * kT + tid] += (CT)1;
         }
     }
     for (; k < k1; ++k) {
         const long ki = (long)floor(((double)p[k * szK] - a) * dinv + 1.5);
-        if (ki >= 1 && ki <= npts) wx_cnt[(int)(ki - 1) * kT + tid] += 1u;
+        if (ki >= 1 && ki <= npts) wx_cnt[(int)(ki - 1) * kT + tid] += (CT)1;
     }
     for (int i = 0; i < npts; ++i) {
-        const unsigned c = wx_cnt[i * kT + tid];
+        const unsigned c = (unsigned)wx_cnt[i * kT + tid];
         if (c) atomicAdd(&counts[(long)i * szK + e], (double)c);
     }
 }
@@ -674,12 +677,30 @@ int lsdb_pass2(double *counts, const double *stats, const T *X, long szK, long N
     WX_CUDA(cudaMemsetAsync(counts, 0, (size_t)g.npts * szK * sizeof(double), s));
     if (Nlocal == 0) return WX_OK;
     WxDev dv; int rc = wx_devinfo(dv); if (rc) return rc;
-    const int ksplit = pick_ksplit(szK, Nlocal, dv.sms);
-    const long kchunk = (Nlocal + ksplit - 1) / ksplit;
+    int ksplit = pick_ksplit(szK, Nlocal, dv.sms);
+    long kchunk = (Nlocal + ksplit - 1) / ksplit;
     dim3 grid((unsigned)((szK + kT - 1) / kT), (unsigned)ksplit);
-    const size_t smem = (size_t)g.npts * kT * sizeof(unsigned int);
+    const size_t smem = (size_t)g.npts * kT * sizeof(unsigned int), smem16 = (size_t)g.npts * kT * sizeof(unsigned short);
+    static const bool no16 = getenv("WX_B200_LSDB_HIST32") != nullptr;           // A-B measurements
+    if (!no16 && smem16 <= dv.smem_optin) {
+        auto kern = lsdb_hist_smem_k<T, unsigned short>;
+        WX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16));
+        int occ = 0;
+        WX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kT, smem16));
+        // slices: two full waves of resident CTAs, at most 65535 signals (the counter range) and at least 64 signals each
+        long ks = occ > 0 ? (2L * dv.sms * occ) / grid.x : ksplit;
+        if (ks < 1) ks = 1;
+        if (ks > (Nlocal + 63) / 64) ks = (Nlocal + 63) / 64;
+        if (ks < (Nlocal + 65534) / 65535) ks = (Nlocal + 65534) / 65535;
+        if (ks <= 65535) {
+            ksplit = (int)ks; kchunk = (Nlocal + ksplit - 1) / ksplit; grid.y = (unsigned)ksplit;
+            kern<<<grid, kT, smem16, s>>>(counts, stats, X, szK, Nlocal, kchunk, (double)Ntotal, (int)g.npts);
+            WX_LAUNCHED();
+            return WX_OK;
+        }
+    }
     if (smem <= dv.smem_optin && kchunk < (1L << 32)) {
-        auto kern = lsdb_hist_smem_k<T>;
+        auto kern = lsdb_hist_smem_k<T, unsigned int>;
         WX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<grid, kT, smem, s>>>(counts, stats, X, szK, Nlocal, kchunk, (double)Ntotal, (int)g.npts);
     } else {
