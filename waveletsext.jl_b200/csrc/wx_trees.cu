@@ -199,6 +199,41 @@ __global__ void __launch_bounds__(kT) gather_k(T *out, const T *Xw, long sz, lon
     const long e = idx % sz, k = idx / sz;
     out[idx] = Xw[(k * K + depth[e]) * sz + e];
 }
+// grid.x = signal, grid.y * blockDim walks the positions: no 64-bit division per element, four gathers in flight per thread
+template <typename T>
+__global__ void __launch_bounds__(kT) gather_sig_k(T *__restrict__ out, const T *__restrict__ Xw, long sz, long K, const unsigned char *__restrict__ depth)
+{
+    const long k = blockIdx.x;
+    const T *Xk = Xw + k * K * sz;
+    T *ok = out + k * sz;
+    const long step = (long)gridDim.y * kT;
+    long e = (long)blockIdx.y * kT + threadIdx.x;
+    for (; e + 3 * step < sz; e += 4 * step) {
+        T v[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v[q] = Xk[(long)depth[e + q * step] * sz + e + q * step];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) ok[e + q * step] = v[q];
+    }
+    for (; e < sz; e += step) ok[e] = Xk[(long)depth[e] * sz + e];
+}
+
+// the same with V consecutive positions per thread (one 16-byte load / store) when no leaf boundary falls inside an aligned group of V
+// positions; grid.x = signal, grid.y * blockDim walks the groups -- no 64-bit division per element
+template <typename T>
+__global__ void __launch_bounds__(kT) gather_vec_k(T *__restrict__ out, const T *__restrict__ Xw, long sz, long K, const unsigned char *__restrict__ depth)
+{
+    using VT = typename WxVec<T>::type;
+    constexpr int V = WxVec<T>::N;
+    const long k = blockIdx.x;
+    const T *Xk = Xw + k * K * sz;
+    T *ok = out + k * sz;
+    const long groups = sz / V;
+    for (long c = (long)blockIdx.y * kT + threadIdx.x; c < groups; c += (long)gridDim.y * kT) {
+        const long e = c * V;
+        *reinterpret_cast<VT *>(ok + e) = __ldcs(reinterpret_cast<const VT *>(Xk + (long)depth[e] * sz + e));
+    }
+}
 
 // ---- host helpers -------------------------------------------------------------------------------------
 struct DevTree {
@@ -458,7 +493,21 @@ int gather_impl(T *out, const T *Xw, long m, long n, int K, long N, const unsign
     int rc = leaf_depth_map(depth, m, n, K, tree, ntree); if (rc) return rc;
     const long sz = (long)depth.size();
     DevTree dd; rc = dd.upload(depth.data(), sz, s); if (rc) return rc;
-    gather_k<T><<<gridf(sz * N), kT, 0, s>>>(out, Xw, sz, K, N, dd.d);
+    constexpr int V = WxVec<T>::N;
+    bool vec = sz % V == 0 && N < (1L << 31) && ((((uintptr_t)out) | ((uintptr_t)Xw)) & 15) == 0;
+    for (long e = 0; vec && e < sz; e += V)
+        for (int q = 1; q < V; ++q) if (depth[(size_t)(e + q)] != depth[(size_t)e]) { vec = false; break; }
+    if (vec) {
+        long gy = (sz / V + kT - 1) / kT;
+        if (gy > 64) gy = 64;
+        gather_vec_k<T><<<dim3((unsigned)N, (unsigned)gy), kT, 0, s>>>(out, Xw, sz, K, dd.d);
+    } else if (N < (1L << 31)) {
+        long gy = (sz + 4 * kT - 1) / (4 * kT);
+        if (gy > 64) gy = 64;
+        gather_sig_k<T><<<dim3((unsigned)N, (unsigned)gy), kT, 0, s>>>(out, Xw, sz, K, dd.d);
+    } else {
+        gather_k<T><<<gridf(sz * N), kT, 0, s>>>(out, Xw, sz, K, N, dd.d);
+    }
     WX_LAUNCHED();
     return WX_OK;
 }
