@@ -416,6 +416,59 @@ __device__ __forceinline__ void iwpt_small_levels4(const T *__restrict__ src, T 
     }
 }
 
+// the same along a tree: a node the tree does not split passes through (its children occupy exactly its range).  tm[q] = split flags of
+// the depth whose nodes have 2 << q ... i.e. q = 0: nodes of length 2, 1: 4, 2: 8, 3: 16; node indices are relative to the staged node.
+template <typename T, int F, int P, int G>
+__device__ __forceinline__ void iwpt_regs_level_tree(const T *v, T *o, const Taps<T> &tp, const TreeMask &tm, long node0)
+{
+    constexpr int H = P / 2;
+#pragma unroll
+    for (int nd = 0; nd < G / P; ++nd) {
+        if (tm.on(node0 + nd)) {
+            const T *w1 = &v[nd * P], *w2 = &v[nd * P + H];
+#pragma unroll
+            for (int t = 0; t < H; ++t) {
+                constexpr int R = F / 2;
+                T e = tp.g[F - 1] * w1[t];
+                T od = tp.g[F - 2] * w1[t];
+                e = fma(tp.h[1], w2[t], e);
+                od = fma(tp.h[0], w2[t], od);
+#pragma unroll
+                for (int r = 1; r < R; ++r) {
+                    e = fma(tp.g[F - 1 - 2 * r], w1[(t - r) & (H - 1)], e);
+                    od = fma(tp.g[F - 2 - 2 * r], w1[(t - r) & (H - 1)], od);
+                    e = fma(tp.h[2 * r + 1], w2[(t + r) & (H - 1)], e);
+                    od = fma(tp.h[2 * r], w2[(t + r) & (H - 1)], od);
+                }
+                o[nd * P + 2 * t] = e;
+                o[nd * P + 2 * t + 1] = od;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < P; ++i) o[nd * P + i] = v[nd * P + i];
+        }
+    }
+}
+template <typename T, int F>
+__device__ __forceinline__ void iwpt_small_levels4_tree(const T *__restrict__ src, T *__restrict__ dst, int n0, const Taps<T> &tp, int tid, int nthreads,
+                                                        TreeMask tm2, TreeMask tm4, TreeMask tm8, TreeMask tm16)
+{
+    using VT = typename WxVec<T>::type;
+    constexpr int V = WxVec<T>::N, G = 16;
+    for (int u = tid; u < n0 / G; u += nthreads) {
+        const int g0 = wx_swz_chunk((u * G) / V) * V;
+        T v[G], o[G];
+#pragma unroll
+        for (int c = 0; c < G / V; ++c) wx_unpack(&v[c * V], *reinterpret_cast<const VT *>(src + (g0 ^ (c * V))));
+        iwpt_regs_level_tree<T, F, 2, G>(v, o, tp, tm2, (long)u * 8);
+        iwpt_regs_level_tree<T, F, 4, G>(o, v, tp, tm4, (long)u * 4);
+        iwpt_regs_level_tree<T, F, 8, G>(v, o, tp, tm8, (long)u * 2);
+        iwpt_regs_level_tree<T, F, 16, G>(o, v, tp, tm16, (long)u);
+#pragma unroll
+        for (int c = 0; c < G / V; ++c) *reinterpret_cast<VT *>(dst + (g0 ^ (c * V))) = wx_pack(&v[c * V]);
+    }
+}
+
 // any even node length, one output pair per thread
 template <typename T, int F, bool TREE>
 __device__ __forceinline__ void iwpt_generic_level(const T *__restrict__ src, T *__restrict__ dst, int n0, int p, const Taps<T> &tp, int tid,

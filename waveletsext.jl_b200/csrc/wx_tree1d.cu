@@ -54,9 +54,17 @@ __global__ void __launch_bounds__(WX_TREE_MAXT) tree1d_fused_k(T *__restrict__ y
         // ---- levels ---------------------------------------------------------------------------------
         T *a = buf0, *b = buf1;
         int q0 = 0;
-        if (INV && !TREE && nl >= 4 && (n0 >> (nl - 1)) == 2 && n0 % 16 == 0) {
-            // complete tree down to nodes of length 2: the four deepest levels in registers
-            iwpt_small_levels4<T, F>(a, b, n0, tp, tid, nthreads);
+        if (INV && nl >= 4 && (n0 >> (nl - 1)) == 2 && n0 % 16 == 0) {
+            // down to nodes of length 2: the four deepest levels in registers (along the tree: nodes that are not split pass through)
+            if (TREE) {
+                auto mask = [&](int l) {                   // split flags of relative level l of this item
+                    const long first = ((1L << (d0 + l)) - 1) + (j0 << l);
+                    return TreeMask{tree + first, ntree - first};
+                };
+                iwpt_small_levels4_tree<T, F>(a, b, n0, tp, tid, nthreads, mask(nl - 1), mask(nl - 2), mask(nl - 3), mask(nl - 4));
+            } else {
+                iwpt_small_levels4<T, F>(a, b, n0, tp, tid, nthreads);
+            }
             __syncthreads();
             T *t = a; a = b; b = t;
             q0 = 4;
