@@ -175,6 +175,55 @@ __device__ __forceinline__ void wpd_small_level(const T *__restrict__ src, T *__
     }
 }
 
+// one forward level of the nodes of length P inside a register-resident run of G elements (compile-time wraps); along a tree the nodes
+// that are not split pass through
+template <typename T, int F, int P, int G, bool TREE>
+__device__ __forceinline__ void wpd_regs_level(const T *v, T *o, const Taps<T> &tp, const TreeMask &tm, long node0)
+{
+#pragma unroll
+    for (int nd = 0; nd < G / P; ++nd) {
+        if (!TREE || tm.on(node0 + nd)) {
+#pragma unroll
+            for (int i = 0; i < P / 2; ++i) {
+                T a = tp.g[F - 1] * v[nd * P + ((2 * i) & (P - 1))];
+                T b = tp.h[0] * v[nd * P + ((2 * i + 1) & (P - 1))];
+#pragma unroll
+                for (int jj = 1; jj < F; ++jj) {
+                    a = fma(tp.g[F - 1 - jj], v[nd * P + ((2 * i + jj) & (P - 1))], a);
+                    b = fma(tp.h[jj], v[nd * P + ((2 * i + 1 - jj) & (P - 1))], b);
+                }
+                o[nd * P + i] = a;
+                o[nd * P + P / 2 + i] = b;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < P; ++i) o[nd * P + i] = v[nd * P + i];
+        }
+    }
+}
+// the four deepest levels of a by-tree forward transform that goes down to nodes of length 2: a thread owns a node of length 16 and
+// everything below it, splits 16 -> 8 -> 4 -> 2 in registers and writes the run once (three shared-memory round trips and barriers fewer).
+// tm16 .. tm2: split flags of the depths whose nodes have length 16 .. 2.
+template <typename T, int F, bool TREE>
+__device__ __forceinline__ void wpd_small_levels4(const T *__restrict__ src, T *__restrict__ dst, int n0, const Taps<T> &tp, int tid, int nthreads,
+                                                  TreeMask tm16, TreeMask tm8, TreeMask tm4, TreeMask tm2)
+{
+    using VT = typename WxVec<T>::type;
+    constexpr int V = WxVec<T>::N, G = 16;
+    for (int u = tid; u < n0 / G; u += nthreads) {
+        const int g0 = wx_swz_chunk((u * G) / V) * V;
+        T v[G], o[G];
+#pragma unroll
+        for (int c = 0; c < G / V; ++c) wx_unpack(&v[c * V], *reinterpret_cast<const VT *>(src + (g0 ^ (c * V))));
+        wpd_regs_level<T, F, 16, G, TREE>(v, o, tp, tm16, (long)u);
+        wpd_regs_level<T, F, 8, G, TREE>(o, v, tp, tm8, (long)u * 2);
+        wpd_regs_level<T, F, 4, G, TREE>(v, o, tp, tm4, (long)u * 4);
+        wpd_regs_level<T, F, 2, G, TREE>(o, v, tp, tm2, (long)u * 8);
+#pragma unroll
+        for (int c = 0; c < G / V; ++c) *reinterpret_cast<VT *>(dst + (g0 ^ (c * V))) = wx_pack(&v[c * V]);
+    }
+}
+
 // ---- generic level: any even node length, one output pair per thread ----------------------------------
 template <typename T, int F, bool GST, bool TREE = false>
 __device__ __forceinline__ void wpd_generic_level(const T *__restrict__ src, T *__restrict__ dst, T *__restrict__ grow, int n0, int p,

@@ -69,13 +69,25 @@ __global__ void __launch_bounds__(WX_TREE_MAXT) tree1d_fused_k(T *__restrict__ y
             T *t = a; a = b; b = t;
             q0 = 4;
         }
-        for (int q = q0; q < nl; ++q) {
+        // forward: the four deepest levels (nodes of length 16, 8, 4, 2) run in registers after the loop
+        const bool fwd4 = !INV && nl >= 4 && (n0 >> (nl - 1)) == 2 && n0 % 16 == 0;
+        const int qend = fwd4 ? nl - 4 : nl;
+        for (int q = q0; q < qend; ++q) {
             const int l = INV ? nl - 1 - q : q;       // level relative to the staged node
             const int d = d0 + l;
             const long first = ((1L << d) - 1) + (j0 << l);               // 0-based heap position of the node's first depth-d descendant
             TreeMask tm{TREE ? tree + first : nullptr, ntree - first};
             if (INV) iwpt_level<T, F, TREE, KM>(a, b, n0, n0 >> l, tp, tid, nthreads, tm);
             else     wpd_level<T, F, false, TREE, KM>(a, b, nullptr, n0, n0 >> l, false, tp, tid, nthreads, tm);
+            __syncthreads();
+            T *t = a; a = b; b = t;
+        }
+        if (fwd4) {
+            auto mask = [&](int l) {
+                const long first = ((1L << (d0 + l)) - 1) + (j0 << l);
+                return TreeMask{TREE ? tree + first : nullptr, ntree - first};
+            };
+            wpd_small_levels4<T, F, TREE>(a, b, n0, tp, tid, nthreads, mask(nl - 4), mask(nl - 3), mask(nl - 2), mask(nl - 1));
             __syncthreads();
             T *t = a; a = b; b = t;
         }
