@@ -178,8 +178,8 @@ def test_redundant_2d(wx, O, cuda, dt, ac):
 @pytest.mark.parametrize("ac", [False, True])
 @pytest.mark.parametrize("name,nr,nc,L", [("haar", 64, 32, 3), ("db4", 96, 64, 2), ("db2", 128, 128, 3), ("db4", 32, 160, 1)])
 def test_redundant_2d_tiles(wx, O, cuda, dt, ac, name, nr, nc, L):
-    """images larger than a tile: the fused 2-D a-trous step (halo patches, shifted detail outputs, periodic wrap at the image
-    border, parent copies for the in-place swpt / sdwt layouts) and the per-pass path beyond the halo threshold"""
+    """images larger than a tile: the fused 2-D a-trous step (row halo patches, one column coset per tile, sliding windows, shifted detail
+    outputs, periodic wrap at the image border, parent copies for the in-place swpt / sdwt layouts) at depths 0 .. 2"""
     wt = wx.wavelet(name)
     x = np.random.default_rng(nr + nc + L).standard_normal((2, nc, nr)).astype(dt)
     xd = dev(x, cuda)
