@@ -320,7 +320,9 @@ __global__ void __launch_bounds__(kThreads) copy_k(View<T> dst, View<const T> sr
         case 10: { constexpr int FF = 10; CALL; } break; case 11: { constexpr int FF = 11; CALL; } break;                 \
         case 12: { constexpr int FF = 12; CALL; } break; case 15: { constexpr int FF = 15; CALL; } break;                 \
         case 16: { constexpr int FF = 16; CALL; } break; case 23: { constexpr int FF = 23; CALL; } break;                 \
-        case 31: { constexpr int FF = 31; CALL; } break;                                                                  \
+        case 31: { constexpr int FF = 31; CALL; } break; case 14: { constexpr int FF = 14; CALL; } break;                 \
+        case 18: { constexpr int FF = 18; CALL; } break; case 20: { constexpr int FF = 20; CALL; } break;                 \
+        case 24: { constexpr int FF = 24; CALL; } break;                                                                  \
         default: { constexpr int FF = 0; CALL; } break;                                                                   \
     }
 
