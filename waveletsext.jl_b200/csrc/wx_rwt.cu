@@ -16,6 +16,7 @@ template <typename T>
 int wx_rdwt1d_fused(int ac, T *xw, const T *x, long n, int L, long N, const Taps<T> &t, cudaStream_t s, int *done);
 template <typename T> int wx_iac_tree_sum(T *x, const T *xw, long n, long ncols, long c0, int L, long N, cudaStream_t s);
 template <typename T> int wx_iac_chain_sum(T *x, const T *xw, long n, int L, long N, cudaStream_t s);
+template <typename T> int wx_isdwt_shift_chain(T *x, const T *xw, long n, int L, long N, const long *sd, const Taps<T> &t, cudaStream_t s, bool *handled);
 // fused 2-D a-trous step (wx_rwt2d.cu)
 template <typename T>
 int wx_rdwt2d_fused(int ac, T *w1, long wns, long wis, long wq, const T *v, long vns, long vis, long m, long n, long nodes, long Nc, int d,
@@ -240,6 +241,11 @@ int irwt_1d(int imode, int mode, T *x, const T *xw, long n, long ncols, int L, l
         int dhi = 0;                                         // levels d < dhi run in the fused chain kernel (average based only)
         if (imode == 0) { rc = wx_irdwt_chain_depth<T>(x, xw, n, L, N, t, &dhi); if (rc) return rc; }
         if (dhi == L) return wx_irdwt_chain_run<T>(x, xw, n, L, dhi, N, t, s);
+        if (imode == 1) {                                    // shift based: the whole chain in one launch when a signal fits shared memory
+            bool handled = false;
+            rc = wx_isdwt_shift_chain<T>(x, xw, n, L, N, sd.data(), t, s, &handled);
+            if (rc || handled) return rc;
+        }
         T *tmp; rc = wx_scratch(&tmp, (size_t)n * N, s); if (rc) return rc;
         rc = wx_launch_copy<T>(View<T>{x, 1, n, 0, 0}, View<const T>{xw, 1, str, 0, 0}, n, Batch{N, 1, 1, false}, s);
         for (int d = L - 1; d >= dhi && !rc; --d) {

@@ -252,6 +252,48 @@ __global__ void __launch_bounds__(kThreads) isdwt_shift_fast_k(View<T> v, View<c
     pv[(long)j * v.es] = acc;
 }
 
+// isdwt!(xw, wt, sm) SWT.jl:270-282 as ONE launch: a CTA keeps the running reconstruction of one signal in shared memory (ping-pong) and
+// walks the levels d = L-1 .. 0; level d writes the sv(d) coset from the sw(d) = sv(d+1) coset of the previous level and of detail column
+// L-d (read straight from the table), so nothing off those cosets is ever needed.  Replaces L copies of x plus L step launches.
+struct WxShiftList { int s[34]; };
+template <typename T, int FF>
+__global__ void __launch_bounds__(kThreads) isdwt_shift_chain_k(T *__restrict__ x, const T *__restrict__ xw, int n, int L, WxShiftList sl, Taps<T> tp)
+{
+    constexpr int F = FF > 0 ? FF : 2, R = F / 2;
+    extern __shared__ __align__(16) unsigned char wx_chain_smem[];
+    T *cur = reinterpret_cast<T *>(wx_chain_smem), *nxt = cur + n;
+    const long k = blockIdx.x;
+    const T *col = xw + k * (long)(L + 1) * n;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < n; i += kThreads) cur[i] = col[i];
+    __syncthreads();
+    for (int d = L - 1; d >= 0; --d) {
+        const int D = 1 << d, sc = 2 * D, sv = sl.s[d], sw = sl.s[d + 1];
+        const int cnt = (n - 1 - sv) / D + 1;
+        const T *det = col + (long)(L - d) * n;
+        for (int t0 = tid; t0 < cnt; t0 += kThreads) {
+            const int t = t0 + 1, m = sv + 1 + t0 * D;
+            int j = ((sw == sv) ? m - D - 1 : m - 1) % n; if (j < 0) j += n;
+            const bool odd = (t & 1) != 0;
+            int k1 = ((t - 1) >> 1) * sc + sw, k2 = k1;
+            T gr = odd ? tp.g[F - 1] : tp.g[F - 2], hr = odd ? tp.h[1] : tp.h[0];
+            T acc = fma(gr, cur[k1], hr * det[k2]);
+#pragma unroll
+            for (int r = 1; r < R; ++r) {
+                k1 -= sc; if (k1 < 0) k1 += n;
+                k2 += sc; if (k2 >= n) k2 -= n;
+                gr = odd ? tp.g[F - 1 - 2 * r] : tp.g[F - 2 - 2 * r];
+                hr = odd ? tp.h[2 * r + 1] : tp.h[2 * r];
+                acc += fma(gr, cur[k1], hr * det[k2]);
+            }
+            nxt[j] = acc;
+        }
+        __syncthreads();
+        T *tsw = cur; cur = nxt; nxt = tsw;
+    }
+    for (int i = tid; i < n; i += kThreads) x[k * n + i] = cur[i];
+}
+
 // a10 isdwt_step! average based: one thread per output position (requires n % 2^(d+1) == 0)
 template <typename T, int FF>
 __global__ void __launch_bounds__(kThreads) isdwt_avg_k(View<T> v, View<const T> w1, View<const T> w2, long n, int d, Geo geo, Taps<T> tp)
@@ -412,6 +454,39 @@ int wx_launch_isdwt_avg(View<T> v, View<const T> w1, View<const T> w2, long n, i
     WX_LAUNCHED();
     return WX_OK;
 }
+
+namespace {
+template <typename T, int FF>
+int shift_chain_launch(T *x, const T *xw, long n, int L, long N, const WxShiftList &sl, size_t smem, const Taps<T> &t, cudaStream_t s)
+{
+    auto kern = isdwt_shift_chain_k<T, FF>;
+    WX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)N, kThreads, smem, s>>>(x, xw, (int)n, L, sl, t);
+    return WX_OK;
+}
+}  // namespace
+
+// the whole shift-based isdwt! chain in one launch (see isdwt_shift_chain_k); *handled = false: shape not covered, nothing launched
+template <typename T>
+int wx_isdwt_shift_chain(T *x, const T *xw, long n, int L, long N, const long *sd, const Taps<T> &t, cudaStream_t s, bool *handled)
+{
+    *handled = false;
+    static const bool off = getenv("WX_B200_NO_SHIFT_CHAIN") != nullptr;            // A-B measurements
+    WxDev dv; int rc = wx_devinfo(dv); if (rc) return rc;
+    bool known = false;
+    WX_DISPATCH_F(t.F, (known = FF > 0 && FF % 2 == 0))
+    const size_t smem = (size_t)2 * n * sizeof(T);
+    if (off || !known || L < 1 || L > 32 || N < 1 || N >= (1L << 31) || n >= (1L << 28) || smem > dv.smem_optin || n % (1L << L) != 0) return WX_OK;
+    WxShiftList sl;
+    for (int d = 0; d <= L; ++d) sl.s[d] = (int)sd[d];
+    WX_DISPATCH_F(t.F, (rc = shift_chain_launch<T, FF>(x, xw, n, L, N, sl, smem, t, s)))
+    if (rc) return rc;
+    WX_LAUNCHED();
+    *handled = true;
+    return WX_OK;
+}
+template int wx_isdwt_shift_chain<double>(double *, const double *, long, int, long, const long *, const Taps<double> &, cudaStream_t, bool *);
+template int wx_isdwt_shift_chain<float>(float *, const float *, long, int, long, const long *, const Taps<float> &, cudaStream_t, bool *);
 
 template <typename T>
 int wx_launch_iacdwt_step(View<T> v, View<const T> w1, View<const T> w2, long n, Batch b, cudaStream_t s)
