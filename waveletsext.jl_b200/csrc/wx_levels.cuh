@@ -1,6 +1,6 @@
 // wx_levels.cuh -- one decomposition / reconstruction level of every node of a signal staged in shared memory
 // (16-byte-chunk XOR swizzle, see wx_common.cuh).  Shared by the fused wpd kernel (wx_wpd1d.cu) and the fused
-// tree kernels (wx_tree1d.cu).
+// tree kernels (wx_tree1d.inl).
 //   forward: dwt_step!  dwt/dwt_one_level.jl:79-107      inverse: idwt_step!  dwt/dwt_one_level.jl:192-223
 // TREE = true: `tm[j]` (j < ntm) says whether node j of this depth is split; other nodes are copied through.
 #pragma once

@@ -1,4 +1,5 @@
-// wx_tree1d.cu -- fused 1-D wavelet packet transforms by tree: wpt / iwpt (Wavelets.jl wpt!/iwpt!, call sites
+// wx_tree1d.inl (compiled once per element type by wx_tree1d_f64.cu / wx_tree1d_f32.cu: the translation unit is the longest of the
+// build) -- fused 1-D wavelet packet transforms by tree: wpt / iwpt (Wavelets.jl wpt!/iwpt!, call sites
 // dwt/dwt_all.jl:162,221 -> wptall / iwptall) and iwpd (DWT.jl:337-351 = getbasiscoef + iwpt!), every level in ONE launch.
 //
 // A persistent CTA stages one signal (or one depth-d0 node of a signal too long for shared memory) in shared memory,
@@ -183,5 +184,4 @@ int wx_tree1d_fused(bool inverse, bool full, T *y, const T *x, long n, long N, i
     template int wx_tree1d_fused_depth<T>(const T *, const T *, long, int, int);                                                            \
     template int wx_tree1d_fused<T>(bool, bool, T *, const T *, long, long, int, int, const unsigned char *, long, const unsigned char *, \
                                     int, int, const Taps<T> &, cudaStream_t);
-WX_TR_INST(double)
-WX_TR_INST(float)
+WX_TR_INST(WX_TR_TYPE)

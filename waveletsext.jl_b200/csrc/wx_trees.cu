@@ -9,7 +9,7 @@
 #include <vector>
 #include <cstdlib>
 
-// fused all-levels-in-one-launch kernels (wx_tree1d.cu)
+// fused all-levels-in-one-launch kernels (wx_tree1d.inl, one translation unit per element type)
 template <typename T> int wx_tree1d_fused_depth(const T *y, const T *x, long n, int nlev, int F);
 template <typename T>
 int wx_tree1d_fused(bool inverse, bool full, T *y, const T *x, long n, long N, int d0, int nlev, const unsigned char *dtree, long ntree,
