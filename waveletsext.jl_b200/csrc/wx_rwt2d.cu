@@ -13,6 +13,8 @@
 #include "wx_steps.cuh"
 #include "wx_2d.cuh"
 #include <cstdlib>
+#include <mutex>
+#include <vector>
 
 namespace {
 
@@ -184,6 +186,15 @@ int launch_rdwt2d(T *w1, long wns, long wis, long wq, const T *v, long vns, long
     // tile (tr rows dividing m, tc coset columns dividing nc) with the least shared-memory traffic per output -- patch loads plus the
     // column pass over the column halo -- among those that keep three CTAs per SM; larger shared-memory budgets only if none fits
     int tr = 0, tc = 0; long PR = 0, PC = 0; size_t smem = 0;
+    // the search walks up to 16 K candidates: remember the answer per (shape, depth) -- one entry per template instantiation
+    struct Choice { long m, n, D; int tr, tc; long PR, PC; size_t smem; };
+    static std::mutex mtx;
+    static std::vector<Choice> cache;
+    {
+        std::lock_guard<std::mutex> lk(mtx);
+        for (const Choice &c : cache) if (c.m == m && c.n == n && c.D == D) { tr = c.tr; tc = c.tc; PR = c.PR; PC = c.PC; smem = c.smem; break; }
+    }
+    if (tr == 0)
     for (size_t budget : {(size_t)72 << 10, (size_t)110 << 10, dv.smem_optin}) {
         double best = 0;
         for (long a = 1; a <= 256 && a <= m; ++a) {
@@ -203,6 +214,12 @@ int launch_rdwt2d(T *w1, long wns, long wis, long wq, const T *v, long vns, long
         if (tr) break;
     }
     if (tr == 0) return WX_OK;
+    {
+        std::lock_guard<std::mutex> lk(mtx);
+        bool have = false;
+        for (const Choice &c : cache) if (c.m == m && c.n == n && c.D == D) have = true;
+        if (!have && cache.size() < 256) cache.push_back(Choice{m, n, D, tr, tc, PR, PC, smem});
+    }
     const long gy = (m / tr) * (nc / tc) * D, gx = nodes * Nc;
     if (gx >= (1L << 31) || gy > 65535) return WX_OK;
     auto kern = rdwt2d_tile_k<T, F, AC>;
