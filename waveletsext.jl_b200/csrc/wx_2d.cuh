@@ -31,6 +31,14 @@ __device__ __forceinline__ void cp_async_pair(T *smem_dst, const T *gsrc)
     if (sizeof(T) == 8) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gsrc) : "memory");
     else                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gsrc) : "memory");
 }
+// one element per asynchronous copy (8 / 4 bytes): for patches whose rows are not pair aligned
+template <typename T>
+__device__ __forceinline__ void cp_async_elem(T *smem_dst, const T *gsrc)
+{
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    if (sizeof(T) == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gsrc) : "memory");
+    else                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(gsrc) : "memory");
+}
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); }
 
 // division of a 32-bit index by a launch constant (host-built): shift for powers of two, else round-up multiply-high

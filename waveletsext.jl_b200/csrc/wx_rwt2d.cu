@@ -76,8 +76,9 @@ __global__ void __launch_bounds__(kT2, 3) rdwt2d_tile_k(T *__restrict__ w1, long
         for (Walk2 w(tid, PR); w.hi < PC; w.next()) {
             int rr = rs + w.lo; while (rr >= m) rr -= m;
             int cc = cs + w.hi; while (cc >= nc) cc -= nc;
-            P[w.hi * LDP + w.lo] = par[(long)(gam + cc * D) * m + rr];
+            cp_async_elem<T>(P + w.hi * LDP + w.lo, par + (long)(gam + cc * D) * m + rr);      // asynchronous: every copy of the thread in flight
         }
+        cp_async_wait_all();
     }
     __syncthreads();
     // ---- column pass (along the rows): every patch column, tr output rows ----
