@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(kThreads) isdwt_shift_chain_k(T *__restrict__ 
     const long k = blockIdx.x;
     const T *col = xw + k * (long)(L + 1) * n;
     const int tid = threadIdx.x;
-    for (int i = tid; i < n; i += kThreads) cur[i] = col[i];
+    for (int i = tid; i < n; i += kThreads) cur[i] = col[i];      // (cp.async element copies measured slower here: 0.15 -> 0.19 ms)
     __syncthreads();
     for (int d = L - 1; d >= 0; --d) {
         const int D = 1 << d, sc = 2 * D, sv = sl.s[d], sw = sl.s[d + 1];

@@ -16,6 +16,12 @@
 
 namespace {
 
+__device__ __forceinline__ void wx_cp_async16(void *smem_dst, const void *gsrc)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void wx_cp_async_wait() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); }
+
 // item = (signal k, node j0 of depth d0).  Levels d0..nlev-1 of that node are processed (forward: top down, inverse:
 // bottom up).  depth != nullptr: x is a packet table (n, Kx, N) and position e is read from level depth[e].
 template <typename T, int F, bool INV, bool TREE, int KM>
@@ -37,16 +43,17 @@ __global__ void __launch_bounds__(WX_TREE_MAXT) tree1d_fused_k(T *__restrict__ y
         const long j0 = item & ((1L << d0) - 1);
         const long pos0 = j0 * n0;
         // ---- stage in -------------------------------------------------------------------------------
-        if (depth == nullptr) {
+        if (depth == nullptr) {                       // 16-byte asynchronous copies: every chunk of the thread in flight, no register staging
             const T *src = x + k * n + pos0;
-            for (int c = tid; c < n0 / V; c += nthreads)
-                *reinterpret_cast<VT *>(buf0 + wx_swz_chunk(c) * V) = wx_ldg_stream<T>(src + c * V);
+            for (int c = tid; c < n0 / V; c += nthreads) wx_cp_async16(buf0 + wx_swz_chunk(c) * V, src + c * V);
+            wx_cp_async_wait();
         } else if (vecgather) {                       // every leaf is at least one 16-byte chunk long
             const T *src = x + k * (long)Kx * n + pos0;
             for (int c = tid; c < n0 / V; c += nthreads) {
                 const long lv = depth[pos0 + (long)c * V];
-                *reinterpret_cast<VT *>(buf0 + wx_swz_chunk(c) * V) = wx_ldg_stream<T>(src + lv * n + c * V);
+                wx_cp_async16(buf0 + wx_swz_chunk(c) * V, src + lv * n + c * V);
             }
+            wx_cp_async_wait();
         } else {
             const T *src = x + k * (long)Kx * n + pos0;
             for (int e = tid; e < n0; e += nthreads) buf0[wx_swz_elem<T>(e)] = src[(long)depth[pos0 + e] * n + e];
